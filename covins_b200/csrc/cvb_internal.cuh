@@ -1,0 +1,101 @@
+// cvb_internal.cuh — ctx, error plumbing and small device helpers shared by all translation units of
+// libcovins_b200.so.  Not part of the public boundary (that is include/covins_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/covins_b200.h"
+
+struct cvb_buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct cvb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::string err;
+  // grow-only device workspaces (named slots so independent stages never alias)
+  cvb_buf ws[16];
+  // pinned host staging
+  void* h_pin = nullptr;
+  size_t h_pin_cap = 0;
+  void* ba = nullptr;  // BA state (owned by ba_*.cu)
+};
+
+enum { WS_Q = 0, WS_T, WS_SEG, WS_OUT0, WS_OUT1, WS_OUT2, WS_PART_I, WS_PART_D, WS_LIST_I, WS_LIST_D, WS_SKIPA,
+       WS_SKIPB, WS_TMP0, WS_TMP1, WS_FLAG, WS_MISC };
+
+int cvb_fail(cvb_ctx* ctx, int code, const char* fmt, ...);
+void* cvb_ws(cvb_ctx* ctx, int slot, size_t bytes);          // returns nullptr on failure (ctx->err set)
+void* cvb_pinned(cvb_ctx* ctx, size_t bytes);
+
+#define CVB_CUDA(ctx, call)                                                                         \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return cvb_fail((ctx), CVB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),  \
+                      __FILE__, __LINE__);                                                          \
+  } while (0)
+
+#define CVB_CHECK_LAUNCH(ctx)                                                                       \
+  do {                                                                                              \
+    (ctx)->launches++;                                                                              \
+    cudaError_t e_ = cudaGetLastError();                                                            \
+    if (e_ != cudaSuccess)                                                                          \
+      return cvb_fail((ctx), CVB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                      \
+                      cudaGetErrorString(e_), __FILE__, __LINE__);                                  \
+  } while (0)
+
+#define CVB_REQUIRE(ctx, cond, ...)                                      \
+  do {                                                                   \
+    if (!(cond)) return cvb_fail((ctx), CVB_ERR_INVALID, __VA_ARGS__);   \
+  } while (0)
+
+static inline cudaStream_t cvb_stream(cvb_ctx* ctx, void* s) { return s ? (cudaStream_t)s : ctx->stream; }
+
+// ---------------------------------------------------------------------------------------------
+// Device helpers: mbarrier + 1-D bulk TMA (cp.async.bulk → SASS UBLKCP), used to stage descriptor
+// tiles into shared memory.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t cvb_smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void cvb_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cvb_smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void cvb_fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void cvb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cvb_smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cvb_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(cvb_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global → shared bulk copy (bytes % 16 == 0, both addresses 16-B aligned), completion on `bar`.
+__device__ __forceinline__ void cvb_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          cvb_smem_addr(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(cvb_smem_addr(bar))
+      : "memory");
+}
+#endif

@@ -1,0 +1,180 @@
+"""Host-side mirror of the reference's matching step on top of the C-ABI.
+
+Names follow the reference: `knn_match` is cv::DescriptorMatcher::knnMatch as called in
+PlaceRecognitionG::ComputeSE3 (covins_backend/src/covins_backend/placerec_gen_be.cpp:82-100),
+`match_candidates` is that call fused with the distance+ratio filter of :102-114 for a list of
+candidate keyframes, `landmark_match` is DenseMatcher<LandmarkMatchingAlgorithm> as called in
+PlaceRecognition::ComputeSE3 (placerec_be.cpp:85-90).
+
+numpy arrays go through the host-buffer entry points (copies included); torch CUDA tensors go
+through the `_dev` entry points on the current torch stream (no copies, no sync).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Context, lib
+
+
+def _np(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def _seg(seg_ptr, n_rows):
+    if seg_ptr is None:
+        seg_ptr = np.array([0, n_rows], np.int32)
+    return _np(seg_ptr, np.int32)
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr")
+
+
+def _torch_stream():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------------------------
+# Hamming k-NN (ORB)
+# ------------------------------------------------------------------------------------------------
+def knn_match_hamming(ctx: Context, q, t, seg_ptr=None, k: int = 2):
+    """→ (idx [n_seg, nq, k] i32 segment-local trainIdx, dist [n_seg, nq, k] i32)."""
+    if _is_torch(q):
+        import torch
+        h_seg = _seg(seg_ptr[1] if isinstance(seg_ptr, tuple) else seg_ptr, t.shape[0])
+        d_seg = seg_ptr[0] if isinstance(seg_ptr, tuple) else torch.from_numpy(h_seg).to(q.device)
+        ns, nq = len(h_seg) - 1, q.shape[0]
+        idx = torch.empty((ns, nq, k), dtype=torch.int32, device=q.device)
+        dist = torch.empty((ns, nq, k), dtype=torch.int32, device=q.device)
+        ctx.check(lib().cvb_knn_hamming_batch_dev(ctx.handle, _ptr(q), nq, _ptr(t), _ptr(d_seg), _ptr(h_seg), ns, k,
+                                                  _ptr(idx), _ptr(dist), _torch_stream()))
+        return idx, dist
+    q = _np(q, np.uint8); t = _np(t, np.uint8)
+    assert q.ndim == 2 and q.shape[1] == 32 and t.shape[1] == 32, "ORB descriptors are 32-byte rows"
+    seg = _seg(seg_ptr, len(t))
+    ns, nq = len(seg) - 1, len(q)
+    idx = np.empty((ns, nq, k), np.int32); dist = np.empty((ns, nq, k), np.int32)
+    ctx.check(lib().cvb_knn_hamming_batch(ctx.handle, _ptr(q), nq, _ptr(t), _ptr(seg), ns, k, _ptr(idx), _ptr(dist)))
+    return idx, dist
+
+
+def match_candidates_hamming(ctx: Context, q, t, seg_ptr=None, thr: float = 40.0, ratio: float = 0.8):
+    """knnMatch(k=2) + distance/ratio filter (placerec_gen_be.cpp:99-114) per candidate segment.
+    → (match_train [n_seg, nq] i32 (-1 = rejected), match_dist [n_seg, nq] f32, n_matches [n_seg] i32).
+    Defaults: img_match_thres 40.0, ratio_thres 0.8 (config/config_backend.yaml:38-39)."""
+    if _is_torch(q):
+        import torch
+        h_seg = _seg(seg_ptr[1] if isinstance(seg_ptr, tuple) else seg_ptr, t.shape[0])
+        d_seg = seg_ptr[0] if isinstance(seg_ptr, tuple) else torch.from_numpy(h_seg).to(q.device)
+        ns, nq = len(h_seg) - 1, q.shape[0]
+        mt = torch.empty((ns, nq), dtype=torch.int32, device=q.device)
+        md = torch.empty((ns, nq), dtype=torch.float32, device=q.device)
+        nm = torch.empty((ns,), dtype=torch.int32, device=q.device)
+        ctx.check(lib().cvb_match_hamming_batch_dev(ctx.handle, _ptr(q), nq, _ptr(t), _ptr(d_seg), _ptr(h_seg), ns,
+                                                    thr, ratio, _ptr(mt), _ptr(md), _ptr(nm), _torch_stream()))
+        return mt, md, nm
+    q = _np(q, np.uint8); t = _np(t, np.uint8)
+    seg = _seg(seg_ptr, len(t))
+    ns, nq = len(seg) - 1, len(q)
+    mt = np.empty((ns, nq), np.int32); md = np.empty((ns, nq), np.float32); nm = np.empty(ns, np.int32)
+    ctx.check(lib().cvb_match_hamming_batch(ctx.handle, _ptr(q), nq, _ptr(t), _ptr(seg), ns, thr, ratio, _ptr(mt),
+                                            _ptr(md), _ptr(nm)))
+    return mt, md, nm
+
+
+# ------------------------------------------------------------------------------------------------
+# L2 k-NN (SIFT)
+# ------------------------------------------------------------------------------------------------
+def knn_match_l2(ctx: Context, q, t, seg_ptr=None, k: int = 2):
+    """float32 rows (host) → (idx [n_seg,nq,k] i32, dist [n_seg,nq,k] f32 = sqrt(sum (a-b)^2))."""
+    if _is_torch(q):
+        import torch
+        assert q.dtype == torch.uint8, "device path takes the HBM-resident u8 layout (see quantize_u8)"
+        h_seg = _seg(seg_ptr[1] if isinstance(seg_ptr, tuple) else seg_ptr, t.shape[0])
+        d_seg = seg_ptr[0] if isinstance(seg_ptr, tuple) else torch.from_numpy(h_seg).to(q.device)
+        ns, nq = len(h_seg) - 1, q.shape[0]
+        idx = torch.empty((ns, nq, k), dtype=torch.int32, device=q.device)
+        dist = torch.empty((ns, nq, k), dtype=torch.float32, device=q.device)
+        ctx.check(lib().cvb_knn_l2_u8_batch_dev(ctx.handle, _ptr(q), nq, _ptr(t), _ptr(d_seg), _ptr(h_seg), ns,
+                                                q.shape[1], k, _ptr(idx), _ptr(dist), _torch_stream()))
+        return idx, dist
+    q = _np(q, np.float32); t = _np(t, np.float32)
+    seg = _seg(seg_ptr, len(t))
+    ns, nq = len(seg) - 1, len(q)
+    idx = np.empty((ns, nq, k), np.int32); dist = np.empty((ns, nq, k), np.float32)
+    ctx.check(lib().cvb_knn_l2_batch(ctx.handle, _ptr(q), nq, _ptr(t), _ptr(seg), ns, q.shape[1], k, _ptr(idx),
+                                     _ptr(dist)))
+    return idx, dist
+
+
+def match_candidates_l2(ctx: Context, q, t, seg_ptr=None, thr: float = 500.0, ratio: float = 0.8):
+    """SIFT branch of placerec_gen_be.cpp:86-114 (img_match_thres 500 for SIFT, config_backend.yaml:38)."""
+    q = _np(q, np.float32); t = _np(t, np.float32)
+    seg = _seg(seg_ptr, len(t))
+    ns, nq = len(seg) - 1, len(q)
+    mt = np.empty((ns, nq), np.int32); md = np.empty((ns, nq), np.float32); nm = np.empty(ns, np.int32)
+    ctx.check(lib().cvb_match_l2_batch(ctx.handle, _ptr(q), nq, _ptr(t), _ptr(seg), ns, q.shape[1], thr, ratio,
+                                       _ptr(mt), _ptr(md), _ptr(nm)))
+    return mt, md, nm
+
+
+def quantize_u8(ctx: Context, x):
+    """torch f32 CUDA tensor → (u8 tensor, bad flag tensor): the exact HBM-resident SIFT layout."""
+    import torch
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=x.device)
+    ctx.check(lib().cvb_quantize_u8_dev(ctx.handle, _ptr(x), x.numel(), _ptr(out), _ptr(bad), _torch_stream()))
+    return out, bad
+
+
+# ------------------------------------------------------------------------------------------------
+# DenseMatcher<LandmarkMatchingAlgorithm> (COVINS mode)
+# ------------------------------------------------------------------------------------------------
+def landmark_match(ctx: Context, A, skipA, B, skipB, seg_ptr=None, thr: float = 50.0, num_best: int = 4):
+    """→ list over candidate segments of (idxA, idxB, dist) arrays ordered by idxB — the `Matches`
+    vector of placerec_be.cpp:91 — for numpy inputs; for torch inputs the raw
+    (outA, outB, outD, n_out) device tensors (slice [seg_ptr[s], seg_ptr[s]+n_out[s]))."""
+    if _is_torch(A):
+        import torch
+        h_seg = _seg(seg_ptr[1] if isinstance(seg_ptr, tuple) else seg_ptr, B.shape[0])
+        d_seg = seg_ptr[0] if isinstance(seg_ptr, tuple) else torch.from_numpy(h_seg).to(A.device)
+        ns, rows = len(h_seg) - 1, B.shape[0]
+        oA = torch.empty(rows, dtype=torch.int32, device=A.device)
+        oB = torch.empty(rows, dtype=torch.int32, device=A.device)
+        oD = torch.empty(rows, dtype=torch.float32, device=A.device)
+        n = torch.empty(ns, dtype=torch.int32, device=A.device)
+        ctx.check(lib().cvb_landmark_match_batch_dev(ctx.handle, _ptr(A), _ptr(skipA), A.shape[0], _ptr(B), _ptr(skipB),
+                                                     _ptr(d_seg), _ptr(h_seg), ns, thr, num_best, _ptr(oA), _ptr(oB),
+                                                     _ptr(oD), _ptr(n), _torch_stream()))
+        return oA, oB, oD, n
+    A = _np(A, np.uint8); B = _np(B, np.uint8)
+    sA = _np(skipA, np.uint8) if skipA is not None else None
+    sB = _np(skipB, np.uint8) if skipB is not None else None
+    seg = _seg(seg_ptr, len(B))
+    ns, rows = len(seg) - 1, len(B)
+    oA = np.empty(max(rows, 1), np.int32); oB = np.empty(max(rows, 1), np.int32); oD = np.empty(max(rows, 1), np.float32)
+    n = np.empty(ns, np.int32)
+    ctx.check(lib().cvb_landmark_match_batch(ctx.handle, _ptr(A), _ptr(sA), len(A), _ptr(B), _ptr(sB), _ptr(seg), ns,
+                                             thr, num_best, _ptr(oA), _ptr(oB), _ptr(oD), _ptr(n)))
+    out = []
+    for s in range(ns):
+        a, b = seg[s], seg[s] + n[s]
+        out.append((oA[a:b].copy(), oB[a:b].copy(), oD[a:b].copy()))
+    return out
+
+
+def microbench_popc(ctx: Context, iters: int = 20000) -> float:
+    v = C.c_double()
+    ctx.check(lib().cvb_microbench_popc(ctx.handle, iters, C.byref(v)))
+    return v.value

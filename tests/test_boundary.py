@@ -1,0 +1,61 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/covins_b200.h declares; the
+product package never touches oracle/; without a GPU the product fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    syms = []
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        txt = open(os.path.join(ROOT, "include", h)).read()
+        syms += re.findall(r"CVB_API\s+[\w\s\*]+?\b(cvb_\w+)\s*\(", txt)
+    return sorted(set(syms))
+
+
+def test_library_exports_every_declared_symbol():
+    import covins_b200
+    if not os.path.exists(covins_b200.LIB_PATH):
+        covins_b200.build()
+    lib = ctypes.CDLL(covins_b200.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.cvb_version() >= 100
+
+
+def test_python_signatures_cover_the_header():
+    from covins_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "covins_b200")
+    bad = []
+    for dp, _, fs in os.walk(pkg):
+        if os.sep + "build" in dp:
+            continue
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", ".c")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"(from|import)\s+oracle|oracle/|libcovins_oracle|/root/reference", txt):
+                    # doc-strings may *mention* the rule; flag only code-like uses
+                    for line in txt.splitlines():
+                        if re.search(r"^\s*(from|import)\s+oracle|#include\s+\".*oracle|libcovins_oracle|/root/reference",
+                                     line):
+                            bad.append((f, line.strip()))
+    assert not bad, bad
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    import covins_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(covins_b200.CvbError):
+        covins_b200.Context(0)

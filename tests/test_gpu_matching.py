@@ -1,0 +1,195 @@
+"""GPU parity tests of the matching half, all through the C-ABI (covins_b200.matching → libcovins_b200.so):
+bit-exact against (1) the committed cv2.BFMatcher golden vectors, (2) the CPU oracle on seeded inputs,
+(3) size-independent properties at BASELINE.json's full sizes."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_cases
+from covins_b200 import matching as M
+from covins_b200 import synth
+from oracle import knn as ora
+
+pytestmark = pytest.mark.gpu
+
+
+# ---------------------------------------------------------------------------------------------- golden
+def test_hamming_knn_matches_cv2_golden(ctx, golden_dir):
+    g, names = golden_cases(os.path.join(golden_dir, "knn_hamming.npz"))
+    for n in names:
+        idx, dist = M.knn_match_hamming(ctx, g[n + "/q"], g[n + "/t"], k=2)
+        assert np.array_equal(idx[0], g[n + "/idx"]), n
+        d = np.where(idx[0] >= 0, dist[0].astype(np.float32), np.inf)
+        assert np.array_equal(d, g[n + "/dist"]), n
+        mt, md, nm = M.match_candidates_hamming(ctx, g[n + "/q"], g[n + "/t"], thr=40.0, ratio=0.8)
+        assert np.array_equal(mt[0], g[n + "/match"]), n
+        assert nm[0] == (g[n + "/match"] >= 0).sum()
+
+
+def test_l2_knn_matches_cv2_golden(ctx, golden_dir):
+    g, names = golden_cases(os.path.join(golden_dir, "knn_l2.npz"))
+    for n in names:
+        q = g[n + "/q"].astype(np.float32); t = g[n + "/t"].astype(np.float32)
+        idx, dist = M.knn_match_l2(ctx, q, t, k=2)
+        assert np.array_equal(idx[0], g[n + "/idx"]), n
+        d = np.where(idx[0] >= 0, dist[0], np.inf)
+        assert np.array_equal(d, g[n + "/dist"]), n  # bit-exact float distances
+        mt, md, nm = M.match_candidates_l2(ctx, q, t, thr=500.0, ratio=0.8)
+        assert np.array_equal(mt[0], g[n + "/match"]), n
+
+
+# ---------------------------------------------------------------------------------------------- oracle
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_hamming_batch_ragged_vs_oracle(ctx, k):
+    rng = np.random.default_rng(10 + k)
+    desc, _ = synth.orb_keyframes(seed=5, n_kf=9, n_feat=700, n_lm=1500, window=1500)
+    q = desc[0][:613]
+    lens = [700, 0, 1, 2, 3, 257, 512, 699]
+    t = np.concatenate([desc[i + 1][:l] for i, l in enumerate(lens)])
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    idx, dist = M.knn_match_hamming(ctx, q, t, seg, k=k)
+    ri, rd = ora.knn_hamming_batch(q, t, seg, k=k)
+    assert np.array_equal(idx, ri) and np.array_equal(dist, rd)
+
+
+def test_hamming_split_path_vs_oracle(ctx):
+    """one long segment, few queries → row-split + merge path; heavy ties to stress the merge rule"""
+    rng = np.random.default_rng(42)
+    base = rng.integers(0, 256, (40, 32), dtype=np.uint8)
+    t = base[rng.integers(0, 40, 50_000)]
+    t ^= (rng.integers(0, 256, t.shape, dtype=np.uint8) & rng.integers(0, 256, t.shape, dtype=np.uint8)
+          & rng.integers(0, 256, t.shape, dtype=np.uint8) & rng.integers(0, 256, t.shape, dtype=np.uint8) & 3)
+    q = base[rng.integers(0, 40, 37)]
+    for k in (2, 4):
+        idx, dist = M.knn_match_hamming(ctx, q, t, None, k=k)
+        ri, rd = ora.knn_hamming(q, t, k=k)
+        assert np.array_equal(idx[0], ri) and np.array_equal(dist[0], rd)
+    mt, md, nm = M.match_candidates_hamming(ctx, q, t, None, 40.0, 0.8)
+    ri, rd = ora.knn_hamming(q, t, k=2)
+    rmt, rmd, rc = ora.ratio_filter(ri, rd.astype(np.float32), 40.0, 0.8)
+    assert np.array_equal(mt[0], rmt) and nm[0] == rc
+
+
+def test_fused_filter_vs_oracle(ctx):
+    desc, _ = synth.orb_keyframes(seed=7, n_kf=21, n_feat=500, n_lm=900, window=900)
+    q = desc[0]
+    t = desc[1:].reshape(-1, 32)
+    seg = synth.seg_ptr_uniform(20, 500)
+    mt, md, nm = M.match_candidates_hamming(ctx, q, t, seg, 40.0, 0.8)
+    ri, rd = ora.knn_hamming_batch(q, t, seg, k=2)
+    rmt, rmd, rc = ora.ratio_filter(ri, rd.astype(np.float32), 40.0, 0.8)
+    assert np.array_equal(mt, rmt) and np.array_equal(nm, rc)
+    assert np.array_equal(md[mt >= 0], rmd[rmt >= 0])
+    assert nm.max() > 25  # covisible neighbours clear placerec.matches_thres (config_backend.yaml:74)
+
+
+def test_l2_batch_and_split_vs_oracle(ctx):
+    s, _ = synth.sift_keyframes(seed=3, n_kf=7, n_feat=300, n_lm=500, window=500)
+    q = s[0][:211]
+    lens = [300, 0, 2, 129, 300, 77]
+    t = np.concatenate([s[i + 1][:l] for i, l in enumerate(lens)])
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    for k in (1, 2, 4):
+        idx, dist = M.knn_match_l2(ctx, q, t, seg, k=k)
+        ri, rd = ora.knn_l2_batch(q, t, seg, k=k)
+        rd = np.where(ri >= 0, rd, np.finfo(np.float32).max)
+        assert np.array_equal(idx, ri) and np.array_equal(dist, rd)
+    # long single segment with duplicated rows (ties in the sqrt domain) → split path
+    rng = np.random.default_rng(0)
+    tl = s.reshape(-1, 128)[rng.integers(0, 400, 20_000)]
+    idx, dist = M.knn_match_l2(ctx, q[:19], tl, None, k=2)
+    ri, rd = ora.knn_l2(q[:19], tl, k=2)
+    assert np.array_equal(idx[0], ri) and np.array_equal(dist[0], rd)
+
+
+def test_l2_rejects_non_integer_descriptors(ctx):
+    import covins_b200
+    q = np.full((4, 128), 0.5, np.float32); t = np.zeros((8, 128), np.float32)
+    with pytest.raises(covins_b200.CvbError):
+        M.knn_match_l2(ctx, q, t)
+    with pytest.raises(covins_b200.CvbError):
+        M.knn_match_l2(ctx, np.zeros((4, 64), np.float32), np.zeros((8, 64), np.float32))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_landmark_match_vs_oracle(ctx, seed):
+    desc, lm = synth.orb_keyframes(seed=20 + seed, n_kf=13, n_feat=600, n_lm=800, window=800)
+    A, skipA = desc[0], (lm[0] < 0).astype(np.uint8)
+    lens = [600, 0, 1, 333, 600, 600, 45, 600, 600, 600, 600, 599]
+    B = np.concatenate([desc[i + 1][:l] for i, l in enumerate(lens)])
+    skipB = np.concatenate([(lm[i + 1][:l] < 0) for i, l in enumerate(lens)]).astype(np.uint8)
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    out = M.landmark_match(ctx, A, skipA, B, skipB, seg, thr=50.0, num_best=4)
+    tot = 0
+    for s in range(len(lens)):
+        ra, rb, rd = ora.landmark_match(A, skipA, B[seg[s]:seg[s + 1]], skipB[seg[s]:seg[s + 1]], 50.0, 4)
+        a, b, d = out[s]
+        assert np.array_equal(a, ra) and np.array_equal(b, rb) and np.array_equal(d, rd), s
+        tot += len(ra)
+    assert tot > 100
+
+
+def test_landmark_match_ties_and_displacement_chains(ctx):
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (10, 32), dtype=np.uint8)
+
+    def mk(n):
+        d = base[rng.integers(0, 10, n)].copy()
+        return d ^ (rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8)
+                    & rng.integers(0, 256, (n, 32), dtype=np.uint8))
+    for nb in (1, 2, 4):
+        A, B = mk(200), mk(260)
+        skipA = (rng.random(200) < 0.2).astype(np.uint8); skipB = (rng.random(260) < 0.2).astype(np.uint8)
+        (a, b, d), = M.landmark_match(ctx, A, skipA, B, skipB, None, 50.0, nb)
+        ra, rb, rd = ora.landmark_match(A, skipA, B, skipB, 50.0, nb)
+        assert np.array_equal(a, ra) and np.array_equal(b, rb) and np.array_equal(d, rd)
+    # no skip masks at all
+    (a, b, d), = M.landmark_match(ctx, A, None, B, None, None, 50.0, 4)
+    ra, rb, rd = ora.landmark_match(A, None, B, None, 50.0, 4)
+    assert np.array_equal(a, ra) and np.array_equal(b, rb)
+
+
+# ---------------------------------------------------------------------------------------------- device path
+def test_device_path_equals_host_path(ctx):
+    import torch
+    desc, lm = synth.orb_keyframes(seed=9, n_kf=6, n_feat=400, n_lm=600, window=600)
+    q = desc[0]; t = desc[1:].reshape(-1, 32); seg = synth.seg_ptr_uniform(5, 400)
+    hi, hd = M.knn_match_hamming(ctx, q, t, seg, 2)
+    dq = torch.from_numpy(q).cuda(); dt = torch.from_numpy(t).cuda()
+    di, dd = M.knn_match_hamming(ctx, dq, dt, seg, 2)
+    torch.cuda.synchronize()
+    assert np.array_equal(di.cpu().numpy(), hi) and np.array_equal(dd.cpu().numpy(), hd)
+    mt, md, nm = M.match_candidates_hamming(ctx, dq, dt, seg)
+    hmt, hmd, hnm = M.match_candidates_hamming(ctx, q, t, seg)
+    torch.cuda.synchronize()
+    assert np.array_equal(mt.cpu().numpy(), hmt) and np.array_equal(nm.cpu().numpy(), hnm)
+
+
+# ---------------------------------------------------------------------------------------------- full size
+def test_full_size_properties_c3(ctx):
+    """BASELINE config 3 size: one 1000-feature query KF against 2000 candidate KFs (2 Gpair).
+    Properties: (a) the candidate that IS the query returns idx == own row, distance 0 for every row and
+    passes the ratio test wherever the row is unique; (b) permuting candidate order permutes the result;
+    (c) a sample of 16 candidates equals the oracle bit-for-bit."""
+    import torch
+    n_kf, nf = 2000, 1000
+    g = torch.Generator(device="cuda").manual_seed(1)
+    t = torch.randint(0, 256, (n_kf * nf, 32), dtype=torch.uint8, device="cuda", generator=g)
+    q = t[777 * nf:778 * nf].clone()
+    seg = synth.seg_ptr_uniform(n_kf, nf)
+    idx, dist = M.knn_match_hamming(ctx, q, t, seg, 2)
+    mt, md, nm = M.match_candidates_hamming(ctx, q, t, seg)
+    torch.cuda.synchronize()
+    own = idx[777, :, 0].cpu().numpy()
+    assert np.array_equal(own, np.arange(nf)) and int(dist[777, :, 0].max()) == 0
+    assert int(nm[777]) == nf and int(nm.sum()) == nf  # random codes: nothing else passes thr 40
+    perm = torch.randperm(n_kf, device="cuda", generator=g)
+    tp = t.view(n_kf, nf, 32)[perm].reshape(-1, 32).contiguous()
+    idx_p, dist_p = M.knn_match_hamming(ctx, q, tp, seg, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(idx_p, idx[perm]) and torch.equal(dist_p, dist[perm])
+    sample = [0, 1, 5, 100, 776, 777, 778, 999, 1000, 1234, 1500, 1776, 1900, 1997, 1998, 1999]
+    tn = t.view(n_kf, nf, 32)[sample].reshape(-1, 32).cpu().numpy()
+    ri, rd = ora.knn_hamming_batch(q.cpu().numpy(), tn, synth.seg_ptr_uniform(len(sample), nf), 2)
+    assert np.array_equal(idx[sample].cpu().numpy(), ri) and np.array_equal(dist[sample].cpu().numpy(), rd)
