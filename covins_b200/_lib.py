@@ -55,6 +55,16 @@ SIGNATURES = {
     "cvb_landmark_match_batch_dev": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_float,
                                                C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_microbench_popc": (C.c_int, [c_vp, C.c_int, c_f64p]),
+    "cvb_dense_cholesky_solve": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_f64p]),
+    "cvb_ba_create": (C.c_int, [c_vp, c_vp, c_vp, C.POINTER(c_vp)]),
+    "cvb_ba_set_allreduce": (C.c_int, [c_vp, c_vp, c_vp]),
+    "cvb_ba_restart": (C.c_int, [c_vp]),
+    "cvb_ba_iterate": (C.c_int, [c_vp, C.c_int, C.POINTER(C.c_int)]),
+    "cvb_ba_result_get": (C.c_int, [c_vp, c_vp, c_vp]),
+    "cvb_ba_reproj_norms": (C.c_int, [c_vp, c_vp, C.c_int]),
+    "cvb_ba_destroy": (C.c_int, [c_vp]),
+    "cvb_ba_solve": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "cvb_gba": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 

@@ -1,0 +1,1649 @@
+// ba_engine.cu — global bundle adjustment / pose-graph optimisation on the GPU (K4-K9).
+//
+// Replaces, behind the flat problem format of include/covins_b200.h, what the reference hands to Ceres in
+//   Optimization::GlobalBundleAdjustment   optimization_be.cpp:56-618   (ceres::Solve at :265 and :567)
+//   Optimization::PoseGraphOptimization    optimization_be.cpp:833-1086 (ceres::Solve at :1031)
+// i.e. cost-function evaluation (robopt_open), CauchyLoss + corrector, Jacobi scaling, the SPARSE_SCHUR linear
+// solve and the DOGLEG trust-region loop (Ceres 1.x defaults; assumptions in SURVEY.md Appendix A.7).
+//
+// One outer iteration =
+//   lin_obs / lin_imu / lin_edge   residuals + analytic Jacobians per factor, loss-corrected, Jacobi-scaled (K4-K6)
+//   lm_reduce, lm_damp_inv, obs_Y  per-landmark 3x3 blocks, their inverses, Y = W Hll^-1
+//   kf_visual, factor_gather       camera blocks of J^T J into the dense reduced system S, gradient
+//   cam_diag, schur                damping + S -= sum_l Y W^T over precomputed (block → observation pair) lists (K7)
+//   cvb_chol::factor / solve       dense FP64 tiled Cholesky on DMMA (K8), landmark back-substitution
+//   dogleg algebra + J*step        Cauchy point, interpolation, model decrease
+//   plus + residual-only pass      candidate state and its cost (K9)
+// Every accumulation is a gather in a fixed order (no floating-point atomics): results are bit-reproducible.
+//
+// HBM layout: per observation an 160-B record {r[2], Jp[12], Jl[6]} and a 288-B record {W[18], Y[18]} (AoS so the
+// per-keyframe and per-pair gathers read whole records), per landmark Hll/Hll^-1/b (15 doubles), S dense
+// row-major (n_c_pad^2 doubles, lower triangle), state double-buffered for accept/reject.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "ba_math.cuh"
+#include "cvb_internal.cuh"
+
+namespace cvb_chol {
+constexpr int T = 128;
+int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, cudaStream_t st);
+int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x, cudaStream_t st);
+}  // namespace cvb_chol
+
+namespace {
+
+using namespace bam;
+
+struct ObsLin {
+  double r[2], Jp[12], Jl[6];
+};
+struct ObsWY {
+  double W[18], Y[18];
+};
+
+constexpr int RED_BLOCKS = 512;   // fixed grid for reducing kernels → fixed summation order
+constexpr int RED_SLOTS = 8;
+
+template <typename T>
+struct DevArr {
+  T* p = nullptr;
+  size_t n = 0;
+  int alloc(size_t count) {
+    n = count;
+    if (count == 0) count = 1;
+    return cudaMalloc(&p, count * sizeof(T)) == cudaSuccess ? 0 : 1;
+  }
+  void free_() {
+    if (p) cudaFree(p);
+    p = nullptr;
+  }
+};
+
+struct Engine {
+  cvb_ctx* ctx = nullptr;
+  cudaStream_t st = nullptr;
+  // sizes
+  int K = 0, L_in = 0, n_obs = 0, n_imu = 0, n_edge = 0, per = 6, n_c = 0, n_c_pad = 0, n_vec = 0;
+  int visual_only = 1;
+  double a2_reproj = 1.0, a2_edge = 0.25, g = 9.81;
+  int rank = 0, world = 1;
+  // host-side maps
+  std::vector<int> lm_of_compact;        // compact landmark → original index
+  std::vector<int> obs_of_compact;       // compact observation → original index
+  std::vector<uint8_t> h_const;
+  // device state (double buffered)
+  DevArr<double> pose[2], sb[2], lm[2];
+  DevArr<uint8_t> pose_const;
+  DevArr<double> extr_kf, intr_kf, dist_kf;
+  DevArr<int> obs_kf, obs_lm, lm_ptr, kf_ptr, kf_obs;
+  DevArr<double> obs_uv, obs_sigma;
+  DevArr<ObsLin> lin;
+  DevArr<ObsWY> wy;
+  DevArr<double> Hll, HllInv, bl;
+  // imu
+  DevArr<ImuPre> pre;
+  DevArr<int> imu_i, imu_j;
+  DevArr<double> Jimu, rimu;
+  // edges
+  DevArr<int> edge_i, edge_j;
+  DevArr<double> edge_q, edge_t, edge_S, Jedge, redge;
+  DevArr<uint8_t> edge_robust;
+  // gather structures
+  DevArr<int> fb_hi, fb_lo, fb_ptr, ft_type, ft_fac, ft_rhi, ft_rlo;   // factor blocks / terms
+  int n_fb = 0;
+  DevArr<int> sb_hi, sb_lo, sb_ptr, sp_a, sp_b;                         // schur blocks / pairs
+  int n_sb = 0;
+  // vectors of size n_vec: [cam part n_c_pad | landmark part 3 L_in]
+  DevArr<double> scale, colsq, diag, gvec, grad, sgrad, gn, step, xsol, yb, gs, tmp;
+  DevArr<double> S, linv;
+  DevArr<int> flag;
+  DevArr<double> partials, scalars;
+  double* h_scalars = nullptr;   // pinned
+  int cur = 0;
+  // trust-region state (Ceres DoglegStrategy / TrustRegionMinimizer)
+  double radius = 1e4, mu = 1e-8, cost = 0.0, x_norm = 0.0, alpha = 0.0, dogleg_norm = 0.0;
+  double gn2 = 0.0, gg = 0.0, g_gn = 0.0;   // |gn|^2, |grad|^2, grad.gn of the current Gauss-Newton solve
+  bool reuse = false, have_lin = false, scaled = false;
+  int invalid_run = 0, iterations = 0, termination = 0;
+  std::vector<double> cost_hist;
+  std::vector<int> step_status;
+  std::function<int(void*, size_t)> allreduce;   // (device ptr, count of doubles) in-place sum over ranks
+  ~Engine() {
+    for (int i = 0; i < 2; i++) { pose[i].free_(); sb[i].free_(); lm[i].free_(); }
+    pose_const.free_(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
+    obs_kf.free_(); obs_lm.free_(); lm_ptr.free_(); kf_ptr.free_(); kf_obs.free_(); obs_uv.free_(); obs_sigma.free_();
+    lin.free_(); wy.free_(); Hll.free_(); HllInv.free_(); bl.free_();
+    pre.free_(); imu_i.free_(); imu_j.free_(); Jimu.free_(); rimu.free_();
+    edge_i.free_(); edge_j.free_(); edge_q.free_(); edge_t.free_(); edge_S.free_(); Jedge.free_(); redge.free_();
+    edge_robust.free_();
+    fb_hi.free_(); fb_lo.free_(); fb_ptr.free_(); ft_type.free_(); ft_fac.free_(); ft_rhi.free_(); ft_rlo.free_();
+    sb_hi.free_(); sb_lo.free_(); sb_ptr.free_(); sp_a.free_(); sp_b.free_();
+    scale.free_(); colsq.free_(); diag.free_(); gvec.free_(); grad.free_(); sgrad.free_(); gn.free_(); step.free_();
+    xsol.free_(); yb.free_(); gs.free_(); tmp.free_(); S.free_(); linv.free_(); flag.free_(); partials.free_();
+    scalars.free_();
+    if (h_scalars) cudaFreeHost(h_scalars);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// reductions: every reducing kernel writes RED_BLOCKS partials per slot; reduce_final sums them in a fixed tree
+// ------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* partials, const int (&slots)[NV]) {
+  __shared__ double sm[NV][256];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < NV; i++) sm[i][tid] = v[i];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) {
+#pragma unroll
+      for (int i = 0; i < NV; i++) sm[i][tid] += sm[i][tid + s];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; i++) partials[slots[i] * RED_BLOCKS + blockIdx.x] = sm[i][0];
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_final(const double* __restrict__ partials, double* __restrict__ scalars,
+                                                    int nslots, int add) {
+  __shared__ double sm[256];
+  for (int s = 0; s < nslots; s++) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < RED_BLOCKS; i += 256) v += partials[s * RED_BLOCKS + i];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+      if (threadIdx.x < k) sm[threadIdx.x] += sm[threadIdx.x + k];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) scalars[s] = (add ? scalars[s] : 0.0) + sm[0];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: reprojection linearisation.  mode 0: residual + Jacobian records + cost; 1: cost only; 2: corrected norms
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lin_obs_kernel(int n_obs, const int* __restrict__ obs_kf, const int* __restrict__ obs_lm,
+                                                      const double* __restrict__ obs_uv, const double* __restrict__ obs_sigma,
+                                                      const double* __restrict__ pose, const double* __restrict__ lm,
+                                                      const double* __restrict__ extr_kf, const double* __restrict__ intr_kf,
+                                                      const double* __restrict__ dist_kf, const double* __restrict__ scale,
+                                                      int per, int n_c_pad, double a2, int mode, ObsLin* __restrict__ lin,
+                                                      ObsWY* __restrict__ wy, double* __restrict__ norms,
+                                                      double* __restrict__ partials, int slot) {
+  double csum[1] = {0.0};
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
+    const int k = obs_kf[o], l = obs_lm[o];
+    double r[2], Jp[12], Jl[6];
+    reproj(pose + 7 * k, extr_kf + 7 * k, intr_kf + 4 * k, dist_kf + 4 * k, lm + 3 * l, obs_uv[2 * o], obs_uv[2 * o + 1],
+           obs_sigma[o], r, Jp, Jl, mode == 0);
+    const double s = r[0] * r[0] + r[1] * r[1];
+    double sc, c;
+    cauchy(s, a2, &sc, &c);
+    csum[0] += c;
+    if (mode == 2) norms[o] = sqrt(s) * sc;
+    if (mode != 0) continue;
+    ObsLin rec;
+    rec.r[0] = r[0] * sc;
+    rec.r[1] = r[1] * sc;
+    const double* sp = scale + (size_t)k * per;
+    const double* sl = scale + n_c_pad + 3 * (size_t)l;
+#pragma unroll
+    for (int c2 = 0; c2 < 6; c2++) {
+      rec.Jp[c2] = Jp[c2] * sc * sp[c2];
+      rec.Jp[6 + c2] = Jp[6 + c2] * sc * sp[c2];
+    }
+#pragma unroll
+    for (int c2 = 0; c2 < 3; c2++) {
+      rec.Jl[c2] = Jl[c2] * sc * sl[c2];
+      rec.Jl[3 + c2] = Jl[3 + c2] * sc * sl[c2];
+    }
+    lin[o] = rec;
+    ObsWY* w = wy + o;   // W = Jp^T Jl (6x3)
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) w->W[3 * a + b] = rec.Jp[a] * rec.Jl[b] + rec.Jp[6 + a] * rec.Jl[3 + b];
+  }
+  const int slots[1] = {slot};
+  block_reduce_store<1>(csum, partials, slots);
+}
+
+// per landmark: Hll = sum Jl^T Jl (6 unique: 00 01 02 11 12 22), bl = sum Jl^T r, colsq of the 3 columns
+__global__ void lm_reduce_kernel(int L, const int* __restrict__ lm_ptr, const ObsLin* __restrict__ lin,
+                                 double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ colsq_l,
+                                 double* __restrict__ g_l) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  double h[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+  for (int o = lm_ptr[l]; o < lm_ptr[l + 1]; o++) {
+    const double* J = lin[o].Jl;
+    const double r0 = lin[o].r[0], r1 = lin[o].r[1];
+    h[0] += J[0] * J[0] + J[3] * J[3];
+    h[1] += J[0] * J[1] + J[3] * J[4];
+    h[2] += J[0] * J[2] + J[3] * J[5];
+    h[3] += J[1] * J[1] + J[4] * J[4];
+    h[4] += J[1] * J[2] + J[4] * J[5];
+    h[5] += J[2] * J[2] + J[5] * J[5];
+    b[0] += J[0] * r0 + J[3] * r1;
+    b[1] += J[1] * r0 + J[4] * r1;
+    b[2] += J[2] * r0 + J[5] * r1;
+  }
+  for (int i = 0; i < 6; i++) Hll[6 * (size_t)l + i] = h[i];
+  for (int i = 0; i < 3; i++) {
+    bl[3 * (size_t)l + i] = b[i];
+    g_l[3 * (size_t)l + i] = b[i];
+  }
+  colsq_l[3 * (size_t)l + 0] = h[0];
+  colsq_l[3 * (size_t)l + 1] = h[3];
+  colsq_l[3 * (size_t)l + 2] = h[5];
+}
+
+__device__ __forceinline__ double clamp_diag(double v) { return fmin(fmax(v, 1e-6), 1e32); }
+
+// (Hll + mu * diag_l^2)^-1, symmetric 3x3
+__global__ void lm_damp_inv_kernel(int L, const double* __restrict__ Hll, const double* __restrict__ colsq_l, double mu,
+                                   double* __restrict__ HllInv) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const double* h = Hll + 6 * (size_t)l;
+  const double a = h[0] + mu * clamp_diag(colsq_l[3 * (size_t)l]), b = h[1], c = h[2];
+  const double d = h[3] + mu * clamp_diag(colsq_l[3 * (size_t)l + 1]), e = h[4];
+  const double f = h[5] + mu * clamp_diag(colsq_l[3 * (size_t)l + 2]);
+  const double A = d * f - e * e, B = c * e - b * f, C = b * e - c * d;
+  const double det = a * A + b * B + c * C;
+  const double id = 1.0 / det;
+  double* o = HllInv + 6 * (size_t)l;
+  o[0] = A * id;
+  o[1] = B * id;
+  o[2] = C * id;
+  o[3] = (a * f - c * c) * id;
+  o[4] = (b * c - a * e) * id;
+  o[5] = (a * d - b * b) * id;
+}
+
+// Y = W * Hll^-1 (6x3)
+__global__ void obs_Y_kernel(int n_obs, const int* __restrict__ obs_lm, const double* __restrict__ HllInv,
+                             ObsWY* __restrict__ wy) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_obs) return;
+  const double* h = HllInv + 6 * (size_t)obs_lm[o];
+  const double H[9] = {h[0], h[1], h[2], h[1], h[3], h[4], h[2], h[4], h[5]};
+  ObsWY* w = wy + o;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) w->Y[3 * a + b] = w->W[3 * a] * H[b] + w->W[3 * a + 1] * H[3 + b] + w->W[3 * a + 2] * H[6 + b];
+}
+
+// per keyframe (one warp): Hpp = sum Jp^T Jp → lower part of the 6x6 diagonal block of S; g_c = sum Jp^T r;
+// yb = sum Y b_l
+__global__ void __launch_bounds__(128) kf_visual_kernel(int K, const int* __restrict__ kf_ptr, const int* __restrict__ kf_obs,
+                                                        const int* __restrict__ obs_lm, const ObsLin* __restrict__ lin,
+                                                        const ObsWY* __restrict__ wy, const double* __restrict__ bl,
+                                                        int per, size_t ld, double* __restrict__ S, double* __restrict__ g_c,
+                                                        double* __restrict__ yb, int what) {
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (k >= K) return;
+  double h[21], b[6], y[6];
+#pragma unroll
+  for (int i = 0; i < 21; i++) h[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) b[i] = y[i] = 0.0;
+  for (int e = kf_ptr[k] + lane; e < kf_ptr[k + 1]; e += 32) {
+    const int o = kf_obs[e];
+    if (what == 0) {
+      const ObsLin& L = lin[o];
+      int idx = 0;
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c <= r; c++) h[idx++] += L.Jp[r] * L.Jp[c] + L.Jp[6 + r] * L.Jp[6 + c];
+#pragma unroll
+      for (int r = 0; r < 6; r++) b[r] += L.Jp[r] * L.r[0] + L.Jp[6 + r] * L.r[1];
+    } else {
+      const double* bb = bl + 3 * (size_t)obs_lm[o];
+      const double* Y = wy[o].Y;
+#pragma unroll
+      for (int r = 0; r < 6; r++) y[r] += Y[3 * r] * bb[0] + Y[3 * r + 1] * bb[1] + Y[3 * r + 2] * bb[2];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 21; i++) h[i] += __shfl_xor_sync(0xffffffffu, h[i], off);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      b[i] += __shfl_xor_sync(0xffffffffu, b[i], off);
+      y[i] += __shfl_xor_sync(0xffffffffu, y[i], off);
+    }
+  }
+  if (lane == 0) {
+    if (what == 0) {
+      int idx = 0;
+      for (int r = 0; r < 6; r++)
+        for (int c = 0; c <= r; c++) {
+          S[((size_t)k * per + r) * ld + (size_t)k * per + c] = h[idx];
+          if (c != r) S[((size_t)k * per + c) * ld + (size_t)k * per + r] = h[idx];
+          idx++;
+        }
+      for (int r = 0; r < 6; r++) g_c[(size_t)k * per + r] = b[r];
+    } else {
+      for (int r = 0; r < 6; r++) yb[(size_t)k * per + r] = y[r];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: IMU preintegration (repropagate) and factor linearisation
+// ------------------------------------------------------------------------------------------------
+// One thread per factor.  VINS-Mono IntegrationBase::midPointIntegration restated [A]; covariance P and Jacobian
+// J (15x15) live in local memory.  Output: ImuPre with sqrt_info = chol(P^-1)^T.
+__global__ void imu_repropagate_kernel(int n_imu, const int* __restrict__ imu_j, const int* __restrict__ imu_ptr,
+                                       const double* __restrict__ dt, const double* __restrict__ acc,
+                                       const double* __restrict__ gyr, const double* __restrict__ acc0,
+                                       const double* __restrict__ gyr0, const double* __restrict__ sb,
+                                       const double* __restrict__ noise, ImuPre* __restrict__ pre, int* __restrict__ flag) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_imu) return;
+  const int j = imu_j[f];
+  const V3 ba{sb[9 * j + 3], sb[9 * j + 4], sb[9 * j + 5]}, bg{sb[9 * j + 6], sb[9 * j + 7], sb[9 * j + 8]};
+  const double q_[6] = {noise[0] * noise[0], noise[1] * noise[1], noise[0] * noise[0], noise[1] * noise[1],
+                        noise[2] * noise[2], noise[3] * noise[3]};
+  double Jm[225], P[225], F[225], V[270], Tm[225];
+  for (int i = 0; i < 225; i++) { Jm[i] = 0.0; P[i] = 0.0; }
+  for (int i = 0; i < 15; i++) Jm[16 * i] = 1.0;
+  V3 dp{0, 0, 0}, dv{0, 0, 0};
+  Q4 dq{0, 0, 0, 1};
+  V3 a0{acc0[3 * f], acc0[3 * f + 1], acc0[3 * f + 2]}, g0{gyr0[3 * f], gyr0[3 * f + 1], gyr0[3 * f + 2]};
+  double Tsum = 0.0;
+  for (int s = imu_ptr[f]; s < imu_ptr[f + 1]; s++) {
+    const double h = dt[s];
+    const V3 a1{acc[3 * s], acc[3 * s + 1], acc[3 * s + 2]}, g1{gyr[3 * s], gyr[3 * s + 1], gyr[3 * s + 2]};
+    const M3 R0 = q2R(dq);
+    const V3 ua0 = mul(R0, a0 - ba);
+    const V3 ug = 0.5 * (g0 + g1) - bg;
+    const Q4 q1 = qnormalized(qmul(dq, Q4{ug.x * h / 2, ug.y * h / 2, ug.z * h / 2, 1.0}));
+    const M3 R1 = q2R(q1);
+    const V3 ua1 = mul(R1, a1 - ba);
+    const V3 ua = 0.5 * (ua0 + ua1);
+    const V3 ndp = dp + h * dv + (0.5 * h * h) * ua;
+    const V3 ndv = dv + h * ua;
+    const M3 Rw = skew(ug), Ra0 = skew(a0 - ba), Ra1 = skew(a1 - ba);
+    M3 ImRw = eye3();
+    for (int i = 0; i < 9; i++) ImRw.m[i] -= Rw.m[i] * h;
+    const M3 R0Ra0 = mul(R0, Ra0), R1Ra1 = mul(R1, Ra1), R1Ra1I = mul(R1Ra1, ImRw);
+    for (int i = 0; i < 225; i++) F[i] = 0.0;
+    for (int i = 0; i < 270; i++) V[i] = 0.0;
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        const int ab = 3 * a + b;
+        const double I = (a == b) ? 1.0 : 0.0;
+        F[15 * a + b] = I;
+        F[15 * a + 3 + b] = -0.25 * R0Ra0.m[ab] * h * h - 0.25 * R1Ra1I.m[ab] * h * h;
+        F[15 * a + 6 + b] = I * h;
+        F[15 * a + 9 + b] = -0.25 * (R0.m[ab] + R1.m[ab]) * h * h;
+        F[15 * a + 12 + b] = -0.25 * R1Ra1.m[ab] * h * h * (-h);
+        F[15 * (3 + a) + 3 + b] = ImRw.m[ab];
+        F[15 * (3 + a) + 12 + b] = -I * h;
+        F[15 * (6 + a) + 3 + b] = -0.5 * R0Ra0.m[ab] * h - 0.5 * R1Ra1I.m[ab] * h;
+        F[15 * (6 + a) + 6 + b] = I;
+        F[15 * (6 + a) + 9 + b] = -0.5 * (R0.m[ab] + R1.m[ab]) * h;
+        F[15 * (6 + a) + 12 + b] = -0.5 * R1Ra1.m[ab] * h * (-h);
+        F[15 * (9 + a) + 9 + b] = I;
+        F[15 * (12 + a) + 12 + b] = I;
+        V[18 * a + b] = 0.25 * R0.m[ab] * h * h;
+        V[18 * a + 3 + b] = 0.25 * (-R1Ra1.m[ab] * h * h) * 0.5 * h;
+        V[18 * a + 6 + b] = 0.25 * R1.m[ab] * h * h;
+        V[18 * a + 9 + b] = V[18 * a + 3 + b];
+        V[18 * (3 + a) + 3 + b] = 0.5 * I * h;
+        V[18 * (3 + a) + 9 + b] = 0.5 * I * h;
+        V[18 * (6 + a) + b] = 0.5 * R0.m[ab] * h;
+        V[18 * (6 + a) + 3 + b] = 0.5 * (-R1Ra1.m[ab] * h) * 0.5 * h;
+        V[18 * (6 + a) + 6 + b] = 0.5 * R1.m[ab] * h;
+        V[18 * (6 + a) + 9 + b] = V[18 * (6 + a) + 3 + b];
+        V[18 * (9 + a) + 12 + b] = I * h;
+        V[18 * (12 + a) + 15 + b] = I * h;
+      }
+    // Jm <- F Jm
+    for (int r = 0; r < 15; r++)
+      for (int c = 0; c < 15; c++) {
+        double s2 = 0;
+        for (int m = 0; m < 15; m++) s2 += F[15 * r + m] * Jm[15 * m + c];
+        Tm[15 * r + c] = s2;
+      }
+    for (int i = 0; i < 225; i++) Jm[i] = Tm[i];
+    // P <- F P F^T + V Q V^T
+    for (int r = 0; r < 15; r++)
+      for (int c = 0; c < 15; c++) {
+        double s2 = 0;
+        for (int m = 0; m < 15; m++) s2 += F[15 * r + m] * P[15 * m + c];
+        Tm[15 * r + c] = s2;
+      }
+    for (int r = 0; r < 15; r++)
+      for (int c = 0; c < 15; c++) {
+        double s2 = 0;
+        for (int m = 0; m < 15; m++) s2 += Tm[15 * r + m] * F[15 * c + m];
+        for (int m = 0; m < 18; m++) s2 += V[18 * r + m] * q_[m / 3] * V[18 * c + m];
+        P[15 * r + c] = s2;
+      }
+    dp = ndp; dv = ndv; dq = q1; a0 = a1; g0 = g1; Tsum += h;
+  }
+  ImuPre& O = pre[f];
+  O.T = Tsum;
+  O.alpha[0] = dp.x; O.alpha[1] = dp.y; O.alpha[2] = dp.z;
+  O.beta[0] = dv.x; O.beta[1] = dv.y; O.beta[2] = dv.z;
+  O.gamma[0] = dq.x; O.gamma[1] = dq.y; O.gamma[2] = dq.z; O.gamma[3] = dq.w;
+  O.ba[0] = ba.x; O.ba[1] = ba.y; O.ba[2] = ba.z;
+  O.bg[0] = bg.x; O.bg[1] = bg.y; O.bg[2] = bg.z;
+  for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++) {
+      O.dp_dba[3 * a + b] = Jm[15 * a + 9 + b];
+      O.dp_dbg[3 * a + b] = Jm[15 * a + 12 + b];
+      O.dq_dbg[3 * a + b] = Jm[15 * (3 + a) + 12 + b];
+      O.dv_dba[3 * a + b] = Jm[15 * (6 + a) + 9 + b];
+      O.dv_dbg[3 * a + b] = Jm[15 * (6 + a) + 12 + b];
+    }
+  // sqrt_info = chol(P^-1)^T :  P = Lp Lp^T,  P^-1 = Lp^-T Lp^-1;  chol(P^-1) = M with M M^T = P^-1.
+  // Take X = Lp^-1 (lower).  P^-1 = X^T X.  Its Cholesky factor (lower, positive diagonal) is computed directly.
+  // 1. Pinv via Cholesky of P
+  bool ok = true;
+  for (int c = 0; c < 15; c++) {   // F <- chol(P) lower
+    for (int r = c; r < 15; r++) {
+      double s2 = P[15 * r + c];
+      for (int m = 0; m < c; m++) s2 -= F[15 * r + m] * F[15 * c + m];
+      if (r == c) {
+        if (!(s2 > 0.0)) { ok = false; s2 = 1.0; }
+        F[15 * c + c] = sqrt(s2);
+      } else {
+        F[15 * r + c] = s2 / F[15 * c + c];
+      }
+    }
+    for (int r = 0; r < c; r++) F[15 * r + c] = 0.0;
+  }
+  for (int c = 0; c < 15; c++)      // Tm <- F^-1 (lower)
+    for (int r = 0; r < 15; r++) {
+      if (r < c) { Tm[15 * r + c] = 0.0; continue; }
+      double s2 = (r == c) ? 1.0 : 0.0;
+      for (int m = c; m < r; m++) s2 -= F[15 * r + m] * Tm[15 * m + c];
+      Tm[15 * r + c] = s2 / F[15 * r + r];
+    }
+  for (int r = 0; r < 15; r++)      // P <- Pinv = Tm^T Tm
+    for (int c = 0; c < 15; c++) {
+      double s2 = 0;
+      for (int m = (r > c ? r : c); m < 15; m++) s2 += Tm[15 * m + r] * Tm[15 * m + c];
+      P[15 * r + c] = s2;
+    }
+  for (int c = 0; c < 15; c++)      // F <- chol(Pinv) lower
+    for (int r = c; r < 15; r++) {
+      double s2 = P[15 * r + c];
+      for (int m = 0; m < c; m++) s2 -= F[15 * r + m] * F[15 * c + m];
+      if (r == c) {
+        if (!(s2 > 0.0)) { ok = false; s2 = 1.0; }
+        F[15 * c + c] = sqrt(s2);
+      } else {
+        F[15 * r + c] = s2 / F[15 * c + c];
+      }
+    }
+  for (int r = 0; r < 15; r++)
+    for (int c = 0; c < 15; c++) O.sqrt_info[15 * r + c] = (c >= r) ? F[15 * c + r] : 0.0;   // L^T (upper)
+  if (!ok) atomicOr(flag, 2);
+}
+
+// IMU factor: whitened residual (15) and whitened, Jacobi-scaled Jacobian (15x30); mode 1: cost only
+__global__ void __launch_bounds__(256) lin_imu_kernel(int n_imu, const int* __restrict__ imu_i, const int* __restrict__ imu_j,
+                               const ImuPre* __restrict__ pre, const double* __restrict__ pose, const double* __restrict__ sb,
+                               const double* __restrict__ scale, int per, double g, int mode, double* __restrict__ Jout,
+                               double* __restrict__ rout, double* __restrict__ partials, int slot) {
+  double csum[1] = {0.0};
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_imu; f += gridDim.x * blockDim.x) {
+    const int i = imu_i[f], j = imu_j[f];
+    double r[15], Jraw[450];
+    imu_raw(pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, pre[f], g, r, mode == 0 ? Jraw : nullptr);
+    const double* W = pre[f].sqrt_info;
+    double rw[15], s = 0;
+    for (int a = 0; a < 15; a++) {
+      double v = 0;
+      for (int m = a; m < 15; m++) v += W[15 * a + m] * r[m];   // upper triangular
+      rw[a] = v;
+      s += v * v;
+    }
+    csum[0] += 0.5 * s;
+    if (mode != 0) continue;
+    for (int a = 0; a < 15; a++) rout[15 * (size_t)f + a] = rw[a];
+    for (int c = 0; c < 30; c++) {
+      const int kf = c < 15 ? i : j;
+      const double sc = scale[(size_t)kf * per + (c < 15 ? c : c - 15)];
+      for (int a = 0; a < 15; a++) {
+        double v = 0;
+        for (int m = a; m < 15; m++) v += W[15 * a + m] * Jraw[30 * m + c];
+        Jout[(size_t)f * 450 + 30 * a + c] = v * sc;
+      }
+    }
+  }
+  const int slots[1] = {slot};
+  block_reduce_store<1>(csum, partials, slots);
+}
+
+// K6: between factor
+__global__ void __launch_bounds__(256) lin_edge_kernel(int n_edge, const int* __restrict__ ei, const int* __restrict__ ej, const double* __restrict__ eq,
+                                const double* __restrict__ et, const double* __restrict__ eS, const uint8_t* __restrict__ robust,
+                                const double* __restrict__ pose, const double* __restrict__ scale, int per, double a2, int mode,
+                                double* __restrict__ Jout, double* __restrict__ rout, double* __restrict__ partials, int slot) {
+  double csum[1] = {0.0};
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edge; e += gridDim.x * blockDim.x) {
+    const int i = ei[e], j = ej[e];
+    double r[6], J[72];
+    between(pose + 7 * i, pose + 7 * j, eq + 4 * e, et + 3 * e, eS + 36 * (size_t)e, r, J, mode == 0);
+    double s = 0;
+    for (int a = 0; a < 6; a++) s += r[a] * r[a];
+    double sc, c;
+    cauchy(s, robust[e] ? a2 : 0.0, &sc, &c);
+    csum[0] += c;
+    if (mode != 0) continue;
+    for (int a = 0; a < 6; a++) rout[6 * (size_t)e + a] = r[a] * sc;
+    for (int a = 0; a < 6; a++)
+      for (int c2 = 0; c2 < 12; c2++) {
+        const int kf = c2 < 6 ? i : j;
+        Jout[(size_t)e * 72 + 12 * a + c2] = J[12 * a + c2] * sc * scale[(size_t)kf * per + (c2 < 6 ? c2 : c2 - 6)];
+      }
+  }
+  const int slots[1] = {slot};
+  block_reduce_store<1>(csum, partials, slots);
+}
+
+// gather J^T J of IMU (type 0, 15 cols per role) and edge (type 1, 6 cols per role) factors into S, and J^T r into g_c
+__global__ void __launch_bounds__(256) factor_gather_kernel(int n_fb, const int* __restrict__ fb_hi, const int* __restrict__ fb_lo,
+                                                            const int* __restrict__ fb_ptr, const int* __restrict__ ft_type,
+                                                            const int* __restrict__ ft_fac, const int* __restrict__ ft_rhi,
+                                                            const int* __restrict__ ft_rlo, const double* __restrict__ Jimu,
+                                                            const double* __restrict__ rimu, const double* __restrict__ Jedge,
+                                                            const double* __restrict__ redge, int per, size_t ld,
+                                                            double* __restrict__ S, double* __restrict__ g_c) {
+  const int b = blockIdx.x;
+  if (b >= n_fb) return;
+  const int hi = fb_hi[b], lo = fb_lo[b];
+  const int r = threadIdx.x / 15, c = threadIdx.x % 15;
+  if (r >= 15) return;
+  double acc = 0.0, gacc = 0.0;
+  for (int t = fb_ptr[b]; t < fb_ptr[b + 1]; t++) {
+    const int type = ft_type[t], f = ft_fac[t];
+    const int d = type == 0 ? 15 : 6, rows = type == 0 ? 15 : 6, ncol = type == 0 ? 30 : 12;
+    if (r >= d || c >= d) continue;
+    const double* J = (type == 0 ? Jimu + (size_t)f * 450 : Jedge + (size_t)f * 72);
+    const double* res = (type == 0 ? rimu + (size_t)f * 15 : redge + (size_t)f * 6);
+    const int ca = ft_rhi[t] * d + r, cb = ft_rlo[t] * d + c;
+    double s = 0.0, gs = 0.0;
+    for (int m = 0; m < rows; m++) {
+      s += J[ncol * m + ca] * J[ncol * m + cb];
+      if (hi == lo && c == 0) gs += J[ncol * m + ca] * res[m];
+    }
+    acc += s;
+    gacc += gs;
+  }
+  if (r < per && c < per) S[((size_t)hi * per + r) * ld + (size_t)lo * per + c] += acc;
+  if (hi == lo && c == 0 && r < per) g_c[(size_t)hi * per + r] += gacc;
+}
+
+// camera part, step 1: colsq = diag(J^T J) (before damping / Schur)
+__global__ void cam_colsq_kernel(int n_c_pad, const double* __restrict__ scale, size_t ld, const double* __restrict__ S,
+                                 double* __restrict__ colsq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_c_pad) return;
+  colsq[i] = scale[i] != 0.0 ? S[(size_t)i * ld + i] : 0.0;
+}
+__global__ void cam_diag_kernel(int n_c_pad, const double* __restrict__ scale, const double* __restrict__ colsq,
+                                double* __restrict__ diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_c_pad) return;
+  diag[i] = scale[i] != 0.0 ? sqrt(clamp_diag(colsq[i])) : 1.0;
+}
+// camera part, step 2 (after the Schur subtraction): damping, reduced gradient, inactive rows → identity
+__global__ void cam_finish_kernel(int n_c_pad, const double* __restrict__ scale, size_t ld, double* __restrict__ S,
+                                  const double* __restrict__ diag, const double* __restrict__ g_c,
+                                  const double* __restrict__ yb, double* __restrict__ gs, double mu) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_c_pad) return;
+  if (scale[i] != 0.0) {
+    const double dg = diag[i];
+    S[(size_t)i * ld + i] += mu * dg * dg;
+    gs[i] = g_c[i] - yb[i];
+  } else {
+    S[(size_t)i * ld + i] = 1.0;
+    gs[i] = 0.0;
+  }
+}
+
+// K7: S(hi,lo) -= sum over (a,b) pairs of Y_a W_b^T, one warp per block
+__global__ void __launch_bounds__(128) schur_kernel(int n_sb, const int* __restrict__ sb_hi, const int* __restrict__ sb_lo,
+                                                    const int* __restrict__ sb_ptr, const int* __restrict__ sp_a,
+                                                    const int* __restrict__ sp_b, const ObsWY* __restrict__ wy, int per,
+                                                    size_t ld, double* __restrict__ S) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= n_sb) return;
+  double acc[36];
+#pragma unroll
+  for (int i = 0; i < 36; i++) acc[i] = 0.0;
+  for (int p = sb_ptr[b] + lane; p < sb_ptr[b + 1]; p += 32) {
+    const double* Y = wy[sp_a[p]].Y;
+    const double* W = wy[sp_b[p]].W;
+    double y[18], w[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) { y[i] = Y[i]; w[i] = W[i]; }
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+      for (int c = 0; c < 6; c++) acc[6 * r + c] += y[3 * r] * w[3 * c] + y[3 * r + 1] * w[3 * c + 1] + y[3 * r + 2] * w[3 * c + 2];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int i = 0; i < 36; i++) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+  const int hi = sb_hi[b], lo = sb_lo[b];
+  // lanes 0..35 → not enough lanes; lane l writes entries l and l+32
+  for (int e = lane; e < 36; e += 32) {
+    const int r = e / 6, c = e % 6;
+    double v = 0.0;
+#pragma unroll
+    for (int i = 0; i < 36; i++)
+      if (i == e) v = acc[i];
+    S[((size_t)hi * per + r) * ld + (size_t)lo * per + c] -= v;
+  }
+}
+
+// landmark back-substitution: x_l = Hll^-1 (b_l - sum W^T x_c)
+__global__ void backsub_kernel(int L, const int* __restrict__ lm_ptr, const int* __restrict__ obs_kf,
+                               const ObsWY* __restrict__ wy, const double* __restrict__ HllInv, const double* __restrict__ bl,
+                               const double* __restrict__ xc, int per, double* __restrict__ xl) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  double t[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
+  for (int o = lm_ptr[l]; o < lm_ptr[l + 1]; o++) {
+    const double* W = wy[o].W;
+    const double* x = xc + (size_t)obs_kf[o] * per;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+      t[0] -= W[3 * a] * x[a];
+      t[1] -= W[3 * a + 1] * x[a];
+      t[2] -= W[3 * a + 2] * x[a];
+    }
+  }
+  const double* h = HllInv + 6 * (size_t)l;
+  xl[3 * (size_t)l + 0] = h[0] * t[0] + h[1] * t[1] + h[2] * t[2];
+  xl[3 * (size_t)l + 1] = h[1] * t[0] + h[3] * t[1] + h[4] * t[2];
+  xl[3 * (size_t)l + 2] = h[2] * t[0] + h[4] * t[1] + h[5] * t[2];
+}
+
+// ------------------------------------------------------------------------------------------------
+// J * v over all residual blocks: sums (Jv)^2 and (Jv).r
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) jv_obs_kernel(int n_obs, const int* __restrict__ obs_kf, const int* __restrict__ obs_lm,
+                                                     const ObsLin* __restrict__ lin, const double* __restrict__ v, int per,
+                                                     int n_c_pad, double* __restrict__ partials, int slot0) {
+  double s[2] = {0.0, 0.0};
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
+    const ObsLin& L = lin[o];
+    const double* vp = v + (size_t)obs_kf[o] * per;
+    const double* vl = v + n_c_pad + 3 * (size_t)obs_lm[o];
+    double j0 = 0, j1 = 0;
+#pragma unroll
+    for (int c = 0; c < 6; c++) { j0 += L.Jp[c] * vp[c]; j1 += L.Jp[6 + c] * vp[c]; }
+#pragma unroll
+    for (int c = 0; c < 3; c++) { j0 += L.Jl[c] * vl[c]; j1 += L.Jl[3 + c] * vl[c]; }
+    s[0] += j0 * j0 + j1 * j1;
+    s[1] += j0 * L.r[0] + j1 * L.r[1];
+  }
+  const int slots[2] = {slot0, slot0 + 1};
+  block_reduce_store<2>(s, partials, slots);
+}
+
+__global__ void __launch_bounds__(256) jv_factor_kernel(int n_imu, const int* __restrict__ imu_i, const int* __restrict__ imu_j,
+                                                        const double* __restrict__ Jimu, const double* __restrict__ rimu,
+                                                        int n_edge, const int* __restrict__ ei, const int* __restrict__ ej,
+                                                        const double* __restrict__ Jedge, const double* __restrict__ redge,
+                                                        const double* __restrict__ v, int per, double* __restrict__ partials,
+                                                        int slot0) {
+  double s[2] = {0.0, 0.0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_imu + n_edge; t += gridDim.x * blockDim.x) {
+    if (t < n_imu) {
+      const double* J = Jimu + (size_t)t * 450;
+      const double* vi = v + (size_t)imu_i[t] * per;
+      const double* vj = v + (size_t)imu_j[t] * per;
+      for (int a = 0; a < 15; a++) {
+        double jv = 0;
+        for (int c = 0; c < 15; c++) jv += J[30 * a + c] * vi[c] + J[30 * a + 15 + c] * vj[c];
+        s[0] += jv * jv;
+        s[1] += jv * rimu[15 * (size_t)t + a];
+      }
+    } else {
+      const int e = t - n_imu;
+      const double* J = Jedge + (size_t)e * 72;
+      const double* vi = v + (size_t)ei[e] * per;
+      const double* vj = v + (size_t)ej[e] * per;
+      for (int a = 0; a < 6; a++) {
+        double jv = 0;
+        for (int c = 0; c < 6; c++) jv += J[12 * a + c] * vi[c] + J[12 * a + 6 + c] * vj[c];
+        s[0] += jv * jv;
+        s[1] += jv * redge[6 * (size_t)e + a];
+      }
+    }
+  }
+  const int slots[2] = {slot0, slot0 + 1};
+  block_reduce_store<2>(s, partials, slots);
+}
+
+// ------------------------------------------------------------------------------------------------
+// vector algebra on [cam | landmark] vectors
+// ------------------------------------------------------------------------------------------------
+// landmark part of diag / grad / sgrad and the whole-vector versions of grad = g / diag, sgrad = grad / diag
+__global__ void prep_vectors_kernel(int n_vec, int n_c_pad, const double* __restrict__ scale, const double* __restrict__ colsq,
+                                    double* __restrict__ diag, const double* __restrict__ g, double* __restrict__ grad,
+                                    double* __restrict__ sgrad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vec) return;
+  const bool active = scale[i] != 0.0;
+  if (i >= n_c_pad) diag[i] = active ? sqrt(clamp_diag(colsq[i])) : 1.0;
+  const double d = diag[i];
+  const double gr = active ? g[i] / d : 0.0;
+  grad[i] = gr;
+  sgrad[i] = gr / d;
+}
+
+// gn = -x * diag ; sums |gn|^2, |grad|^2, grad.gn
+__global__ void __launch_bounds__(256) gn_norms_kernel(int n_vec, const double* __restrict__ x, const double* __restrict__ diag,
+                                                       const double* __restrict__ grad, const double* __restrict__ scale,
+                                                       double* __restrict__ gn, int n_c_pad, double cam_w,
+                                                       double* __restrict__ partials, int slot0) {
+  double s[3] = {0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += gridDim.x * blockDim.x) {
+    const double v = scale[i] != 0.0 ? -x[i] * diag[i] : 0.0;
+    gn[i] = v;
+    const double w = i < n_c_pad ? cam_w : 1.0;
+    s[0] += w * v * v;
+    s[1] += w * grad[i] * grad[i];
+    s[2] += w * grad[i] * v;
+  }
+  const int slots[3] = {slot0, slot0 + 1, slot0 + 2};
+  block_reduce_store<3>(s, partials, slots);
+}
+
+// step = (ca * grad + cb * gn) / diag ; also |ca grad + cb gn|^2
+__global__ void __launch_bounds__(256) dogleg_combine_kernel(int n_vec, double ca, double cb, const double* __restrict__ grad,
+                                                             const double* __restrict__ gn, const double* __restrict__ diag,
+                                                             const double* __restrict__ scale, double* __restrict__ step,
+                                                             int n_c_pad, double cam_w, double* __restrict__ partials,
+                                                             int slot0) {
+  double s[1] = {0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += gridDim.x * blockDim.x) {
+    const double d = ca * grad[i] + cb * gn[i];
+    s[0] += (i < n_c_pad ? cam_w : 1.0) * d * d;
+    step[i] = scale[i] != 0.0 ? d / diag[i] : 0.0;
+  }
+  const int slots[1] = {slot0};
+  block_reduce_store<1>(s, partials, slots);
+}
+
+// candidate = Plus(current, step * scale); sums |cand - cur|^2 (ambient) and |cand|^2 over non-constant blocks
+__global__ void __launch_bounds__(256) plus_kernel(int K, int L, int per, int n_c_pad, int visual_only,
+                                                   const uint8_t* __restrict__ pose_const, const double* __restrict__ step,
+                                                   const double* __restrict__ scale, const double* __restrict__ pose,
+                                                   const double* __restrict__ sb, const double* __restrict__ lm,
+                                                   double* __restrict__ cpose, double* __restrict__ csb, double* __restrict__ clm,
+                                                   double cam_w, double* __restrict__ partials, int slot0) {
+  double s[2] = {0, 0};
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < K + L; t += gridDim.x * blockDim.x) {
+    if (t < K) {
+      const int k = t;
+      double d[6], out[7];
+      const bool cst = pose_const[k] != 0;
+      for (int c = 0; c < 6; c++) d[c] = cst ? 0.0 : step[(size_t)k * per + c] * scale[(size_t)k * per + c];
+      if (cst) {
+        for (int c = 0; c < 7; c++) out[c] = pose[7 * k + c];
+      } else {
+        pose_plus(pose + 7 * k, d, out);
+      }
+      for (int c = 0; c < 7; c++) {
+        cpose[7 * k + c] = out[c];
+        const double df = out[c] - pose[7 * k + c];
+        s[0] += cam_w * df * df;
+        if (!cst) s[1] += cam_w * out[c] * out[c];
+      }
+      for (int c = 0; c < 9; c++) {
+        double v = sb[9 * k + c];
+        if (!visual_only) {
+          const double dd = step[(size_t)k * per + 6 + c] * scale[(size_t)k * per + 6 + c];
+          v += dd;
+          s[0] += cam_w * dd * dd;
+          s[1] += cam_w * v * v;
+        }
+        csb[9 * k + c] = v;
+      }
+    } else {
+      const int l = t - K;
+      const bool own = scale[n_c_pad + 3 * (size_t)l] != 0.0;   // landmarks of other ranks are not touched here
+      for (int c = 0; c < 3; c++) {
+        const double dd = step[n_c_pad + 3 * (size_t)l + c] * scale[n_c_pad + 3 * (size_t)l + c];
+        const double v = lm[3 * (size_t)l + c] + dd;
+        clm[3 * (size_t)l + c] = v;
+        if (own) {
+          s[0] += dd * dd;
+          s[1] += v * v;
+        }
+      }
+    }
+  }
+  const int slots[2] = {slot0, slot0 + 1};
+  block_reduce_store<2>(s, partials, slots);
+}
+
+// Jacobi scaling from the unscaled column norms: 1 / (1 + sqrt(colsq)); 0 for inactive columns
+__global__ void jacobi_scale_kernel(int n_vec, const double* __restrict__ colsq, double* __restrict__ scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vec) return;
+  if (scale[i] != 0.0) scale[i] = 1.0 / (1.0 + sqrt(colsq[i]));
+}
+
+__global__ void max_abs_grad_kernel(int n_vec, const double* __restrict__ g, const double* __restrict__ scale,
+                                    double* __restrict__ partials, int slot) {
+  __shared__ double sm[256];
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += gridDim.x * blockDim.x)
+    if (scale[i] != 0.0) m = fmax(m, fabs(g[i] / scale[i]));
+  sm[threadIdx.x] = m;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sm[threadIdx.x] = fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[slot * RED_BLOCKS + blockIdx.x] = sm[0];
+}
+__global__ void max_final_kernel(const double* __restrict__ partials, double* __restrict__ scalars, int slot) {
+  double m = 0.0;
+  for (int i = 0; i < RED_BLOCKS; i++) m = fmax(m, partials[slot * RED_BLOCKS + i]);
+  scalars[slot] = m;
+}
+
+}  // namespace
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+namespace {
+
+#define ENG_CUDA(call)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t e_ = (call);                                                                                 \
+    if (e_ != cudaSuccess)                                                                                   \
+      return cvb_fail(E.ctx, CVB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                      __LINE__);                                                                             \
+  } while (0)
+#define ENG_LAUNCH() CVB_CHECK_LAUNCH(E.ctx)
+
+template <typename T>
+int upload(Engine& E, DevArr<T>& d, const T* h, size_t n) {
+  if (d.alloc(n)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (%zu bytes)", n * sizeof(T));
+  if (n) ENG_CUDA(cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, E.st));
+  return CVB_OK;
+}
+template <typename T>
+int upload(Engine& E, DevArr<T>& d, const std::vector<T>& h) {
+  return upload(E, d, h.data(), h.size());
+}
+template <typename T>
+int zalloc(Engine& E, DevArr<T>& d, size_t n) {
+  if (d.alloc(n)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (%zu bytes)", n * sizeof(T));
+  ENG_CUDA(cudaMemsetAsync(d.p, 0, (n ? n : 1) * sizeof(T), E.st));
+  return CVB_OK;
+}
+
+inline int grid1(size_t n, int b = 256) { return (int)((n + b - 1) / b); }
+
+int read_scalars(Engine& E, int nslots) {
+  reduce_final<<<1, 256, 0, E.st>>>(E.partials.p, E.scalars.p, nslots, 0);
+  ENG_LAUNCH();
+  if (E.allreduce && E.world > 1) {
+    int rc = E.allreduce(E.scalars.p, (size_t)nslots);
+    if (rc) return cvb_fail(E.ctx, CVB_ERR_CUDA, "allreduce callback failed (%d)", rc);
+  }
+  ENG_CUDA(cudaMemcpyAsync(E.h_scalars, E.scalars.p, nslots * sizeof(double), cudaMemcpyDeviceToHost, E.st));
+  ENG_CUDA(cudaStreamSynchronize(E.st));
+  return CVB_OK;
+}
+
+int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
+  cvb_ctx* ctx = E.ctx;
+  E.visual_only = o->visual_only ? 1 : 0;
+  E.per = E.visual_only ? 6 : 15;
+  E.K = p->K;
+  E.a2_reproj = o->cauchy_reproj > 0 ? o->cauchy_reproj * o->cauchy_reproj : 0.0;
+  E.a2_edge = o->cauchy_edge > 0 ? o->cauchy_edge * o->cauchy_edge : 0.0;
+  E.rank = o->rank;
+  E.world = o->world > 0 ? o->world : 1;
+  CVB_REQUIRE(ctx, p->K > 0, "problem has no keyframes");
+  CVB_REQUIRE(ctx, E.rank >= 0 && E.rank < E.world, "bad rank/world");
+  const int K = p->K;
+  // ---- landmarks with >= 2 usable observations (opt.cpp:158-171, 438-453), observations of this rank's landmarks ----
+  std::vector<int> lm_compact(p->L > 0 ? p->L : 0, -1);
+  E.lm_of_compact.clear();
+  E.obs_of_compact.clear();
+  std::vector<int> h_obs_kf, h_obs_lm, h_lm_ptr(1, 0);
+  std::vector<double> h_uv, h_sigma, h_lm;
+  for (int l = 0; l < p->L; l++) {
+    int cnt = 0;
+    for (int ob = p->lm_obs_ptr[l]; ob < p->lm_obs_ptr[l + 1]; ob++)
+      if (!(p->obs_skip && p->obs_skip[ob])) cnt++;
+    if (cnt < 2) continue;
+    lm_compact[l] = (int)E.lm_of_compact.size();
+    E.lm_of_compact.push_back(l);
+    h_lm.push_back(p->lm[3 * (size_t)l]); h_lm.push_back(p->lm[3 * (size_t)l + 1]); h_lm.push_back(p->lm[3 * (size_t)l + 2]);
+    // landmark blocks are sharded across ranks: a rank linearises only its own landmarks' observations
+    const bool mine = (lm_compact[l] % E.world) == E.rank;
+    if (mine) {
+      int prev = -1;
+      for (int ob = p->lm_obs_ptr[l]; ob < p->lm_obs_ptr[l + 1]; ob++) {
+        if (p->obs_skip && p->obs_skip[ob]) continue;
+        const int kf = p->obs_kf[ob];
+        CVB_REQUIRE(ctx, kf >= 0 && kf < K, "obs_kf out of range");
+        CVB_REQUIRE(ctx, kf > prev, "observations of a landmark must be sorted by keyframe index and unique");
+        prev = kf;
+        h_obs_kf.push_back(kf);
+        h_obs_lm.push_back(lm_compact[l]);
+        h_uv.push_back((double)p->obs_uv[2 * (size_t)ob]); h_uv.push_back((double)p->obs_uv[2 * (size_t)ob + 1]);
+        h_sigma.push_back(p->obs_sigma[ob]);
+        E.obs_of_compact.push_back(ob);
+      }
+    }
+    h_lm_ptr.push_back((int)h_obs_kf.size());
+  }
+  E.L_in = (int)E.lm_of_compact.size();
+  E.n_obs = (int)h_obs_kf.size();
+  E.n_c = K * E.per;
+  E.n_c_pad = ((E.n_c + cvb_chol::T - 1) / cvb_chol::T) * cvb_chol::T;
+  E.n_vec = E.n_c_pad + 3 * E.L_in;
+  // ---- by-keyframe CSR ----
+  std::vector<int> h_kf_ptr(K + 1, 0), h_kf_obs(E.n_obs);
+  for (int ob = 0; ob < E.n_obs; ob++) h_kf_ptr[h_obs_kf[ob] + 1]++;
+  for (int k = 0; k < K; k++) h_kf_ptr[k + 1] += h_kf_ptr[k];
+  {
+    std::vector<int> fill(h_kf_ptr.begin(), h_kf_ptr.end() - 1);
+    for (int ob = 0; ob < E.n_obs; ob++) h_kf_obs[fill[h_obs_kf[ob]]++] = ob;
+  }
+  // ---- Schur (block → pair) lists ----
+  std::vector<uint64_t> keys;
+  std::vector<int> pa, pb;
+  {
+    size_t np = 0;
+    for (int l = 0; l < E.L_in; l++) {
+      const size_t n = h_lm_ptr[l + 1] - h_lm_ptr[l];
+      np += n * (n + 1) / 2;
+    }
+    keys.reserve(np); pa.reserve(np); pb.reserve(np);
+    for (int l = 0; l < E.L_in; l++)
+      for (int a = h_lm_ptr[l]; a < h_lm_ptr[l + 1]; a++)
+        for (int b = h_lm_ptr[l]; b <= a; b++) {
+          keys.push_back(((uint64_t)h_obs_kf[a] << 32) | (uint32_t)h_obs_kf[b]);
+          pa.push_back(a);
+          pb.push_back(b);
+        }
+  }
+  std::vector<uint32_t> order(keys.size());
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+  std::vector<int> h_sb_hi, h_sb_lo, h_sb_ptr, h_sp_a(keys.size()), h_sp_b(keys.size());
+  for (size_t i = 0; i < order.size(); i++) {
+    const uint64_t k = keys[order[i]];
+    if (i == 0 || k != keys[order[i - 1]]) {
+      h_sb_hi.push_back((int)(k >> 32));
+      h_sb_lo.push_back((int)(k & 0xffffffffu));
+      h_sb_ptr.push_back((int)i);
+    }
+    h_sp_a[i] = pa[order[i]];
+    h_sp_b[i] = pb[order[i]];
+  }
+  h_sb_ptr.push_back((int)order.size());
+  E.n_sb = (int)h_sb_hi.size();
+  // ---- factors of this rank (round-robin) and their gather lists ----
+  std::vector<int> h_imu_i, h_imu_j, sel_imu;
+  if (!E.visual_only)
+    for (int f = 0; f < p->n_imu; f++) {
+      if (f % E.world != E.rank) continue;
+      CVB_REQUIRE(ctx, p->imu_i[f] >= 0 && p->imu_i[f] < K && p->imu_j[f] >= 0 && p->imu_j[f] < K && p->imu_i[f] != p->imu_j[f],
+                  "bad IMU factor indices");
+      CVB_REQUIRE(ctx, p->imu_ptr[f + 1] > p->imu_ptr[f], "IMU factor with 0 measurements (drop it: opt.cpp:382-385)");
+      h_imu_i.push_back(p->imu_i[f]);
+      h_imu_j.push_back(p->imu_j[f]);
+      sel_imu.push_back(f);
+    }
+  E.n_imu = (int)h_imu_i.size();
+  std::vector<int> h_edge_i, h_edge_j, sel_edge;
+  for (int e = 0; e < p->n_edge; e++) {
+    if (e % E.world != E.rank) continue;
+    CVB_REQUIRE(ctx, p->edge_i[e] >= 0 && p->edge_i[e] < K && p->edge_j[e] >= 0 && p->edge_j[e] < K && p->edge_i[e] != p->edge_j[e],
+                "bad edge indices");
+    h_edge_i.push_back(p->edge_i[e]);
+    h_edge_j.push_back(p->edge_j[e]);
+    sel_edge.push_back(e);
+  }
+  E.n_edge = (int)h_edge_i.size();
+  struct Term { uint64_t key; int type, fac, rhi, rlo; };
+  std::vector<Term> terms;
+  auto add_terms = [&](int type, int f, int i, int j) {
+    terms.push_back({((uint64_t)i << 32) | (uint32_t)i, type, f, 0, 0});
+    terms.push_back({((uint64_t)j << 32) | (uint32_t)j, type, f, 1, 1});
+    if (i > j) terms.push_back({((uint64_t)i << 32) | (uint32_t)j, type, f, 0, 1});
+    else terms.push_back({((uint64_t)j << 32) | (uint32_t)i, type, f, 1, 0});
+  };
+  for (int f = 0; f < E.n_imu; f++) add_terms(0, f, h_imu_i[f], h_imu_j[f]);
+  for (int e = 0; e < E.n_edge; e++) add_terms(1, e, h_edge_i[e], h_edge_j[e]);
+  std::stable_sort(terms.begin(), terms.end(), [](const Term& a, const Term& b) { return a.key < b.key; });
+  std::vector<int> h_fb_hi, h_fb_lo, h_fb_ptr, h_ft_type, h_ft_fac, h_ft_rhi, h_ft_rlo;
+  for (size_t i = 0; i < terms.size(); i++) {
+    if (i == 0 || terms[i].key != terms[i - 1].key) {
+      h_fb_hi.push_back((int)(terms[i].key >> 32));
+      h_fb_lo.push_back((int)(terms[i].key & 0xffffffffu));
+      h_fb_ptr.push_back((int)i);
+    }
+    h_ft_type.push_back(terms[i].type); h_ft_fac.push_back(terms[i].fac);
+    h_ft_rhi.push_back(terms[i].rhi); h_ft_rlo.push_back(terms[i].rlo);
+  }
+  h_fb_ptr.push_back((int)terms.size());
+  E.n_fb = (int)h_fb_hi.size();
+
+  // ---- uploads ----
+  int rc;
+  E.h_const.assign(p->pose_const, p->pose_const + K);
+  if ((rc = upload(E, E.pose[0], p->pose, (size_t)7 * K))) return rc;
+  if ((rc = zalloc(E, E.pose[1], (size_t)7 * K))) return rc;
+  std::vector<double> h_sb((size_t)9 * K, 0.0);
+  if (p->speedbias) std::memcpy(h_sb.data(), p->speedbias, sizeof(double) * 9 * K);
+  if ((rc = upload(E, E.sb[0], h_sb))) return rc;
+  if ((rc = zalloc(E, E.sb[1], (size_t)9 * K))) return rc;
+  if ((rc = upload(E, E.lm[0], h_lm))) return rc;
+  if ((rc = zalloc(E, E.lm[1], (size_t)3 * E.L_in))) return rc;
+  if ((rc = upload(E, E.pose_const, p->pose_const, (size_t)K))) return rc;
+  std::vector<double> ex((size_t)7 * K), in((size_t)4 * K), di((size_t)4 * K);
+  for (int k = 0; k < K; k++) {
+    const int c = p->cam_of_kf ? p->cam_of_kf[k] : 0;
+    CVB_REQUIRE(ctx, c >= 0 && c < p->n_cam, "cam_of_kf out of range");
+    std::memcpy(&ex[7 * (size_t)k], p->extr + 7 * (size_t)c, 7 * sizeof(double));
+    std::memcpy(&in[4 * (size_t)k], p->intr + 4 * (size_t)c, 4 * sizeof(double));
+    std::memcpy(&di[4 * (size_t)k], p->dist + 4 * (size_t)c, 4 * sizeof(double));
+  }
+  if ((rc = upload(E, E.extr_kf, ex)) || (rc = upload(E, E.intr_kf, in)) || (rc = upload(E, E.dist_kf, di))) return rc;
+  if ((rc = upload(E, E.obs_kf, h_obs_kf)) || (rc = upload(E, E.obs_lm, h_obs_lm)) || (rc = upload(E, E.lm_ptr, h_lm_ptr)) ||
+      (rc = upload(E, E.kf_ptr, h_kf_ptr)) || (rc = upload(E, E.kf_obs, h_kf_obs)) || (rc = upload(E, E.obs_uv, h_uv)) ||
+      (rc = upload(E, E.obs_sigma, h_sigma)))
+    return rc;
+  if ((rc = zalloc(E, E.lin, (size_t)E.n_obs)) || (rc = zalloc(E, E.wy, (size_t)E.n_obs))) return rc;
+  if ((rc = zalloc(E, E.Hll, (size_t)6 * E.L_in)) || (rc = zalloc(E, E.HllInv, (size_t)6 * E.L_in)) ||
+      (rc = zalloc(E, E.bl, (size_t)3 * E.L_in)))
+    return rc;
+  if ((rc = upload(E, E.sb_hi, h_sb_hi)) || (rc = upload(E, E.sb_lo, h_sb_lo)) || (rc = upload(E, E.sb_ptr, h_sb_ptr)) ||
+      (rc = upload(E, E.sp_a, h_sp_a)) || (rc = upload(E, E.sp_b, h_sp_b)))
+    return rc;
+  if ((rc = upload(E, E.fb_hi, h_fb_hi)) || (rc = upload(E, E.fb_lo, h_fb_lo)) || (rc = upload(E, E.fb_ptr, h_fb_ptr)) ||
+      (rc = upload(E, E.ft_type, h_ft_type)) || (rc = upload(E, E.ft_fac, h_ft_fac)) || (rc = upload(E, E.ft_rhi, h_ft_rhi)) ||
+      (rc = upload(E, E.ft_rlo, h_ft_rlo)))
+    return rc;
+  // edges
+  {
+    std::vector<double> q((size_t)4 * E.n_edge), t((size_t)3 * E.n_edge), S((size_t)36 * E.n_edge);
+    std::vector<uint8_t> rb(E.n_edge);
+    for (int e = 0; e < E.n_edge; e++) {
+      const int s = sel_edge[e];
+      std::memcpy(&q[4 * (size_t)e], p->edge_q + 4 * (size_t)s, 4 * sizeof(double));
+      std::memcpy(&t[3 * (size_t)e], p->edge_t + 3 * (size_t)s, 3 * sizeof(double));
+      std::memcpy(&S[36 * (size_t)e], p->edge_sqrt_info + 36 * (size_t)s, 36 * sizeof(double));
+      rb[e] = p->edge_robust ? p->edge_robust[s] : 0;
+    }
+    if ((rc = upload(E, E.edge_i, h_edge_i)) || (rc = upload(E, E.edge_j, h_edge_j)) || (rc = upload(E, E.edge_q, q)) ||
+        (rc = upload(E, E.edge_t, t)) || (rc = upload(E, E.edge_S, S)) || (rc = upload(E, E.edge_robust, rb)))
+      return rc;
+    if ((rc = zalloc(E, E.Jedge, (size_t)72 * E.n_edge)) || (rc = zalloc(E, E.redge, (size_t)6 * E.n_edge))) return rc;
+  }
+  if ((rc = zalloc(E, E.flag, 4))) return rc;
+  // IMU: raw samples → device, repropagate at the current bias of KF j (opt.cpp:132-140, 387-396)
+  if ((rc = upload(E, E.imu_i, h_imu_i)) || (rc = upload(E, E.imu_j, h_imu_j))) return rc;
+  if ((rc = zalloc(E, E.pre, (size_t)E.n_imu)) || (rc = zalloc(E, E.Jimu, (size_t)450 * E.n_imu)) ||
+      (rc = zalloc(E, E.rimu, (size_t)15 * E.n_imu)))
+    return rc;
+  if (E.n_imu > 0) {
+    E.g = p->imu_noise[4];
+    std::vector<int> ptr(1, 0);
+    std::vector<double> dt, acc, gyr, a0, g0;
+    for (int f = 0; f < E.n_imu; f++) {
+      const int s = sel_imu[f];
+      for (int m = p->imu_ptr[s]; m < p->imu_ptr[s + 1]; m++) {
+        dt.push_back(p->imu_dt[m]);
+        for (int c = 0; c < 3; c++) { acc.push_back(p->imu_acc[3 * (size_t)m + c]); gyr.push_back(p->imu_gyr[3 * (size_t)m + c]); }
+      }
+      for (int c = 0; c < 3; c++) { a0.push_back(p->imu_acc0[3 * (size_t)s + c]); g0.push_back(p->imu_gyr0[3 * (size_t)s + c]); }
+      ptr.push_back((int)dt.size());
+    }
+    DevArr<int> d_ptr; DevArr<double> d_dt, d_acc, d_gyr, d_a0, d_g0, d_noise;
+    if ((rc = upload(E, d_ptr, ptr)) || (rc = upload(E, d_dt, dt)) || (rc = upload(E, d_acc, acc)) || (rc = upload(E, d_gyr, gyr)) ||
+        (rc = upload(E, d_a0, a0)) || (rc = upload(E, d_g0, g0)) || (rc = upload(E, d_noise, p->imu_noise, 5)))
+      return rc;
+    imu_repropagate_kernel<<<grid1(E.n_imu, 64), 64, 0, E.st>>>(E.n_imu, E.imu_j.p, d_ptr.p, d_dt.p, d_acc.p, d_gyr.p, d_a0.p,
+                                                               d_g0.p, E.sb[0].p, d_noise.p, E.pre.p, E.flag.p);
+    ENG_LAUNCH();
+    ENG_CUDA(cudaStreamSynchronize(E.st));
+    d_ptr.free_(); d_dt.free_(); d_acc.free_(); d_gyr.free_(); d_a0.free_(); d_g0.free_(); d_noise.free_();
+  }
+  // ---- vectors, S ----
+  std::vector<double> h_scale(E.n_vec, 0.0);
+  for (int k = 0; k < K; k++) {
+    if (!p->pose_const[k])
+      for (int c = 0; c < 6; c++) h_scale[(size_t)k * E.per + c] = 1.0;
+    if (!E.visual_only)
+      for (int c = 6; c < 15; c++) h_scale[(size_t)k * E.per + c] = 1.0;
+  }
+  for (int c = 0; c < E.L_in; c++)   // landmark blocks are owned by rank (c % world); others stay inactive here
+    if (c % E.world == E.rank)
+      for (int a = 0; a < 3; a++) h_scale[(size_t)E.n_c_pad + 3 * (size_t)c + a] = 1.0;
+  if ((rc = upload(E, E.scale, h_scale))) return rc;
+  DevArr<double>* vecs[] = {&E.colsq, &E.diag, &E.gvec, &E.grad, &E.sgrad, &E.gn, &E.step, &E.xsol, &E.yb, &E.gs, &E.tmp};
+  for (auto* v : vecs)
+    if ((rc = zalloc(E, *v, (size_t)E.n_vec))) return rc;
+  if ((rc = zalloc(E, E.S, (size_t)E.n_c_pad * E.n_c_pad))) return rc;
+  if ((rc = zalloc(E, E.linv, (size_t)E.n_c_pad * cvb_chol::T))) return rc;
+  if ((rc = zalloc(E, E.partials, (size_t)RED_SLOTS * RED_BLOCKS)) || (rc = zalloc(E, E.scalars, RED_SLOTS))) return rc;
+  ENG_CUDA(cudaMallocHost(&E.h_scalars, RED_SLOTS * sizeof(double)));
+  ENG_CUDA(cudaStreamSynchronize(E.st));
+  return CVB_OK;
+}
+
+// cost (and optionally full linearisation) at state buffer `b`; mode 0 = linearise, 1 = cost only
+int evaluate(Engine& E, int b, int mode, double* cost_out) {
+  const int rg = RED_BLOCKS;
+  lin_obs_kernel<<<rg, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.obs_uv.p, E.obs_sigma.p, E.pose[b].p, E.lm[b].p,
+                                       E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.scale.p, E.per, E.n_c_pad, E.a2_reproj, mode,
+                                       E.lin.p, E.wy.p, nullptr, E.partials.p, 0);
+  ENG_LAUNCH();
+  lin_imu_kernel<<<rg, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.pre.p, E.pose[b].p, E.sb[b].p, E.scale.p, E.per, E.g,
+                                       mode, E.Jimu.p, E.rimu.p, E.partials.p, 1);
+  ENG_LAUNCH();
+  lin_edge_kernel<<<rg, 256, 0, E.st>>>(E.n_edge, E.edge_i.p, E.edge_j.p, E.edge_q.p, E.edge_t.p, E.edge_S.p, E.edge_robust.p,
+                                        E.pose[b].p, E.scale.p, E.per, E.a2_edge, mode, E.Jedge.p, E.redge.p, E.partials.p, 2);
+  ENG_LAUNCH();
+  int rc = read_scalars(E, 3);
+  if (rc) return rc;
+  *cost_out = E.h_scalars[0] + E.h_scalars[1] + E.h_scalars[2];
+  return CVB_OK;
+}
+
+
+// ---- per-linearisation blocks -----------------------------------------------------------------------------------
+int lm_blocks(Engine& E) {
+  if (E.L_in > 0) {
+    lm_reduce_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.lm_ptr.p, E.lin.p, E.Hll.p, E.bl.p, E.colsq.p + E.n_c_pad,
+                                                      E.gvec.p + E.n_c_pad);
+    ENG_LAUNCH();
+  }
+  return CVB_OK;
+}
+
+int ar(Engine& E, double* p, size_t n) {
+  if (E.allreduce && E.world > 1) {
+    int rc = E.allreduce(p, n);
+    if (rc) return cvb_fail(E.ctx, CVB_ERR_CUDA, "allreduce callback failed (%d)", rc);
+  }
+  return CVB_OK;
+}
+
+// camera blocks of J^T J (before Schur / damping) into S, camera gradient into gvec
+int cam_blocks(Engine& E) {
+  const size_t ld = (size_t)E.n_c_pad;
+  ENG_CUDA(cudaMemsetAsync(E.S.p, 0, ld * ld * sizeof(double), E.st));
+  ENG_CUDA(cudaMemsetAsync(E.gvec.p, 0, ld * sizeof(double), E.st));
+  kf_visual_kernel<<<grid1((size_t)E.K * 32, 128), 128, 0, E.st>>>(E.K, E.kf_ptr.p, E.kf_obs.p, E.obs_lm.p, E.lin.p, E.wy.p,
+                                                                  E.bl.p, E.per, ld, E.S.p, E.gvec.p, E.yb.p, 0);
+  ENG_LAUNCH();
+  if (E.n_fb > 0) {
+    factor_gather_kernel<<<E.n_fb, 256, 0, E.st>>>(E.n_fb, E.fb_hi.p, E.fb_lo.p, E.fb_ptr.p, E.ft_type.p, E.ft_fac.p,
+                                                   E.ft_rhi.p, E.ft_rlo.p, E.Jimu.p, E.rimu.p, E.Jedge.p, E.redge.p, E.per, ld,
+                                                   E.S.p, E.gvec.p);
+    ENG_LAUNCH();
+  }
+  return CVB_OK;
+}
+
+int cam_colsq(Engine& E) {
+  cam_colsq_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, (size_t)E.n_c_pad, E.S.p, E.colsq.p);
+  ENG_LAUNCH();
+  return ar(E, E.colsq.p, (size_t)E.n_c_pad);
+}
+
+// damped Schur complement + Cholesky for the given mu; *ok = false if the factorisation broke down
+int factor_rcs(Engine& E, double mu, bool* ok) {
+  const size_t ld = (size_t)E.n_c_pad;
+  if (E.L_in > 0) {
+    lm_damp_inv_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.Hll.p, E.colsq.p + E.n_c_pad, mu, E.HllInv.p);
+    ENG_LAUNCH();
+    if (E.n_obs > 0) {
+      obs_Y_kernel<<<grid1(E.n_obs), 256, 0, E.st>>>(E.n_obs, E.obs_lm.p, E.HllInv.p, E.wy.p);
+      ENG_LAUNCH();
+    }
+  }
+  ENG_CUDA(cudaMemsetAsync(E.yb.p, 0, ld * sizeof(double), E.st));
+  kf_visual_kernel<<<grid1((size_t)E.K * 32, 128), 128, 0, E.st>>>(E.K, E.kf_ptr.p, E.kf_obs.p, E.obs_lm.p, E.lin.p, E.wy.p,
+                                                                  E.bl.p, E.per, ld, E.S.p, E.gvec.p, E.yb.p, 1);
+  ENG_LAUNCH();
+  if (E.n_sb > 0) {
+    schur_kernel<<<grid1((size_t)E.n_sb * 32, 128), 128, 0, E.st>>>(E.n_sb, E.sb_hi.p, E.sb_lo.p, E.sb_ptr.p, E.sp_a.p,
+                                                                   E.sp_b.p, E.wy.p, E.per, ld, E.S.p);
+    ENG_LAUNCH();
+  }
+  // the one exchange of the data path: sum the rank-partial reduced normal equations over NVLink
+  int rc = ar(E, E.S.p, ld * ld);
+  if (rc) return rc;
+  if ((rc = ar(E, E.yb.p, ld))) return rc;
+  cam_finish_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, ld, E.S.p, E.diag.p, E.gvec.p, E.yb.p, E.gs.p, mu);
+  ENG_LAUNCH();
+  rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.st);
+  if (rc) return rc;
+  int flag = 0;
+  ENG_CUDA(cudaMemcpyAsync(&flag, E.flag.p, sizeof(int), cudaMemcpyDeviceToHost, E.st));
+  ENG_CUDA(cudaStreamSynchronize(E.st));
+  *ok = (flag & 1) == 0;
+  return CVB_OK;
+}
+
+enum { TERM_NO_CONVERGENCE = 0, TERM_GRADIENT = 1, TERM_PARAMETER = 2, TERM_FUNCTION = 3, TERM_FAILURE = 4 };
+enum { STEP_ACCEPTED = 1, STEP_REJECTED = 2, STEP_INVALID = 3, STEP_CONVERGED = 4 };
+
+// full linearisation at the current state (cost included)
+int linearize(Engine& E, double* cost) {
+  int rc = evaluate(E, E.cur, 0, cost);
+  if (rc) return rc;
+  return lm_blocks(E);
+}
+
+int engine_begin(Engine& E) {
+  // iteration 0 of TrustRegionMinimizer: evaluate, fix the Jacobi scaling at x0, re-linearise in the scaled space
+  double c0;
+  int rc = linearize(E, &c0);
+  if (rc) return rc;
+  if ((rc = cam_blocks(E)) || (rc = cam_colsq(E))) return rc;
+  jacobi_scale_kernel<<<grid1(E.n_vec), 256, 0, E.st>>>(E.n_vec, E.colsq.p, E.scale.p);
+  ENG_LAUNCH();
+  if ((rc = linearize(E, &E.cost))) return rc;
+  // |x| over the non-constant parameter blocks
+  ENG_CUDA(cudaMemsetAsync(E.step.p, 0, (size_t)E.n_vec * sizeof(double), E.st));
+  const int nxt = E.cur ^ 1;
+  plus_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.K, E.L_in, E.per, E.n_c_pad, E.visual_only, E.pose_const.p, E.step.p, E.scale.p,
+                                            E.pose[E.cur].p, E.sb[E.cur].p, E.lm[E.cur].p, E.pose[nxt].p, E.sb[nxt].p,
+                                            E.lm[nxt].p, E.rank == 0 ? 1.0 : 0.0, E.partials.p, 0);
+  ENG_LAUNCH();
+  if ((rc = read_scalars(E, 2))) return rc;
+  E.x_norm = std::sqrt(E.h_scalars[1]);
+  E.cost_hist.assign(1, E.cost);
+  E.step_status.clear();
+  E.radius = 1e4; E.mu = 1e-8; E.reuse = false; E.invalid_run = 0; E.iterations = 0; E.termination = TERM_NO_CONVERGENCE;
+  E.have_lin = true;
+  return CVB_OK;
+}
+
+// DoglegStrategy::ComputeStep up to the Gauss-Newton solve; *solver_ok false → step invalid; *converged on gradient tol.
+int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
+  constexpr double MAX_MU = 1.0, MU_INC = 10.0;
+  *solver_ok = true;
+  *grad_converged = false;
+  int rc;
+  if ((rc = cam_blocks(E))) return rc;
+  if ((rc = ar(E, E.gvec.p, (size_t)E.n_c_pad))) return rc;
+  if ((rc = cam_colsq(E))) return rc;
+  cam_diag_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, E.colsq.p, E.diag.p);
+  ENG_LAUNCH();
+  prep_vectors_kernel<<<grid1(E.n_vec), 256, 0, E.st>>>(E.n_vec, E.n_c_pad, E.scale.p, E.colsq.p, E.diag.p, E.gvec.p, E.grad.p,
+                                                        E.sgrad.p);
+  ENG_LAUNCH();
+  // gradient tolerance (max-norm of the unscaled gradient)
+  max_abs_grad_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_vec, E.gvec.p, E.scale.p, E.partials.p, 7);
+  ENG_LAUNCH();
+  max_final_kernel<<<1, 1, 0, E.st>>>(E.partials.p, E.scalars.p, 7);
+  ENG_LAUNCH();
+  // Cauchy point: alpha = |grad|^2 / |J (grad / diag)|^2
+  jv_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.lin.p, E.sgrad.p, E.per, E.n_c_pad,
+                                              E.partials.p, 3);
+  ENG_LAUNCH();
+  jv_factor_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.Jimu.p, E.rimu.p, E.n_edge, E.edge_i.p,
+                                                 E.edge_j.p, E.Jedge.p, E.redge.p, E.sgrad.p, E.per, E.partials.p, 5);
+  ENG_LAUNCH();
+  bool cam_fresh = true;
+  bool solved = false;
+  while (E.mu < MAX_MU) {
+    if (!cam_fresh) {
+      if ((rc = cam_blocks(E))) return rc;
+      if ((rc = ar(E, E.gvec.p, (size_t)E.n_c_pad))) return rc;
+    }
+    bool ok = false;
+    if ((rc = factor_rcs(E, E.mu, &ok))) return rc;
+    cam_fresh = false;
+    if (!ok) {
+      E.mu *= MU_INC;
+      continue;
+    }
+    if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.st))) return rc;
+    if (E.L_in > 0) {
+      backsub_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.lm_ptr.p, E.obs_kf.p, E.wy.p, E.HllInv.p, E.bl.p, E.xsol.p, E.per,
+                                                      E.xsol.p + E.n_c_pad);
+      ENG_LAUNCH();
+    }
+    gn_norms_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_vec, E.xsol.p, E.diag.p, E.grad.p, E.scale.p, E.gn.p, E.n_c_pad,
+                                                  E.rank == 0 ? 1.0 : 0.0, E.partials.p, 0);
+    ENG_LAUNCH();
+    // slots: 0 |gn|^2, 1 |grad|^2, 2 grad.gn, 3 |J sgrad|^2 (obs), 5 (factors); slot 7 = max |g| (not summed over ranks)
+    reduce_final<<<1, 256, 0, E.st>>>(E.partials.p, E.scalars.p, 7, 0);
+    ENG_LAUNCH();
+    if ((rc = ar(E, E.scalars.p, 7))) return rc;
+    ENG_CUDA(cudaMemcpyAsync(E.h_scalars, E.scalars.p, RED_SLOTS * sizeof(double), cudaMemcpyDeviceToHost, E.st));
+    ENG_CUDA(cudaStreamSynchronize(E.st));
+    if (!std::isfinite(E.h_scalars[0])) {
+      E.mu *= MU_INC;
+      continue;
+    }
+    solved = true;
+    break;
+  }
+  if (!solved) {
+    *solver_ok = false;
+    return CVB_OK;
+  }
+  E.gn2 = E.h_scalars[0]; E.gg = E.h_scalars[1]; E.g_gn = E.h_scalars[2];
+  const double JgJg = E.h_scalars[3] + E.h_scalars[5];
+  E.alpha = E.gg / JgJg;
+  if (E.h_scalars[7] <= 1e-10 && E.world == 1) *grad_converged = true;
+  return CVB_OK;
+}
+
+// one TrustRegionMinimizer iteration; returns CVB_OK and sets *done when the minimiser terminates
+int engine_iterate(Engine& E, bool* done) {
+  constexpr double MU_INC = 10.0, MIN_MU = 1e-8;
+  *done = false;
+  int rc;
+  E.iterations++;
+  bool solver_ok = true, gconv = false;
+  if (!E.reuse) {
+    E.reuse = true;
+    if ((rc = prepare_step(E, &solver_ok, &gconv))) return rc;
+    if (gconv && E.iterations == 1) {   // gradient tolerance reached at the start point
+      E.termination = TERM_GRADIENT;
+      E.iterations = 0;
+      *done = true;
+      return CVB_OK;
+    }
+  }
+  double model_change = -1.0;
+  if (solver_ok) {
+    const double gn_norm = std::sqrt(E.gn2), g_norm = std::sqrt(E.gg), g_dot_gn = E.g_gn;
+    double ca, cb;
+    if (gn_norm <= E.radius) {
+      ca = 0.0; cb = 1.0;
+    } else if (g_norm * E.alpha >= E.radius) {
+      ca = -(E.radius / g_norm); cb = 0.0;
+    } else {
+      const double b_dot_a = -E.alpha * g_dot_gn;
+      const double a2 = (E.alpha * g_norm) * (E.alpha * g_norm);
+      const double bma2 = a2 - 2.0 * b_dot_a + gn_norm * gn_norm;
+      const double c = b_dot_a - a2;
+      const double d = std::sqrt(c * c + bma2 * (E.radius * E.radius - a2));
+      const double beta = (c <= 0) ? (d - c) / bma2 : (E.radius * E.radius - a2) / (d + c);
+      ca = -E.alpha * (1.0 - beta); cb = beta;
+    }
+    dogleg_combine_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_vec, ca, cb, E.grad.p, E.gn.p, E.diag.p, E.scale.p, E.step.p,
+                                                        E.n_c_pad, E.rank == 0 ? 1.0 : 0.0, E.partials.p, 0);
+    ENG_LAUNCH();
+    jv_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.lin.p, E.step.p, E.per, E.n_c_pad,
+                                                E.partials.p, 1);
+    ENG_LAUNCH();
+    jv_factor_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.Jimu.p, E.rimu.p, E.n_edge, E.edge_i.p,
+                                                   E.edge_j.p, E.Jedge.p, E.redge.p, E.step.p, E.per, E.partials.p, 3);
+    ENG_LAUNCH();
+    // candidate state + its cost in the same sync
+    const int nxt = E.cur ^ 1;
+    plus_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.K, E.L_in, E.per, E.n_c_pad, E.visual_only, E.pose_const.p, E.step.p, E.scale.p,
+                                              E.pose[E.cur].p, E.sb[E.cur].p, E.lm[E.cur].p, E.pose[nxt].p, E.sb[nxt].p,
+                                              E.lm[nxt].p, E.rank == 0 ? 1.0 : 0.0, E.partials.p, 5);
+    ENG_LAUNCH();
+    if ((rc = read_scalars(E, 7))) return rc;
+    const double dl2 = E.h_scalars[0];
+    const double jv2 = E.h_scalars[1] + E.h_scalars[3], jvr = E.h_scalars[2] + E.h_scalars[4];
+    const double step2 = E.h_scalars[5], cand_x2 = E.h_scalars[6];
+    E.dogleg_norm = std::sqrt(dl2);
+    model_change = -(jvr + 0.5 * jv2);
+    if (model_change > 0.0) {
+      E.invalid_run = 0;
+      double ccost;
+      if ((rc = evaluate(E, nxt, 1, &ccost))) return rc;
+      const double step_norm = std::sqrt(step2);
+      if (step_norm <= 1e-8 * (E.x_norm + 1e-8)) {
+        E.termination = TERM_PARAMETER; E.step_status.push_back(STEP_CONVERGED); *done = true;
+        return CVB_OK;
+      }
+      if (std::fabs(E.cost - ccost) <= 1e-6 * E.cost) {
+        E.termination = TERM_FUNCTION; E.step_status.push_back(STEP_CONVERGED); *done = true;
+        return CVB_OK;
+      }
+      const double rho = (E.cost - ccost) / model_change;
+      if (rho > 1e-3) {
+        E.cur = nxt;
+        E.cost = ccost;
+        E.x_norm = std::sqrt(cand_x2);
+        double c2;
+        if ((rc = linearize(E, &c2))) return rc;
+        if (rho < 0.25) E.radius *= 0.5;
+        if (rho > 0.75) E.radius = std::max(E.radius, 3.0 * E.dogleg_norm);
+        E.mu = std::max(MIN_MU, 2.0 * E.mu / MU_INC);
+        E.reuse = false;
+        E.step_status.push_back(STEP_ACCEPTED);
+      } else {
+        E.radius *= 0.5;
+        E.reuse = true;
+        E.step_status.push_back(STEP_REJECTED);
+      }
+      E.cost_hist.push_back(E.cost);
+      return CVB_OK;
+    }
+  }
+  // invalid step (solver failure or non-positive model decrease)
+  E.invalid_run++;
+  E.step_status.push_back(STEP_INVALID);
+  E.cost_hist.push_back(E.cost);
+  if (E.invalid_run > 5) {
+    E.termination = TERM_FAILURE;
+    *done = true;
+    return CVB_OK;
+  }
+  E.mu *= MU_INC;
+  E.reuse = false;
+  return CVB_OK;
+}
+
+int engine_corrected_norms(Engine& E, double* h_norms_full, int n_obs_full) {
+  DevArr<double> d;
+  if (d.alloc((size_t)E.n_obs)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed");
+  lin_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.obs_uv.p, E.obs_sigma.p, E.pose[E.cur].p,
+                                               E.lm[E.cur].p, E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.scale.p, E.per, E.n_c_pad,
+                                               E.a2_reproj, 2, E.lin.p, E.wy.p, d.p, E.partials.p, 0);
+  ENG_LAUNCH();
+  std::vector<double> h(E.n_obs);
+  ENG_CUDA(cudaMemcpyAsync(h.data(), d.p, sizeof(double) * E.n_obs, cudaMemcpyDeviceToHost, E.st));
+  ENG_CUDA(cudaStreamSynchronize(E.st));
+  d.free_();
+  for (int i = 0; i < n_obs_full; i++) h_norms_full[i] = -1.0;   // -1: observation not in this rank's problem
+  for (int i = 0; i < E.n_obs; i++) h_norms_full[E.obs_of_compact[i]] = h[i];
+  return CVB_OK;
+}
+
+int engine_download(Engine& E, const cvb_ba_problem* p, cvb_ba_result* r) {
+  const int K = E.K;
+  if (r->pose) ENG_CUDA(cudaMemcpyAsync(r->pose, E.pose[E.cur].p, sizeof(double) * 7 * K, cudaMemcpyDeviceToHost, E.st));
+  if (r->speedbias) ENG_CUDA(cudaMemcpyAsync(r->speedbias, E.sb[E.cur].p, sizeof(double) * 9 * K, cudaMemcpyDeviceToHost, E.st));
+  std::vector<double> h_lm((size_t)3 * E.L_in);
+  if (E.L_in) ENG_CUDA(cudaMemcpyAsync(h_lm.data(), E.lm[E.cur].p, sizeof(double) * 3 * E.L_in, cudaMemcpyDeviceToHost, E.st));
+  ENG_CUDA(cudaStreamSynchronize(E.st));
+  if (r->lm) {
+    std::memcpy(r->lm, p->lm, sizeof(double) * 3 * (size_t)p->L);
+    for (int c = 0; c < E.L_in; c++)
+      if (c % E.world == E.rank) std::memcpy(r->lm + 3 * (size_t)E.lm_of_compact[c], &h_lm[3 * (size_t)c], 3 * sizeof(double));
+  }
+  if (r->lm_owner) {
+    for (int l = 0; l < p->L; l++) r->lm_owner[l] = -1;
+    for (int c = 0; c < E.L_in; c++) r->lm_owner[E.lm_of_compact[c]] = c % E.world;
+  }
+  r->iterations = E.iterations;
+  r->termination = E.termination;
+  r->initial_cost = E.cost_hist.empty() ? 0.0 : E.cost_hist.front();
+  r->final_cost = E.cost;
+  r->n_cost_history = 0;
+  if (r->cost_history && r->cost_history_cap > 0) {
+    const int n = std::min<int>(r->cost_history_cap, (int)E.cost_hist.size());
+    for (int i = 0; i < n; i++) r->cost_history[i] = E.cost_hist[i];
+    r->n_cost_history = n;
+  }
+  if (r->step_status && r->cost_history_cap > 0) {
+    const int n = std::min<int>(r->cost_history_cap, (int)E.step_status.size());
+    for (int i = 0; i < n; i++) r->step_status[i] = (uint8_t)E.step_status[i];
+  }
+  return CVB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+struct cvb_ba {
+  Engine E;
+  const cvb_ba_problem* prob = nullptr;
+  cvb_ba_problem prob_copy;
+};
+
+extern "C" {
+
+void cvb_ba_free(cvb_ctx*) {}
+
+int cvb_ba_create(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o, cvb_ba** out) {
+  if (!ctx || !p || !o || !out) return CVB_ERR_INVALID;
+  *out = nullptr;
+  cvb_ba* h = new cvb_ba();
+  h->E.ctx = ctx;
+  h->E.st = ctx->stream;
+  h->prob_copy = *p;
+  int rc = engine_setup(h->E, p, o);
+  if (!rc) rc = engine_begin(h->E);
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  *out = h;
+  return CVB_OK;
+}
+
+int cvb_ba_set_allreduce(cvb_ba* h, cvb_allreduce_fn fn, void* user) {
+  if (!h) return CVB_ERR_INVALID;
+  cudaStream_t st = h->E.st;
+  if (fn)
+    h->E.allreduce = [fn, user, st](void* p, size_t n) { return fn(user, p, n, (void*)st); };
+  else
+    h->E.allreduce = nullptr;
+  return CVB_OK;
+}
+
+int cvb_ba_restart(cvb_ba* h) {
+  if (!h) return CVB_ERR_INVALID;
+  return engine_begin(h->E);
+}
+
+int cvb_ba_iterate(cvb_ba* h, int max_iterations, int* iterations_done) {
+  if (!h) return CVB_ERR_INVALID;
+  Engine& E = h->E;
+  int n = 0;
+  bool done = E.termination != TERM_NO_CONVERGENCE;
+  while (!done && n < max_iterations) {
+    int rc = engine_iterate(E, &done);
+    if (rc) return rc;
+    n++;
+  }
+  if (iterations_done) *iterations_done = n;
+  return CVB_OK;
+}
+
+int cvb_ba_result_get(cvb_ba* h, const cvb_ba_problem* p, cvb_ba_result* r) {
+  if (!h || !p || !r) return CVB_ERR_INVALID;
+  return engine_download(h->E, p, r);
+}
+
+int cvb_ba_reproj_norms(cvb_ba* h, double* norms, int n_obs) {
+  if (!h || !norms) return CVB_ERR_INVALID;
+  return engine_corrected_norms(h->E, norms, n_obs);
+}
+
+int cvb_ba_destroy(cvb_ba* h) {
+  if (h) {
+    cudaStreamSynchronize(h->E.st);
+    delete h;
+  }
+  return CVB_OK;
+}
+
+// Optimization::PoseGraphOptimization / one round of GlobalBundleAdjustment: build, iterate, read back.
+int cvb_ba_solve(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o, cvb_ba_result* r) {
+  cvb_ba* h = nullptr;
+  int rc = cvb_ba_create(ctx, p, o, &h);
+  if (rc) return rc;
+  rc = cvb_ba_iterate(h, o->max_iterations, nullptr);
+  if (!rc) rc = cvb_ba_result_get(h, p, r);
+  cvb_ba_destroy(h);
+  return rc;
+}
+
+// Optimization::GlobalBundleAdjustment (optimization_be.cpp:56-618) on the flat problem: round 1 (5 iterations, loop
+// edges without loss) + outlier purge on the loss-corrected residual norms (:270-290), round 2 from the ORIGINAL
+// state (the reference re-reads the map at :325,454-457; round 1 only removes observations) with Cauchy(1) on loops.
+int cvb_gba(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_gba_options* g, cvb_ba_result* r, uint8_t* obs_removed) {
+  if (!ctx || !p || !g || !r) return CVB_ERR_INVALID;
+  std::vector<uint8_t> skip(p->n_obs > 0 ? p->n_obs : 1, 0), rb0(p->n_edge > 0 ? p->n_edge : 1, 0), rb1(p->n_edge > 0 ? p->n_edge : 1, 1);
+  if (p->obs_skip) std::memcpy(skip.data(), p->obs_skip, (size_t)p->n_obs);
+  cvb_ba_options o{};
+  o.visual_only = g->visual_only;
+  o.cauchy_reproj = 1.0;   // ceres::CauchyLoss(1.0), optimization_be.cpp:68,302
+  o.cauchy_edge = 1.0;
+  o.world = 1;
+  int rc;
+  if (g->outlier_removal) {
+    cvb_ba_problem p1 = *p;
+    p1.edge_robust = rb0.data();   // round 1: loop edges without loss (optimization_be.cpp:253)
+    o.max_iterations = 5;          // :261
+    cvb_ba* h = nullptr;
+    if ((rc = cvb_ba_create(ctx, &p1, &o, &h))) return rc;
+    rc = cvb_ba_iterate(h, o.max_iterations, nullptr);
+    std::vector<double> norms(p->n_obs > 0 ? p->n_obs : 1);
+    if (!rc) rc = cvb_ba_reproj_norms(h, norms.data(), p->n_obs);
+    cvb_ba_destroy(h);
+    if (rc) return rc;
+    for (int i = 0; i < p->n_obs; i++)
+      if (norms[i] > g->th_outlier) skip[i] = 1;   // th_gba_outlier_global, :277-281
+  }
+  if (obs_removed)
+    for (int i = 0; i < p->n_obs; i++) obs_removed[i] = skip[i] && !(p->obs_skip && p->obs_skip[i]);
+  cvb_ba_problem p2 = *p;
+  p2.obs_skip = skip.data();
+  p2.edge_robust = rb1.data();     // round 2: loss_function on the loop edges (:555)
+  o.max_iterations = g->iterations_limit;
+  return cvb_ba_solve(ctx, &p2, &o, r);
+}
+
+}  // extern "C"

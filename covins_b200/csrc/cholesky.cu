@@ -1,0 +1,329 @@
+// cholesky.cu — dense FP64 Cholesky factorisation + triangular solves of the reduced camera system (K8).
+//
+// Replaces the CHOLMOD factorisation inside Ceres' SPARSE_SCHUR (optimization_be.cpp:258,561,1025).  The
+// reduced camera matrix S (n = 6K or 15K) is stored dense, row-major, lower triangle significant, padded to a
+// multiple of the 128 tile.  At EuRoC scale every keyframe is covisible with hundreds of others (all agents fly
+// the same hall), so S is ~10 % block-dense before fill and a dense tiled factorisation is the right shape for
+// the GPU; this is the one BA stage that is a true GEMM and runs on the FP64 tensor cores (DMMA,
+// mma.sync.m8n8k4.f64 — tcgen05 has no FP64 kind).
+//
+// Right-looking, panel width 128:
+//   potrf_inv_kernel   1 CTA: factor the 128x128 diagonal tile in shared memory, write L, write L^-1
+//   trsm_kernel        row tiles below: A(i,k) <- A(i,k) * Linv^T            (128^3 DMMA GEMM per CTA)
+//   syrk_kernel        trailing tiles (i >= j > k): A(i,j) -= A(i,k) A(j,k)^T (128^3 DMMA GEMM per CTA)
+// Solves use the stored tile inverses: forward L y = b, backward L^T x = y, one launch per tile column.
+// All reductions have a fixed order → bit-reproducible run to run.
+#include "cvb_internal.cuh"
+
+namespace cvb_chol {
+
+constexpr int T = 128;        // tile edge
+constexpr int KC = 32;        // K chunk staged in shared memory
+constexpr int LDS = KC + 4;   // padded row stride (doubles): conflict-free m8n8k4 fragment loads
+constexpr int GEMM_THREADS = 512;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cvb_smem_addr(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// acc(128x128) = A(128xT) * B(128xT)^T, both operands row-major with K contiguous (leading dims lda, ldb).
+// 16 warps in a 4x4 grid, 32x32 per warp = 4x4 m8n8k4 tiles; K staged in chunks of 32, double buffered.
+__device__ __forceinline__ void gemm_abt_128(const double* __restrict__ A, size_t lda, const double* __restrict__ B,
+                                             size_t ldb, double (&acc)[4][4][2], double* smem) {
+  double* As[2] = {smem, smem + 2 * T * LDS};
+  double* Bs[2] = {smem + T * LDS, smem + 3 * T * LDS};
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  auto load_chunk = [&](int kc, int st) {
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      const int u = tid + it * GEMM_THREADS;  // 2048 16-byte units per operand
+      const int r = u >> 4, seg = u & 15;
+      cp_async16(As[st] + r * LDS + seg * 2, A + (size_t)r * lda + kc * KC + seg * 2);
+      cp_async16(Bs[st] + r * LDS + seg * 2, B + (size_t)r * ldb + kc * KC + seg * 2);
+    }
+    cp_async_commit();
+  };
+  constexpr int NCH = T / KC;
+  load_chunk(0, 0);
+  for (int kc = 0; kc < NCH; kc++) {
+    const int st = kc & 1;
+    if (kc + 1 < NCH) {
+      load_chunk(kc + 1, st ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const double* a_base = As[st] + (wm * 32 + (lane >> 2)) * LDS + (lane & 3);
+    const double* b_base = Bs[st] + (wn * 32 + (lane >> 2)) * LDS + (lane & 3);
+#pragma unroll
+    for (int ks = 0; ks < KC / 4; ks++) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = a_base[i * 8 * LDS + ks * 4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = b_base[j * 8 * LDS + ks * 4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+}
+
+constexpr size_t kGemmSmem = (size_t)4 * T * LDS * sizeof(double);  // 147456 B
+
+// A(i,k) <- A(i,k) * Linv_k^T for row tiles i = k+1 .. nt-1
+__global__ void __launch_bounds__(GEMM_THREADS, 1) trsm_kernel(double* __restrict__ S, size_t ld, int k,
+                                                                const double* __restrict__ linv_k) {
+  extern __shared__ __align__(16) double smem_d[];
+  const int i = k + 1 + blockIdx.x;
+  double* At = S + (size_t)i * T * ld + (size_t)k * T;
+  double acc[4][4][2];
+  gemm_abt_128(At, ld, linv_k, T, acc, smem_d);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int r = wm * 32 + a * 8 + (lane >> 2), c = wn * 32 + b * 8 + (lane & 3) * 2;
+      *reinterpret_cast<double2*>(At + (size_t)r * ld + c) = make_double2(acc[a][b][0], acc[a][b][1]);
+    }
+}
+
+// A(i,j) -= A(i,k) A(j,k)^T for all tile pairs i >= j > k; blockIdx.x enumerates the pairs of the trailing
+// (m x m) lower triangle, m = nt-k-1.
+__global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(double* __restrict__ S, size_t ld, int k, int m) {
+  extern __shared__ __align__(16) double smem_d[];
+  // unrank blockIdx.x → (ri >= rj) in the lower triangle, row-major enumeration
+  int ri = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((ri + 1) * (ri + 2) / 2 <= (int)blockIdx.x) ri++;
+  while (ri * (ri + 1) / 2 > (int)blockIdx.x) ri--;
+  const int rj = blockIdx.x - ri * (ri + 1) / 2;
+  if (ri >= m) return;
+  const int i = k + 1 + ri, j = k + 1 + rj;
+  const double* Ai = S + (size_t)i * T * ld + (size_t)k * T;
+  const double* Aj = S + (size_t)j * T * ld + (size_t)k * T;
+  double* C = S + (size_t)i * T * ld + (size_t)j * T;
+  double acc[4][4][2];
+  gemm_abt_128(Ai, ld, Aj, ld, acc, smem_d);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 2, wn = warp & 3;
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const int r = wm * 32 + a * 8 + (lane >> 2), c = wn * 32 + b * 8 + (lane & 3) * 2;
+      double2* p = reinterpret_cast<double2*>(C + (size_t)r * ld + c);
+      double2 v = *p;
+      v.x -= acc[a][b][0];
+      v.y -= acc[a][b][1];
+      *p = v;
+    }
+}
+
+// Factor the diagonal tile k in shared memory (left-looking, one thread per row), write L back, and write the
+// tile inverse (row-major, full 128x128 with zeros above the diagonal) to linv_k.  flag[0] = 1 on a
+// non-positive pivot (matrix not positive definite → caller raises mu, as Ceres does on LINEAR_SOLVER_FAILURE).
+constexpr int LDP = T + 1;
+constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)T * (T + 1) / 2) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ S, size_t ld, int k,
+                                                           double* __restrict__ linv_k, int* __restrict__ flag) {
+  extern __shared__ __align__(16) double smem_d[];
+  double* a = smem_d;               // [T][LDP]
+  double* x = smem_d + T * LDP;     // packed lower triangle of the inverse
+  const int tid = threadIdx.x;
+  double* At = S + (size_t)k * T * ld + (size_t)k * T;
+  for (int u = tid; u < T * T; u += blockDim.x) {
+    const int r = u / T, c = u % T;
+    a[r * LDP + c] = (c <= r) ? At[(size_t)r * ld + c] : 0.0;
+  }
+  __syncthreads();
+  __shared__ double piv;
+  for (int j = 0; j < T; j++) {
+    double s = 0.0;
+    const int i = tid;
+    if (i >= j && i < T) {
+      s = a[i * LDP + j];
+      for (int m = 0; m < j; m++) s -= a[i * LDP + m] * a[j * LDP + m];
+      if (i == j) {
+        if (!(s > 0.0)) {
+          flag[0] = 1;
+          s = 1.0;
+        }
+        piv = sqrt(s);
+      }
+    }
+    __syncthreads();
+    if (i >= j && i < T) a[i * LDP + j] = (i == j) ? piv : s / piv;
+    __syncthreads();
+  }
+  for (int u = tid; u < T * T; u += blockDim.x) {
+    const int r = u / T, c = u % T;
+    if (c <= r) At[(size_t)r * ld + c] = a[r * LDP + c];
+  }
+  // inverse: thread j computes column j of X = L^-1 by forward substitution
+  if (tid < T) {
+    const int j = tid;
+    for (int i = j; i < T; i++) {
+      double s = (i == j) ? 1.0 : 0.0;
+      for (int m = j; m < i; m++) s -= a[i * LDP + m] * x[m * (m + 1) / 2 + j];
+      x[i * (i + 1) / 2 + j] = s / a[i * LDP + i];
+    }
+  }
+  __syncthreads();
+  for (int u = tid; u < T * T; u += blockDim.x) {
+    const int r = u / T, c = u % T;
+    linv_k[u] = (c <= r) ? x[r * (r + 1) / 2 + c] : 0.0;
+  }
+}
+
+// forward step k: y_k = Linv_k b_k (written by CTA 0), b_i -= L(i,k) y_k for i > k (CTA i-k)
+__global__ void __launch_bounds__(T) fwd_kernel(const double* __restrict__ L, size_t ld, int k,
+                                                const double* __restrict__ linv, double* __restrict__ b,
+                                                double* __restrict__ y) {
+  __shared__ double bk[T], yk[T];
+  const int tid = threadIdx.x;
+  bk[tid] = b[(size_t)k * T + tid];
+  __syncthreads();
+  const double* li = linv + (size_t)k * T * T + (size_t)tid * T;
+  double s = 0.0;
+  for (int m = 0; m <= tid; m++) s += li[m] * bk[m];
+  yk[tid] = s;
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    y[(size_t)k * T + tid] = yk[tid];
+    return;
+  }
+  const int i = k + blockIdx.x;
+  const double* row = L + ((size_t)i * T + tid) * ld + (size_t)k * T;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int m = 0; m < T; m++) acc += row[m] * yk[m];
+  b[(size_t)i * T + tid] -= acc;
+}
+
+// backward step k: x_k = Linv_k^T y_k (CTA 0), y_i -= L(k,i)^T x_k for i < k (CTA 1+i)
+__global__ void __launch_bounds__(T) bwd_kernel(const double* __restrict__ L, size_t ld, int k,
+                                                const double* __restrict__ linv, double* __restrict__ y,
+                                                double* __restrict__ x) {
+  __shared__ double ykk[T], xk[T];
+  const int tid = threadIdx.x;
+  ykk[tid] = y[(size_t)k * T + tid];
+  __syncthreads();
+  const double* lk = linv + (size_t)k * T * T;
+  double s = 0.0;
+  for (int m = tid; m < T; m++) s += lk[(size_t)m * T + tid] * ykk[m];  // column tid of Linv (coalesced over tid)
+  xk[tid] = s;
+  __syncthreads();
+  if (blockIdx.x == 0) {
+    x[(size_t)k * T + tid] = xk[tid];
+    return;
+  }
+  const int i = blockIdx.x - 1;
+  const double* tile = L + (size_t)k * T * ld + (size_t)i * T;  // L(k,i): rows m of tile k, cols of tile i
+  double acc = 0.0;
+#pragma unroll 8
+  for (int m = 0; m < T; m++) acc += tile[(size_t)m * ld + tid] * xk[m];
+  y[(size_t)i * T + tid] -= acc;
+}
+
+int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    CVB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    CVB_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
+    attr = true;
+  }
+  const int nt = n_pad / T;
+  CVB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  for (int k = 0; k < nt; k++) {
+    potrf_inv_kernel<<<1, 256, kPotrfSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag);
+    CVB_CHECK_LAUNCH(ctx);
+    const int m = nt - k - 1;
+    if (m > 0) {
+      trsm_kernel<<<m, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T);
+      CVB_CHECK_LAUNCH(ctx);
+      syrk_kernel<<<m * (m + 1) / 2, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, m);
+      CVB_CHECK_LAUNCH(ctx);
+    }
+  }
+  return CVB_OK;
+}
+
+// solves L L^T x = b; b is destroyed, tmp is scratch (n_pad), result in x
+int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
+          cudaStream_t st) {
+  const int nt = n_pad / T;
+  for (int k = 0; k < nt; k++) {
+    fwd_kernel<<<nt - k, T, 0, st>>>(L, (size_t)n_pad, k, linv, b, tmp);
+    CVB_CHECK_LAUNCH(ctx);
+  }
+  for (int k = nt - 1; k >= 0; k--) {
+    bwd_kernel<<<k + 1, T, 0, st>>>(L, (size_t)n_pad, k, linv, tmp, x);
+    CVB_CHECK_LAUNCH(ctx);
+  }
+  return CVB_OK;
+}
+
+}  // namespace cvb_chol
+
+// ---- test/diagnostic entry: solve A x = b for a host SPD matrix (row-major n x n) with the BA factorisation ----
+extern "C" int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, const double* b, double* x,
+                                        double* factor_ms) {
+  if (!ctx || !A || !b || !x || n <= 0) return CVB_ERR_INVALID;
+  using namespace cvb_chol;
+  const int np = ((n + T - 1) / T) * T;
+  cudaStream_t st = ctx->stream;
+  double* dS = (double*)cvb_ws(ctx, WS_T, (size_t)np * np * sizeof(double));
+  double* dl = (double*)cvb_ws(ctx, WS_Q, (size_t)np * T * sizeof(double));
+  double* dv = (double*)cvb_ws(ctx, WS_OUT0, (size_t)np * 3 * sizeof(double));
+  int* dflag = (int*)cvb_ws(ctx, WS_FLAG, 16);
+  if (!dS || !dl || !dv || !dflag) return CVB_ERR_CUDA;
+  std::vector<double> hs((size_t)np * np, 0.0), hb(np, 0.0);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++) hs[(size_t)i * np + j] = A[(size_t)i * n + j];
+  for (int i = n; i < np; i++) hs[(size_t)i * np + i] = 1.0;
+  for (int i = 0; i < n; i++) hb[i] = b[i];
+  CVB_CUDA(ctx, cudaMemcpyAsync(dS, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CVB_CUDA(ctx, cudaMemcpyAsync(dv, hb.data(), np * sizeof(double), cudaMemcpyHostToDevice, st));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  int rc = factor(ctx, dS, np, dl, dflag, st);
+  cudaEventRecord(e1, st);
+  if (rc) return rc;
+  rc = solve(ctx, dS, np, dl, dv, dv + np, dv + 2 * np, st);
+  if (rc) return rc;
+  int flag = 0;
+  CVB_CUDA(ctx, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(ctx, cudaMemcpyAsync(hb.data(), dv + 2 * np, np * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(ctx, cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (factor_ms) *factor_ms = ms;
+  if (flag) return cvb_fail(ctx, CVB_ERR_NUMERIC, "matrix is not positive definite");
+  for (int i = 0; i < n; i++) x[i] = hb[i];
+  return CVB_OK;
+}

@@ -42,7 +42,8 @@ def _is_torch(x):
 
 def _torch_stream():
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    s = torch.cuda.current_stream().cuda_stream
+    return s if s else 1  # 0 would select the ctx's own stream; 1 == cudaStreamLegacy (torch's default stream)
 
 
 # ------------------------------------------------------------------------------------------------

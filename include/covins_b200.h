@@ -22,6 +22,7 @@
 #ifndef COVINS_B200_H_
 #define COVINS_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -138,6 +139,108 @@ CVB_API int cvb_landmark_match_batch_dev(cvb_ctx* ctx, const uint8_t* d_A, const
  * measure the popc issue peak): runs `iters` dependent-free XOR+POPC+ADD rounds on every SM and
  * returns giga-(32-bit popc)/s in *gpopc_per_s. */
 CVB_API int cvb_microbench_popc(cvb_ctx* ctx, int iters, double* gpopc_per_s);
+
+/* diagnostic: solve A x = b (host SPD matrix, row-major n x n) with the BA factorisation (tiled FP64 Cholesky on
+ * DMMA); *factor_ms (nullable) receives the device time of the factorisation. */
+CVB_API int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, const double* b, double* x,
+                                     double* factor_ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimisation half: flat problem format
+ * ---------------------------------------------------------------------------------------------- */
+
+/*
+ * The pointer graph the reference walks (Map → Keyframe / Landmark / LoopConstraint containers,
+ * optimization_be.cpp:75-254, 307-557, 846-1021) flattened to SoA arrays in the canonical orders of SURVEY §8c:
+ * keyframes by (client id, kf id), landmarks by id, the observations of a landmark sorted by keyframe index.
+ * All arrays are caller-owned host memory; the solver never keeps the pointers after a call returns.
+ */
+typedef struct cvb_ba_problem {
+  int32_t K, L, n_obs, n_imu, n_edge, n_cam;
+  const double* pose;         /* [K][7]  qx,qy,qz,qw,x,y,z = T_ws (keyframe_base.cpp:486-499) */
+  const double* speedbias;    /* [K][9]  v_w, b_a, b_g (keyframe_base.cpp:512-521); may be NULL when visual_only */
+  const uint8_t* pose_const;  /* [K]     1 = SetParameterBlockConstant (gauge KF, loaded / GBA-fixed KFs) */
+  const int32_t* cam_of_kf;   /* [K]     calibration index, NULL = 0 */
+  const double* extr;         /* [n_cam][7] T_sc (constant block, optimization_be.cpp:91-92) */
+  const double* intr;         /* [n_cam][4] fx, fy, cx, cy (constant) */
+  const double* dist;         /* [n_cam][4] radtan k1, k2, p1, p2 (constant) */
+  const double* lm;           /* [L][3]  world position */
+  const int32_t* lm_obs_ptr;  /* [L+1]   CSR by landmark */
+  const int32_t* obs_kf;      /* [n_obs] keyframe index */
+  const float* obs_uv;        /* [n_obs][2] distorted keypoint (keypoints_distorted_, float) */
+  const double* obs_sigma;    /* [n_obs] (octave + 1) * 2 (optimization_be.cpp:183-184) */
+  const uint8_t* obs_skip;    /* [n_obs] nullable; 1 = observation not in the problem */
+  /* IMU factor f links predecessor imu_i[f] → imu_j[f] with KF j's preintegration (optimization_be.cpp:119-143) */
+  const int32_t* imu_i;
+  const int32_t* imu_j;
+  const int32_t* imu_ptr;     /* [n_imu+1] sample ranges */
+  const double* imu_dt;       /* [samples] */
+  const double* imu_acc;      /* [samples][3] */
+  const double* imu_gyr;      /* [samples][3] */
+  const double* imu_acc0;     /* [n_imu][3] first reading (keyframe_be.cpp:187) */
+  const double* imu_gyr0;     /* [n_imu][3] */
+  const double* imu_noise;    /* [5] sigma_a_c, sigma_g_c, sigma_aw_c, sigma_gw_c, g */
+  /* 6-DoF between edges: loop constraints (GBA) or loop + successor + neighbour edges (PGO) */
+  const int32_t* edge_i;
+  const int32_t* edge_j;
+  const double* edge_q;         /* [n_edge][4] measured q_12 (x,y,z,w) */
+  const double* edge_t;         /* [n_edge][3] measured t_12 */
+  const double* edge_sqrt_info; /* [n_edge][36] row-major, rotation rows first (optimization_be.cpp:896-897) */
+  const uint8_t* edge_robust;   /* [n_edge] 1 = CauchyLoss(cauchy_edge) on this edge; NULL = none */
+} cvb_ba_problem;
+
+typedef struct cvb_ba_options {
+  int32_t max_iterations;  /* solver_options.max_num_iterations */
+  int32_t visual_only;     /* no speed-bias blocks, no IMU factors (optimization_be.cpp:90,117) */
+  double cauchy_reproj;    /* CauchyLoss parameter on reprojection residuals (1.0); <= 0: none */
+  double cauchy_edge;      /* CauchyLoss parameter on robust edges (GBA 1.0; PGO robust_loss_th 0.5) */
+  int32_t rank, world;     /* landmark-block sharding across GPUs; world <= 1: single GPU */
+} cvb_ba_options;
+
+typedef struct cvb_ba_result {
+  double* pose;            /* [K][7] out (nullable) */
+  double* speedbias;       /* [K][9] out (nullable) */
+  double* lm;              /* [L][3] out (nullable); landmarks not in the problem / owned by another rank keep the input */
+  int32_t* lm_owner;       /* [L] out (nullable): rank that optimised the landmark, -1 = not in the problem */
+  double* cost_history;    /* [cost_history_cap] out (nullable): cost after iteration 0,1,2,... */
+  uint8_t* step_status;    /* [cost_history_cap] out (nullable): 1 accepted, 2 rejected, 3 invalid, 4 converged */
+  int32_t cost_history_cap;
+  int32_t n_cost_history;
+  int32_t iterations;      /* successful + unsuccessful steps, as Ceres counts them */
+  int32_t termination;     /* 0 NO_CONVERGENCE (iteration limit), 1 gradient, 2 parameter, 3 function tolerance, 4 failure */
+  double initial_cost, final_cost;
+} cvb_ba_result;
+
+typedef struct cvb_gba_options {
+  int32_t iterations_limit;  /* covins_params::opt::gba_iteration_limit (10) */
+  int32_t visual_only;
+  int32_t outlier_removal;   /* round 1 of optimization_be.cpp:62-291 */
+  double th_outlier;         /* th_gba_outlier_global (0.92) */
+} cvb_gba_options;
+
+/* in-place sum over all ranks of `count` doubles at device pointer `ptr`, enqueued on `stream` */
+typedef int (*cvb_allreduce_fn)(void* user, void* ptr, size_t count, void* stream);
+
+typedef struct cvb_ba cvb_ba;
+
+/* Replaces the ceres::Problem + ceres::Solve of one optimisation (SPARSE_SCHUR + DOGLEG, optimization_be.cpp:257-265,
+ * 560-567, 1024-1031).  create = problem construction + iteration 0; iterate = that many trust-region iterations. */
+CVB_API int cvb_ba_create(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o, cvb_ba** out);
+CVB_API int cvb_ba_set_allreduce(cvb_ba* h, cvb_allreduce_fn fn, void* user);
+CVB_API int cvb_ba_restart(cvb_ba* h);
+CVB_API int cvb_ba_iterate(cvb_ba* h, int max_iterations, int* iterations_done);
+CVB_API int cvb_ba_result_get(cvb_ba* h, const cvb_ba_problem* p, cvb_ba_result* r);
+/* problem.Evaluate(residual_ids) of optimization_be.cpp:270-274: loss-corrected reprojection residual norm per
+ * observation at the current state (-1 for observations that are not in the problem) */
+CVB_API int cvb_ba_reproj_norms(cvb_ba* h, double* norms, int n_obs);
+CVB_API int cvb_ba_destroy(cvb_ba* h);
+CVB_API int cvb_ba_solve(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o, cvb_ba_result* r);
+
+/* Optimization::GlobalBundleAdjustment(map, iterations_limit, -, visual_only, outlier_removal, -)
+ * (optimization_be.cpp:56-618) on the flat problem; obs_removed [n_obs] (nullable) marks the observations round 1
+ * erases from the map (:285-287).  Edges are the map's loop constraints with sqrt_info diag(100 I3, 1e4 I3) (:238-240). */
+CVB_API int cvb_gba(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_gba_options* g, cvb_ba_result* r,
+                    uint8_t* obs_removed);
 
 #ifdef __cplusplus
 }

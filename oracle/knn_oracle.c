@@ -141,17 +141,22 @@ ORA_API void ora_knn_hamming_batch(const uint8_t *q, int nq, const uint8_t *t, c
 #ifdef _OPENMP
   if (threads > 0) omp_set_num_threads(threads);
 #endif
-#pragma omp parallel for schedule(dynamic, 1)
+  const int QB = 32; /* query block per task: (segment x query block) tasks keep every core busy */
+  const int nqb = (nq + QB - 1) / QB;
+#pragma omp parallel for collapse(2) schedule(dynamic, 4)
   for (int s = 0; s < n_seg; s++) {
-    const uint8_t *ts = t + (size_t)seg_ptr[s] * bytes;
-    int nt = seg_ptr[s + 1] - seg_ptr[s];
-    for (int i = 0; i < nq; i++) {
-      int32_t *ii = idx + ((size_t)s * nq + i) * k, *dd = dist + ((size_t)s * nq + i) * k;
-      for (int c = 0; c < k; c++) { ii[c] = -1; dd[c] = INT32_MAX; }
-      const uint8_t *qi = q + (size_t)i * bytes;
-      for (int j = 0; j < nt; j++) {
-        int d = hamming_bytes(qi, ts + (size_t)j * bytes, bytes);
-        klist_insert_i(ii, dd, k, j, d);
+    for (int b = 0; b < nqb; b++) {
+      const uint8_t *ts = t + (size_t)seg_ptr[s] * bytes;
+      int nt = seg_ptr[s + 1] - seg_ptr[s];
+      int i1 = (b + 1) * QB < nq ? (b + 1) * QB : nq;
+      for (int i = b * QB; i < i1; i++) {
+        int32_t *ii = idx + ((size_t)s * nq + i) * k, *dd = dist + ((size_t)s * nq + i) * k;
+        for (int c = 0; c < k; c++) { ii[c] = -1; dd[c] = INT32_MAX; }
+        const uint8_t *qi = q + (size_t)i * bytes;
+        for (int j = 0; j < nt; j++) {
+          int d = hamming_bytes(qi, ts + (size_t)j * bytes, bytes);
+          klist_insert_i(ii, dd, k, j, d);
+        }
       }
     }
   }
