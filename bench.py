@@ -100,7 +100,7 @@ def run_reference(args):
     if rank != 0:
         return
     from covins_b200 import synth
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     n_cand = 48  # bounded sample: 48 candidate KFs x 1000 x 1000 = 48 Mpair per step
     desc, _ = synth.orb_keyframes(seed=3, n_kf=n_cand + 1, n_feat=N_FEAT)
     q, cands = desc[0], desc[1:]
@@ -155,8 +155,8 @@ def cpu_baseline_match(budget_s=12.0):
     """oracle port (OpenMP, all cores) on a bounded sample of the same workload."""
     from covins_b200 import synth
     from oracle import knn as ora
-    cores = os.cpu_count() or 1
-    n_cand = 16
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    n_cand = 64
     desc, _ = synth.orb_keyframes(seed=3, n_kf=n_cand + 1, n_feat=N_FEAT)
     q, t, seg = desc[0], desc[1:].reshape(-1, 32), synth.seg_ptr_uniform(n_cand, N_FEAT)
     ora.knn_hamming_batch(q, t, seg, 2, threads=cores)

@@ -170,10 +170,10 @@ __host__ __device__ inline bool reproj(const double* pose, const double* extr, c
   const double a00 = fx * dxdx * iz, a01 = fx * dxdy * iz, a02 = -fx * (dxdx * x + dxdy * y) * iz;
   const double a10 = fy * dydx * iz, a11 = fy * dydy * iz, a12 = -fy * (dydx * x + dydy * y) * iz;
   // B = A * Rsc^T (2x3): derivative w.r.t. p_s
-  const double b00 = a00 * Rsc.m[0] + a01 * Rsc.m[3] + a02 * Rsc.m[6], b01 = a00 * Rsc.m[1] + a01 * Rsc.m[4] + a02 * Rsc.m[7],
-               b02 = a00 * Rsc.m[2] + a01 * Rsc.m[5] + a02 * Rsc.m[8];
-  const double b10 = a10 * Rsc.m[0] + a11 * Rsc.m[3] + a12 * Rsc.m[6], b11 = a10 * Rsc.m[1] + a11 * Rsc.m[4] + a12 * Rsc.m[7],
-               b12 = a10 * Rsc.m[2] + a11 * Rsc.m[5] + a12 * Rsc.m[8];
+  const double b00 = a00 * Rsc.m[0] + a01 * Rsc.m[1] + a02 * Rsc.m[2], b01 = a00 * Rsc.m[3] + a01 * Rsc.m[4] + a02 * Rsc.m[5],
+               b02 = a00 * Rsc.m[6] + a01 * Rsc.m[7] + a02 * Rsc.m[8];
+  const double b10 = a10 * Rsc.m[0] + a11 * Rsc.m[1] + a12 * Rsc.m[2], b11 = a10 * Rsc.m[3] + a11 * Rsc.m[4] + a12 * Rsc.m[5],
+               b12 = a10 * Rsc.m[6] + a11 * Rsc.m[7] + a12 * Rsc.m[8];
   // Jl = B * Rws^T
   Jl[0] = b00 * Rws.m[0] + b01 * Rws.m[1] + b02 * Rws.m[2];
   Jl[1] = b00 * Rws.m[3] + b01 * Rws.m[4] + b02 * Rws.m[5];
