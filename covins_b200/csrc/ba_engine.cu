@@ -1591,6 +1591,23 @@ int cvb_ba_reproj_norms(cvb_ba* h, double* norms, int n_obs) {
   return engine_corrected_norms(h->E, norms, n_obs);
 }
 
+// diagnostic: copy an internal vector ([camera part n_c_pad | landmark part 3 L_in]) to the host.
+// which: 0 scale, 1 colsq, 2 diag, 3 gradient g, 4 grad/diag, 5 gn, 6 step, 7 x (linear solve), 8 reduced rhs
+int cvb_ba_debug_vector(cvb_ba* h, int which, double* out, int64_t cap, int64_t* n_cam_pad, int64_t* n_total) {
+  if (!h) return CVB_ERR_INVALID;
+  Engine& E = h->E;
+  const DevArr<double>* v[] = {&E.scale, &E.colsq, &E.diag, &E.gvec, &E.grad, &E.gn, &E.step, &E.xsol, &E.gs};
+  if (which < 0 || which > 8) return CVB_ERR_INVALID;
+  if (n_cam_pad) *n_cam_pad = E.n_c_pad;
+  if (n_total) *n_total = E.n_vec;
+  const int64_t n = cap < E.n_vec ? cap : E.n_vec;
+  if (out && n > 0) {
+    if (cudaMemcpyAsync(out, v[which]->p, n * sizeof(double), cudaMemcpyDeviceToHost, E.st) != cudaSuccess) return CVB_ERR_CUDA;
+    cudaStreamSynchronize(E.st);
+  }
+  return CVB_OK;
+}
+
 int cvb_ba_destroy(cvb_ba* h) {
   if (h) {
     cudaStreamSynchronize(h->E.st);

@@ -134,7 +134,7 @@ __host__ __device__ inline void cauchy(double s, double a2, double* scale, doubl
 }
 
 // ---- reprojection: r (2), Jl = dr/dp_w (2x3, row-major), Jp = dr/d[dtheta,dp] (2x6).  Returns false if the
-// point is not in front of the camera (Z <= 1e-9): the residual is then defined as zero with zero Jacobian.
+// point is not in front of the camera (Z <= 1e-10): the residual is then defined as zero with zero Jacobian.
 __host__ __device__ inline bool reproj(const double* pose, const double* extr, const double* intr, const double* dist,
                                        const double* lm, double u_obs, double v_obs, double sigma, double r[2],
                                        double Jp[12], double Jl[6], bool want_jac) {
@@ -143,7 +143,7 @@ __host__ __device__ inline bool reproj(const double* pose, const double* extr, c
   const V3 d = V3{lm[0], lm[1], lm[2]} - Pw.t;
   const V3 ps = mulT(Rws, d);
   const V3 pc = mulT(Rsc, ps - Ps.t);
-  if (!(pc.z > 1e-9)) {
+  if (!(pc.z > 1e-10)) {   // aslam::ProjectionResult::POINT_BEHIND_CAMERA [A]
     r[0] = r[1] = 0.0;
     if (want_jac) {
       for (int i = 0; i < 12; i++) Jp[i] = 0.0;

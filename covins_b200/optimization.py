@@ -150,6 +150,14 @@ class BaSolver:
         self.ctx.check(lib().cvb_ba_reproj_norms(self.h, out.ctypes.data, self.flat.n_obs))
         return out[:self.flat.n_obs]
 
+    def debug_vector(self, which: int):
+        """(camera part [K*per], landmark part [3*L_in]) of an internal vector; see cvb_ba_debug_vector."""
+        ncp = C.c_int64(); nt = C.c_int64()
+        self.ctx.check(lib().cvb_ba_debug_vector(self.h, which, None, 0, C.byref(ncp), C.byref(nt)))
+        out = np.zeros(nt.value)
+        self.ctx.check(lib().cvb_ba_debug_vector(self.h, which, out.ctypes.data, nt.value, None, None))
+        return out[:ncp.value], out[ncp.value:]
+
     def result(self):
         res = _Res(self.flat.K, self.flat.L)
         self.ctx.check(lib().cvb_ba_result_get(self.h, C.byref(self.flat.s), C.byref(res.r)))

@@ -18,7 +18,8 @@ Restated pieces
   problem construction   optimization_be.cpp:296-557 (GBA round 2), :62-254 (round 1), :833-1031 (PGO)
   state layout           keyframe_base.cpp:486-521: pose [qx,qy,qz,qw,x,y,z] = T_ws, speed-bias [v,ba,bg]
   Plus [A]               PoseQuaternionLocalParameterization: delta = [dtheta, dp], q+ = Exp(dtheta) * q, p+ = p + dp
-  reprojection [A]       GlobalEuclideanReprError<Pinhole,RadTan>: r = (pi(T_sc^-1 T_ws^-1 p_w) - kp) / sigma,
+  reprojection [A]       GlobalEuclideanReprError<Pinhole,RadTan>: r = (pi(T_sc^-1 T_ws^-1 p_w) - kp) / sigma; a point
+                         behind the camera (z < 1e-10, aslam POINT_BEHIND_CAMERA) gives zero residual and Jacobian;
                          sigma = 2 (octave + 1) (optimization_be.cpp:183-184, 477-478)
   between [A]            SixDofBetweenError(kImu): e = sqrt_info [2 vec(q_m^-1 q_1^-1 q_2); R_1^T (t_2 - t_1) - t_m],
                          rotation first (pinned by how :896-897 / :239-240 fill sqrt_info)
@@ -85,7 +86,10 @@ def reproj_residual(pose, lm, extr, intr, dist, uv, sigma):
     q_ws, t_ws = pose[..., :4], pose[..., 4:]
     p_s = qrot(qconj(q_ws), lm - t_ws)
     p_c = qrot(qconj(extr[..., :4]), p_s - extr[..., 4:])
-    x, y = p_c[..., 0] / p_c[..., 2], p_c[..., 1] / p_c[..., 2]
+    # aslam::ProjectionResult POINT_BEHIND_CAMERA (z < 1e-10): the error term zeroes residual and Jacobians [A]
+    front = p_c[..., 2] > 1e-10
+    zs = torch.where(front, p_c[..., 2], torch.ones_like(p_c[..., 2]))
+    x, y = p_c[..., 0] / zs, p_c[..., 1] / zs
     k1, k2, p1, p2 = dist.unbind(-1)
     r2 = x * x + y * y
     rad = 1 + k1 * r2 + k2 * r2 * r2
@@ -93,7 +97,8 @@ def reproj_residual(pose, lm, extr, intr, dist, uv, sigma):
     yd = y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
     u = intr[..., 0] * xd + intr[..., 2]
     v = intr[..., 1] * yd + intr[..., 3]
-    return torch.stack([(u - uv[..., 0]) / sigma, (v - uv[..., 1]) / sigma], -1)
+    r = torch.stack([(u - uv[..., 0]) / sigma, (v - uv[..., 1]) / sigma], -1)
+    return torch.where(front[..., None], r, torch.zeros_like(r))
 
 
 def between_residual(pose1, pose2, q_m, t_m, sqrt_info):
