@@ -63,6 +63,7 @@ SIGNATURES = {
     "cvb_ba_result_get": (C.c_int, [c_vp, c_vp, c_vp]),
     "cvb_ba_reproj_norms": (C.c_int, [c_vp, c_vp, C.c_int]),
     "cvb_ba_debug_vector": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "cvb_ba_timing": (C.c_int, [c_vp, c_f64p, C.c_int]),
     "cvb_ba_destroy": (C.c_int, [c_vp]),
     "cvb_ba_solve": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "cvb_gba": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),

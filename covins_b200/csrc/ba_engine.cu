@@ -114,6 +114,11 @@ struct Engine {
   std::vector<double> cost_hist;
   std::vector<int> step_status;
   std::function<int(void*, size_t)> allreduce;   // (device ptr, count of doubles) in-place sum over ranks
+  // phase timing (CUDA events on the engine stream): 0 linearise, 1 block build + Schur, 2 Cholesky factor,
+  // 3 triangular solves + back-substitution, 4 dogleg / J*step / plus / candidate cost
+  cudaEvent_t ev[8] = {};
+  double phase_ms[5] = {0, 0, 0, 0, 0};
+  double chol_flops = 0.0;
   ~Engine() {
     for (int i = 0; i < 2; i++) { pose[i].free_(); sb[i].free_(); lm[i].free_(); }
     pose_const.free_(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
@@ -128,6 +133,7 @@ struct Engine {
     xsol.free_(); yb.free_(); gs.free_(); tmp.free_(); S.free_(); linv.free_(); flag.free_(); partials.free_();
     scalars.free_();
     if (h_scalars) cudaFreeHost(h_scalars);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
   }
 };
 
@@ -1160,6 +1166,7 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   if ((rc = zalloc(E, E.linv, (size_t)E.n_c_pad * cvb_chol::T))) return rc;
   if ((rc = zalloc(E, E.partials, (size_t)RED_SLOTS * RED_BLOCKS)) || (rc = zalloc(E, E.scalars, RED_SLOTS))) return rc;
   ENG_CUDA(cudaMallocHost(&E.h_scalars, RED_SLOTS * sizeof(double)));
+  for (auto& e : E.ev) ENG_CUDA(cudaEventCreate(&e));
   ENG_CUDA(cudaStreamSynchronize(E.st));
   return CVB_OK;
 }
@@ -1183,6 +1190,12 @@ int evaluate(Engine& E, int b, int mode, double* cost_out) {
   return CVB_OK;
 }
 
+
+inline void tick(Engine& E, int i) { cudaEventRecord(E.ev[i], E.st); }
+inline void tock(Engine& E, int a, int b, int phase) {   // both events must have completed (call after a stream sync)
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, E.ev[a], E.ev[b]) == cudaSuccess) E.phase_ms[phase] += ms;
+}
 
 // ---- per-linearisation blocks -----------------------------------------------------------------------------------
 int lm_blocks(Engine& E) {
@@ -1228,6 +1241,7 @@ int cam_colsq(Engine& E) {
 // damped Schur complement + Cholesky for the given mu; *ok = false if the factorisation broke down
 int factor_rcs(Engine& E, double mu, bool* ok) {
   const size_t ld = (size_t)E.n_c_pad;
+  tick(E, 0);
   if (E.L_in > 0) {
     lm_damp_inv_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.Hll.p, E.colsq.p + E.n_c_pad, mu, E.HllInv.p);
     ENG_LAUNCH();
@@ -1251,11 +1265,16 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
   if ((rc = ar(E, E.yb.p, ld))) return rc;
   cam_finish_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, ld, E.S.p, E.diag.p, E.gvec.p, E.yb.p, E.gs.p, mu);
   ENG_LAUNCH();
+  tick(E, 1);
   rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.st);
   if (rc) return rc;
+  tick(E, 2);
   int flag = 0;
   ENG_CUDA(cudaMemcpyAsync(&flag, E.flag.p, sizeof(int), cudaMemcpyDeviceToHost, E.st));
   ENG_CUDA(cudaStreamSynchronize(E.st));
+  tock(E, 0, 1, 1);
+  tock(E, 1, 2, 2);
+  E.chol_flops += (double)E.n_c_pad * E.n_c_pad * E.n_c_pad / 3.0;
   *ok = (flag & 1) == 0;
   return CVB_OK;
 }
@@ -1301,6 +1320,7 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
   *solver_ok = true;
   *grad_converged = false;
   int rc;
+  tick(E, 5);
   if ((rc = cam_blocks(E))) return rc;
   if ((rc = ar(E, E.gvec.p, (size_t)E.n_c_pad))) return rc;
   if ((rc = cam_colsq(E))) return rc;
@@ -1321,8 +1341,10 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
   jv_factor_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.Jimu.p, E.rimu.p, E.n_edge, E.edge_i.p,
                                                  E.edge_j.p, E.Jedge.p, E.redge.p, E.sgrad.p, E.per, E.partials.p, 5);
   ENG_LAUNCH();
+  tick(E, 6);
   bool cam_fresh = true;
   bool solved = false;
+  bool first_try = true;
   while (E.mu < MAX_MU) {
     if (!cam_fresh) {
       if ((rc = cam_blocks(E))) return rc;
@@ -1330,11 +1352,14 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
     }
     bool ok = false;
     if ((rc = factor_rcs(E, E.mu, &ok))) return rc;
+    if (first_try) tock(E, 5, 6, 1);
+    first_try = false;
     cam_fresh = false;
     if (!ok) {
       E.mu *= MU_INC;
       continue;
     }
+    tick(E, 3);
     if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.st))) return rc;
     if (E.L_in > 0) {
       backsub_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.lm_ptr.p, E.obs_kf.p, E.wy.p, E.HllInv.p, E.bl.p, E.xsol.p, E.per,
@@ -1348,8 +1373,10 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
     reduce_final<<<1, 256, 0, E.st>>>(E.partials.p, E.scalars.p, 7, 0);
     ENG_LAUNCH();
     if ((rc = ar(E, E.scalars.p, 7))) return rc;
+    tick(E, 4);
     ENG_CUDA(cudaMemcpyAsync(E.h_scalars, E.scalars.p, RED_SLOTS * sizeof(double), cudaMemcpyDeviceToHost, E.st));
     ENG_CUDA(cudaStreamSynchronize(E.st));
+    tock(E, 3, 4, 3);
     if (!std::isfinite(E.h_scalars[0])) {
       E.mu *= MU_INC;
       continue;
@@ -1402,6 +1429,7 @@ int engine_iterate(Engine& E, bool* done) {
       const double beta = (c <= 0) ? (d - c) / bma2 : (E.radius * E.radius - a2) / (d + c);
       ca = -E.alpha * (1.0 - beta); cb = beta;
     }
+    tick(E, 5);
     dogleg_combine_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_vec, ca, cb, E.grad.p, E.gn.p, E.diag.p, E.scale.p, E.step.p,
                                                         E.n_c_pad, E.rank == 0 ? 1.0 : 0.0, E.partials.p, 0);
     ENG_LAUNCH();
@@ -1417,7 +1445,9 @@ int engine_iterate(Engine& E, bool* done) {
                                               E.pose[E.cur].p, E.sb[E.cur].p, E.lm[E.cur].p, E.pose[nxt].p, E.sb[nxt].p,
                                               E.lm[nxt].p, E.rank == 0 ? 1.0 : 0.0, E.partials.p, 5);
     ENG_LAUNCH();
+    tick(E, 6);
     if ((rc = read_scalars(E, 7))) return rc;
+    tock(E, 5, 6, 4);
     const double dl2 = E.h_scalars[0];
     const double jv2 = E.h_scalars[1] + E.h_scalars[3], jvr = E.h_scalars[2] + E.h_scalars[4];
     const double step2 = E.h_scalars[5], cand_x2 = E.h_scalars[6];
@@ -1426,7 +1456,11 @@ int engine_iterate(Engine& E, bool* done) {
     if (model_change > 0.0) {
       E.invalid_run = 0;
       double ccost;
+      tick(E, 5);
       if ((rc = evaluate(E, nxt, 1, &ccost))) return rc;
+      tick(E, 6);
+      cudaEventSynchronize(E.ev[6]);
+      tock(E, 5, 6, 4);
       const double step_norm = std::sqrt(step2);
       if (step_norm <= 1e-8 * (E.x_norm + 1e-8)) {
         E.termination = TERM_PARAMETER; E.step_status.push_back(STEP_CONVERGED); *done = true;
@@ -1442,7 +1476,11 @@ int engine_iterate(Engine& E, bool* done) {
         E.cost = ccost;
         E.x_norm = std::sqrt(cand_x2);
         double c2;
+        tick(E, 5);
         if ((rc = linearize(E, &c2))) return rc;
+        tick(E, 6);
+        cudaEventSynchronize(E.ev[6]);
+        tock(E, 5, 6, 0);
         if (rho < 0.25) E.radius *= 0.5;
         if (rho > 0.75) E.radius = std::max(E.radius, 3.0 * E.dogleg_norm);
         E.mu = std::max(MIN_MU, 2.0 * E.mu / MU_INC);
@@ -1604,6 +1642,20 @@ int cvb_ba_debug_vector(cvb_ba* h, int which, double* out, int64_t cap, int64_t*
   if (out && n > 0) {
     if (cudaMemcpyAsync(out, v[which]->p, n * sizeof(double), cudaMemcpyDeviceToHost, E.st) != cudaSuccess) return CVB_ERR_CUDA;
     cudaStreamSynchronize(E.st);
+  }
+  return CVB_OK;
+}
+
+// accumulated device time per phase (ms): [0] linearise, [1] block build + Schur, [2] Cholesky factorisation,
+// [3] triangular solves + back-substitution, [4] dogleg / J*step / plus / candidate cost; [5] = dense-equivalent
+// factorisation flops (n^3/3 per factorisation).  reset != 0 clears the counters after reading.
+int cvb_ba_timing(cvb_ba* h, double out[6], int reset) {
+  if (!h || !out) return CVB_ERR_INVALID;
+  for (int i = 0; i < 5; i++) out[i] = h->E.phase_ms[i];
+  out[5] = h->E.chol_flops;
+  if (reset) {
+    for (int i = 0; i < 5; i++) h->E.phase_ms[i] = 0.0;
+    h->E.chol_flops = 0.0;
   }
   return CVB_OK;
 }

@@ -158,6 +158,12 @@ class BaSolver:
         self.ctx.check(lib().cvb_ba_debug_vector(self.h, which, out.ctypes.data, nt.value, None, None))
         return out[:ncp.value], out[ncp.value:]
 
+    def timing(self, reset=True):
+        out = (C.c_double * 6)()
+        self.ctx.check(lib().cvb_ba_timing(self.h, out, int(reset)))
+        return dict(linearize_ms=out[0], build_schur_ms=out[1], factor_ms=out[2], solve_ms=out[3], step_ms=out[4],
+                    factor_flops=out[5])
+
     def result(self):
         res = _Res(self.flat.K, self.flat.L)
         self.ctx.check(lib().cvb_ba_result_get(self.h, C.byref(self.flat.s), C.byref(res.r)))
@@ -173,6 +179,51 @@ class BaSolver:
             self.close()
         except Exception:
             pass
+
+
+def torch_allreduce():
+    """All-reduce callback for BaSolver(world > 1): sums `count` doubles at a device pointer over the default
+    torch.distributed group (NCCL over NVLink), ordered on the engine's stream.  This is the only exchange of the
+    GBA data path: the reduced normal equations (S, g_c, y_b) and a handful of scalars per iteration."""
+    import torch
+    import torch.distributed as dist
+
+    class _Ptr:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    def fn(user, ptr, count, stream):
+        try:
+            ext = torch.cuda.ExternalStream(stream)
+            with torch.cuda.stream(ext):
+                t = torch.as_tensor(_Ptr(ptr, count), device="cuda")
+                # NCCL caps a single call's element count comfortably above 2^31 bytes, but chunk anyway for safety
+                step = 1 << 28
+                for a in range(0, count, step):
+                    dist.all_reduce(t[a:a + step])
+            return 0
+        except Exception as e:  # never let an exception cross the C boundary
+            print("allreduce callback failed:", e, flush=True)
+            return 1
+    return fn
+
+
+def lm_owner_of_rank(n_included: int, world: int):
+    """Landmark-block sharding rule of the engine: the i-th landmark that is in the problem belongs to rank i % world."""
+    return np.arange(n_included) % max(world, 1)
+
+
+def merge_sharded_landmarks(results: list):
+    """Combine per-rank results of a sharded solve: poses/speed-biases are replicated, each landmark is taken from
+    the rank that owns it (result['lm_owner'])."""
+    out = dict(results[0])
+    lm = results[0]["lm"].copy()
+    owner = results[0]["lm_owner"]
+    for r, res in enumerate(results):
+        m = owner == r
+        lm[m] = res["lm"][m]
+    out["lm"] = lm
+    return out
 
 
 def global_bundle_adjustment(ctx: Context, p: dict, iterations_limit=10, visual_only=False, outlier_removal=True,

@@ -236,6 +236,10 @@ CVB_API int cvb_ba_reproj_norms(cvb_ba* h, double* norms, int n_obs);
 /* diagnostic: internal vector [camera part n_c_pad | landmark part]: 0 Jacobi scale, 1 column sq-norms, 2 dogleg
  * diagonal, 3 gradient, 4 gradient/diag, 5 Gauss-Newton step (scaled), 6 trust-region step, 7 linear-solve x, 8 reduced rhs */
 CVB_API int cvb_ba_debug_vector(cvb_ba* h, int which, double* out, int64_t cap, int64_t* n_cam_pad, int64_t* n_total);
+/* accumulated device time (ms, CUDA events) per phase: [0] linearise, [1] block build + Schur, [2] Cholesky factor,
+ * [3] triangular solves + back-substitution, [4] dogleg / J*step / Plus / candidate cost; [5] dense-equivalent
+ * factorisation flops.  reset != 0 clears the counters. */
+CVB_API int cvb_ba_timing(cvb_ba* h, double out[6], int reset);
 CVB_API int cvb_ba_destroy(cvb_ba* h);
 CVB_API int cvb_ba_solve(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o, cvb_ba_result* r);
 

@@ -38,7 +38,7 @@ def _compare(got, ref, p, lm_mask=None):
     assert got["iterations"] == ref["iterations"], (got["iterations"], ref["iterations"], got["termination"], ref["termination"])
     assert got["steps"] == [s[0].replace("func_tol", "converged").replace("param_tol", "converged") for s in ref["steps"]]
     rc = np.array(ref["cost"])
-    assert np.allclose(got["cost"][:len(rc)], rc, rtol=1e-8, atol=0), (got["cost"], rc)
+    assert np.allclose(got["cost"][:len(rc)], rc, rtol=1e-6, atol=0), (got["cost"], rc)
     assert _rel(got["pose"], ref["pose"].numpy()) < RTOL
     assert _rel(got["speedbias"], ref["sb"].numpy()) < RTOL
     if p.get("L", 0):
@@ -87,7 +87,7 @@ def test_pgo_matches_oracle(ctx):
     got = O.pose_graph_optimization(ctx, p, edges, iterations=10)
     assert got["iterations"] == ref["result"]["iterations"]
     assert _rel(got["pose"], ref["pose"]) < RTOL
-    assert np.allclose(got["cost"], ref["result"]["cost"], rtol=1e-8)
+    assert np.allclose(got["cost"], ref["result"]["cost"], rtol=1e-6)
     assert got["final_cost"] < 0.8 * got["initial_cost"]
 
 
