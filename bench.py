@@ -100,7 +100,7 @@ def run_reference(args):
     if rank != 0:
         return
     from covins_b200 import synth
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    cores = _cores()
     n_cand = 48  # bounded sample: 48 candidate KFs x 1000 x 1000 = 48 Mpair per step
     desc, _ = synth.orb_keyframes(seed=3, n_kf=n_cand + 1, n_feat=N_FEAT)
     q, cands = desc[0], desc[1:]
@@ -155,7 +155,15 @@ WORKLOAD = ("C3 5-agent EuRoC-sized synthetic map (2000 KF / 100k LM / ~800k obs
 
 
 def _cores():
-    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    """usable host cores: affinity mask capped by the cgroup CPU quota (the GPU boxes expose 128 CPUs with a 16-core quota)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
 
 
 def cpu_baseline_match(budget_s=10.0):
@@ -388,7 +396,7 @@ def run_ours(args):
         "match": match,
     }
     if rank == 0:
-        if world == 1:
+        if world == 1 and not os.environ.get("COVINS_SKIP_CPU_BASELINE"):
             line["cpu_baseline"] = cpu_baseline_gba(3)
             line["match"]["cpu_baseline"] = cpu_baseline_match()
         print(json.dumps(line))
