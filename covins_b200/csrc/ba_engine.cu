@@ -28,13 +28,9 @@
 #include <vector>
 
 #include "ba_math.cuh"
+#include "cholesky.cuh"
 #include "cvb_internal.cuh"
 
-namespace cvb_chol {
-constexpr int T = 128;
-int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, cudaStream_t st);
-int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x, cudaStream_t st);
-}  // namespace cvb_chol
 
 namespace {
 
@@ -46,6 +42,13 @@ struct ObsLin {
 struct ObsWY {
   double W[18], Y[18];
 };
+
+// Column of (keyframe kf, local parameter c) in the reduced camera system: c < 6 pose, c >= 6 speed-bias.  The
+// speed-bias blocks are ordered FIRST (off_sb < off_pose): along the IMU chain they form a block-banded system whose
+// elimination costs almost nothing in the tile-sparse Cholesky, leaving only the dense 6K pose part.
+__device__ __forceinline__ int cam_col(const int* __restrict__ off_pose, const int* __restrict__ off_sb, int kf, int c) {
+  return c < 6 ? off_pose[kf] + c : off_sb[kf] + (c - 6);
+}
 
 constexpr int RED_BLOCKS = 512;   // fixed grid for reducing kernels → fixed summation order
 constexpr int RED_SLOTS = 8;
@@ -80,6 +83,9 @@ struct Engine {
   // device state (double buffered)
   DevArr<double> pose[2], sb[2], lm[2];
   DevArr<uint8_t> pose_const;
+  DevArr<int> off_pose, off_sb;
+  std::vector<int> h_off_pose, h_off_sb;
+  cvb_chol::TilePlan plan;
   DevArr<double> extr_kf, intr_kf, dist_kf;
   DevArr<int> obs_kf, obs_lm, lm_ptr, kf_ptr, kf_obs;
   DevArr<double> obs_uv, obs_sigma;
@@ -121,7 +127,7 @@ struct Engine {
   double chol_flops = 0.0;
   ~Engine() {
     for (int i = 0; i < 2; i++) { pose[i].free_(); sb[i].free_(); lm[i].free_(); }
-    pose_const.free_(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
+    pose_const.free_(); off_pose.free_(); off_sb.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
     obs_kf.free_(); obs_lm.free_(); lm_ptr.free_(); kf_ptr.free_(); kf_obs.free_(); obs_uv.free_(); obs_sigma.free_();
     lin.free_(); wy.free_(); Hll.free_(); HllInv.free_(); bl.free_();
     pre.free_(); imu_i.free_(); imu_j.free_(); Jimu.free_(); rimu.free_();
@@ -185,7 +191,8 @@ __global__ void __launch_bounds__(256) lin_obs_kernel(int n_obs, const int* __re
                                                       const double* __restrict__ pose, const double* __restrict__ lm,
                                                       const double* __restrict__ extr_kf, const double* __restrict__ intr_kf,
                                                       const double* __restrict__ dist_kf, const double* __restrict__ scale,
-                                                      int per, int n_c_pad, double a2, int mode, ObsLin* __restrict__ lin,
+                                                      const int* __restrict__ off_pose, int n_c_pad, double a2, int mode,
+                                                      ObsLin* __restrict__ lin,
                                                       ObsWY* __restrict__ wy, double* __restrict__ norms,
                                                       double* __restrict__ partials, int slot) {
   double csum[1] = {0.0};
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(256) lin_obs_kernel(int n_obs, const int* __re
     ObsLin rec;
     rec.r[0] = r[0] * sc;
     rec.r[1] = r[1] * sc;
-    const double* sp = scale + (size_t)k * per;
+    const double* sp = scale + off_pose[k];
     const double* sl = scale + n_c_pad + 3 * (size_t)l;
 #pragma unroll
     for (int c2 = 0; c2 < 6; c2++) {
@@ -298,8 +305,8 @@ __global__ void obs_Y_kernel(int n_obs, const int* __restrict__ obs_lm, const do
 __global__ void __launch_bounds__(128) kf_visual_kernel(int K, const int* __restrict__ kf_ptr, const int* __restrict__ kf_obs,
                                                         const int* __restrict__ obs_lm, const ObsLin* __restrict__ lin,
                                                         const ObsWY* __restrict__ wy, const double* __restrict__ bl,
-                                                        int per, size_t ld, double* __restrict__ S, double* __restrict__ g_c,
-                                                        double* __restrict__ yb, int what) {
+                                                        const int* __restrict__ off_pose, size_t ld, double* __restrict__ S,
+                                                        double* __restrict__ g_c, double* __restrict__ yb, int what) {
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (k >= K) return;
   double h[21], b[6], y[6];
@@ -336,17 +343,14 @@ __global__ void __launch_bounds__(128) kf_visual_kernel(int K, const int* __rest
     }
   }
   if (lane == 0) {
+    const size_t base = (size_t)off_pose[k];
     if (what == 0) {
       int idx = 0;
       for (int r = 0; r < 6; r++)
-        for (int c = 0; c <= r; c++) {
-          S[((size_t)k * per + r) * ld + (size_t)k * per + c] = h[idx];
-          if (c != r) S[((size_t)k * per + c) * ld + (size_t)k * per + r] = h[idx];
-          idx++;
-        }
-      for (int r = 0; r < 6; r++) g_c[(size_t)k * per + r] = b[r];
+        for (int c = 0; c <= r; c++) S[(base + r) * ld + base + c] = h[idx++];   // lower triangle only
+      for (int r = 0; r < 6; r++) g_c[base + r] = b[r];
     } else {
-      for (int r = 0; r < 6; r++) yb[(size_t)k * per + r] = y[r];
+      for (int r = 0; r < 6; r++) yb[base + r] = y[r];
     }
   }
 }
@@ -510,7 +514,8 @@ __global__ void imu_repropagate_kernel(int n_imu, const int* __restrict__ imu_j,
 // IMU factor: whitened residual (15) and whitened, Jacobi-scaled Jacobian (15x30); mode 1: cost only
 __global__ void __launch_bounds__(256) lin_imu_kernel(int n_imu, const int* __restrict__ imu_i, const int* __restrict__ imu_j,
                                const ImuPre* __restrict__ pre, const double* __restrict__ pose, const double* __restrict__ sb,
-                               const double* __restrict__ scale, int per, double g, int mode, double* __restrict__ Jout,
+                               const double* __restrict__ scale, const int* __restrict__ off_pose,
+                               const int* __restrict__ off_sb, double g, int mode, double* __restrict__ Jout,
                                double* __restrict__ rout, double* __restrict__ partials, int slot) {
   double csum[1] = {0.0};
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_imu; f += gridDim.x * blockDim.x) {
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(256) lin_imu_kernel(int n_imu, const int* __re
     for (int a = 0; a < 15; a++) rout[15 * (size_t)f + a] = rw[a];
     for (int c = 0; c < 30; c++) {
       const int kf = c < 15 ? i : j;
-      const double sc = scale[(size_t)kf * per + (c < 15 ? c : c - 15)];
+      const double sc = scale[cam_col(off_pose, off_sb, kf, c < 15 ? c : c - 15)];
       for (int a = 0; a < 15; a++) {
         double v = 0;
         for (int m = a; m < 15; m++) v += W[15 * a + m] * Jraw[30 * m + c];
@@ -545,7 +550,8 @@ __global__ void __launch_bounds__(256) lin_imu_kernel(int n_imu, const int* __re
 // K6: between factor
 __global__ void __launch_bounds__(256) lin_edge_kernel(int n_edge, const int* __restrict__ ei, const int* __restrict__ ej, const double* __restrict__ eq,
                                 const double* __restrict__ et, const double* __restrict__ eS, const uint8_t* __restrict__ robust,
-                                const double* __restrict__ pose, const double* __restrict__ scale, int per, double a2, int mode,
+                                const double* __restrict__ pose, const double* __restrict__ scale,
+                                const int* __restrict__ off_pose, double a2, int mode,
                                 double* __restrict__ Jout, double* __restrict__ rout, double* __restrict__ partials, int slot) {
   double csum[1] = {0.0};
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edge; e += gridDim.x * blockDim.x) {
@@ -562,26 +568,31 @@ __global__ void __launch_bounds__(256) lin_edge_kernel(int n_edge, const int* __
     for (int a = 0; a < 6; a++)
       for (int c2 = 0; c2 < 12; c2++) {
         const int kf = c2 < 6 ? i : j;
-        Jout[(size_t)e * 72 + 12 * a + c2] = J[12 * a + c2] * sc * scale[(size_t)kf * per + (c2 < 6 ? c2 : c2 - 6)];
+        Jout[(size_t)e * 72 + 12 * a + c2] = J[12 * a + c2] * sc * scale[off_pose[kf] + (c2 < 6 ? c2 : c2 - 6)];
       }
   }
   const int slots[1] = {slot};
   block_reduce_store<1>(csum, partials, slots);
 }
 
-// gather J^T J of IMU (type 0, 15 cols per role) and edge (type 1, 6 cols per role) factors into S, and J^T r into g_c
+// gather J^T J of IMU (type 0, 15 cols per role) and edge (type 1, 6 cols per role) factors into the lower triangle of
+// S, and J^T r into g_c.  One CTA per destination (keyframe hi >= keyframe lo) block, thread (r, c) owns one entry and
+// sums its terms in list order.  Because speed-bias columns precede pose columns, an entry whose mapped row index is
+// above its column index is stored at the mirrored position; for hi == lo only r >= c is processed.
 __global__ void __launch_bounds__(256) factor_gather_kernel(int n_fb, const int* __restrict__ fb_hi, const int* __restrict__ fb_lo,
                                                             const int* __restrict__ fb_ptr, const int* __restrict__ ft_type,
                                                             const int* __restrict__ ft_fac, const int* __restrict__ ft_rhi,
                                                             const int* __restrict__ ft_rlo, const double* __restrict__ Jimu,
                                                             const double* __restrict__ rimu, const double* __restrict__ Jedge,
-                                                            const double* __restrict__ redge, int per, size_t ld,
+                                                            const double* __restrict__ redge, const int* __restrict__ off_pose,
+                                                            const int* __restrict__ off_sb, int per, size_t ld,
                                                             double* __restrict__ S, double* __restrict__ g_c) {
   const int b = blockIdx.x;
   if (b >= n_fb) return;
   const int hi = fb_hi[b], lo = fb_lo[b];
   const int r = threadIdx.x / 15, c = threadIdx.x % 15;
   if (r >= 15) return;
+  if (hi == lo && c > r) return;
   double acc = 0.0, gacc = 0.0;
   for (int t = fb_ptr[b]; t < fb_ptr[b + 1]; t++) {
     const int type = ft_type[t], f = ft_fac[t];
@@ -598,8 +609,12 @@ __global__ void __launch_bounds__(256) factor_gather_kernel(int n_fb, const int*
     acc += s;
     gacc += gs;
   }
-  if (r < per && c < per) S[((size_t)hi * per + r) * ld + (size_t)lo * per + c] += acc;
-  if (hi == lo && c == 0 && r < per) g_c[(size_t)hi * per + r] += gacc;
+  if (r < per && c < per) {
+    int ri = cam_col(off_pose, off_sb, hi, r), ci = cam_col(off_pose, off_sb, lo, c);
+    if (ri < ci) { const int t2 = ri; ri = ci; ci = t2; }
+    S[(size_t)ri * ld + ci] += acc;
+  }
+  if (hi == lo && c == 0 && r < per) g_c[cam_col(off_pose, off_sb, hi, r)] += gacc;
 }
 
 // camera part, step 1: colsq = diag(J^T J) (before damping / Schur)
@@ -634,8 +649,8 @@ __global__ void cam_finish_kernel(int n_c_pad, const double* __restrict__ scale,
 // K7: S(hi,lo) -= sum over (a,b) pairs of Y_a W_b^T, one warp per block
 __global__ void __launch_bounds__(128) schur_kernel(int n_sb, const int* __restrict__ sb_hi, const int* __restrict__ sb_lo,
                                                     const int* __restrict__ sb_ptr, const int* __restrict__ sp_a,
-                                                    const int* __restrict__ sp_b, const ObsWY* __restrict__ wy, int per,
-                                                    size_t ld, double* __restrict__ S) {
+                                                    const int* __restrict__ sp_b, const ObsWY* __restrict__ wy,
+                                                    const int* __restrict__ off_pose, size_t ld, double* __restrict__ S) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= n_sb) return;
   double acc[36];
@@ -664,20 +679,20 @@ __global__ void __launch_bounds__(128) schur_kernel(int n_sb, const int* __restr
 #pragma unroll
     for (int i = 0; i < 36; i++)
       if (i == e) v = acc[i];
-    S[((size_t)hi * per + r) * ld + (size_t)lo * per + c] -= v;
+    S[((size_t)off_pose[hi] + r) * ld + (size_t)off_pose[lo] + c] -= v;
   }
 }
 
 // landmark back-substitution: x_l = Hll^-1 (b_l - sum W^T x_c)
 __global__ void backsub_kernel(int L, const int* __restrict__ lm_ptr, const int* __restrict__ obs_kf,
                                const ObsWY* __restrict__ wy, const double* __restrict__ HllInv, const double* __restrict__ bl,
-                               const double* __restrict__ xc, int per, double* __restrict__ xl) {
+                               const double* __restrict__ xc, const int* __restrict__ off_pose, double* __restrict__ xl) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
   if (l >= L) return;
   double t[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
   for (int o = lm_ptr[l]; o < lm_ptr[l + 1]; o++) {
     const double* W = wy[o].W;
-    const double* x = xc + (size_t)obs_kf[o] * per;
+    const double* x = xc + off_pose[obs_kf[o]];
 #pragma unroll
     for (int a = 0; a < 6; a++) {
       t[0] -= W[3 * a] * x[a];
@@ -695,12 +710,13 @@ __global__ void backsub_kernel(int L, const int* __restrict__ lm_ptr, const int*
 // J * v over all residual blocks: sums (Jv)^2 and (Jv).r
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) jv_obs_kernel(int n_obs, const int* __restrict__ obs_kf, const int* __restrict__ obs_lm,
-                                                     const ObsLin* __restrict__ lin, const double* __restrict__ v, int per,
-                                                     int n_c_pad, double* __restrict__ partials, int slot0) {
+                                                     const ObsLin* __restrict__ lin, const double* __restrict__ v,
+                                                     const int* __restrict__ off_pose, int n_c_pad,
+                                                     double* __restrict__ partials, int slot0) {
   double s[2] = {0.0, 0.0};
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
     const ObsLin& L = lin[o];
-    const double* vp = v + (size_t)obs_kf[o] * per;
+    const double* vp = v + off_pose[obs_kf[o]];
     const double* vl = v + n_c_pad + 3 * (size_t)obs_lm[o];
     double j0 = 0, j1 = 0;
 #pragma unroll
@@ -718,14 +734,18 @@ __global__ void __launch_bounds__(256) jv_factor_kernel(int n_imu, const int* __
                                                         const double* __restrict__ Jimu, const double* __restrict__ rimu,
                                                         int n_edge, const int* __restrict__ ei, const int* __restrict__ ej,
                                                         const double* __restrict__ Jedge, const double* __restrict__ redge,
-                                                        const double* __restrict__ v, int per, double* __restrict__ partials,
+                                                        const double* __restrict__ v, const int* __restrict__ off_pose,
+                                                        const int* __restrict__ off_sb, double* __restrict__ partials,
                                                         int slot0) {
   double s[2] = {0.0, 0.0};
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_imu + n_edge; t += gridDim.x * blockDim.x) {
     if (t < n_imu) {
       const double* J = Jimu + (size_t)t * 450;
-      const double* vi = v + (size_t)imu_i[t] * per;
-      const double* vj = v + (size_t)imu_j[t] * per;
+      double vi[15], vj[15];
+      for (int c = 0; c < 15; c++) {
+        vi[c] = v[cam_col(off_pose, off_sb, imu_i[t], c)];
+        vj[c] = v[cam_col(off_pose, off_sb, imu_j[t], c)];
+      }
       for (int a = 0; a < 15; a++) {
         double jv = 0;
         for (int c = 0; c < 15; c++) jv += J[30 * a + c] * vi[c] + J[30 * a + 15 + c] * vj[c];
@@ -735,8 +755,8 @@ __global__ void __launch_bounds__(256) jv_factor_kernel(int n_imu, const int* __
     } else {
       const int e = t - n_imu;
       const double* J = Jedge + (size_t)e * 72;
-      const double* vi = v + (size_t)ei[e] * per;
-      const double* vj = v + (size_t)ej[e] * per;
+      const double* vi = v + off_pose[ei[e]];
+      const double* vj = v + off_pose[ej[e]];
       for (int a = 0; a < 6; a++) {
         double jv = 0;
         for (int c = 0; c < 6; c++) jv += J[12 * a + c] * vi[c] + J[12 * a + 6 + c] * vj[c];
@@ -801,7 +821,8 @@ __global__ void __launch_bounds__(256) dogleg_combine_kernel(int n_vec, double c
 }
 
 // candidate = Plus(current, step * scale); sums |cand - cur|^2 (ambient) and |cand|^2 over non-constant blocks
-__global__ void __launch_bounds__(256) plus_kernel(int K, int L, int per, int n_c_pad, int visual_only,
+__global__ void __launch_bounds__(256) plus_kernel(int K, int L, const int* __restrict__ off_pose, const int* __restrict__ off_sb,
+                                                   int n_c_pad, int visual_only,
                                                    const uint8_t* __restrict__ pose_const, const double* __restrict__ step,
                                                    const double* __restrict__ scale, const double* __restrict__ pose,
                                                    const double* __restrict__ sb, const double* __restrict__ lm,
@@ -813,7 +834,7 @@ __global__ void __launch_bounds__(256) plus_kernel(int K, int L, int per, int n_
       const int k = t;
       double d[6], out[7];
       const bool cst = pose_const[k] != 0;
-      for (int c = 0; c < 6; c++) d[c] = cst ? 0.0 : step[(size_t)k * per + c] * scale[(size_t)k * per + c];
+      for (int c = 0; c < 6; c++) d[c] = cst ? 0.0 : step[off_pose[k] + c] * scale[off_pose[k] + c];
       if (cst) {
         for (int c = 0; c < 7; c++) out[c] = pose[7 * k + c];
       } else {
@@ -828,7 +849,7 @@ __global__ void __launch_bounds__(256) plus_kernel(int K, int L, int per, int n_
       for (int c = 0; c < 9; c++) {
         double v = sb[9 * k + c];
         if (!visual_only) {
-          const double dd = step[(size_t)k * per + 6 + c] * scale[(size_t)k * per + 6 + c];
+          const double dd = step[off_sb[k] + c] * scale[off_sb[k] + c];
           v += dd;
           s[0] += cam_w * dd * dd;
           s[1] += cam_w * v * v;
@@ -975,8 +996,51 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   E.L_in = (int)E.lm_of_compact.size();
   E.n_obs = (int)h_obs_kf.size();
   E.n_c = K * E.per;
-  E.n_c_pad = ((E.n_c + cvb_chol::T - 1) / cvb_chol::T) * cvb_chol::T;
+  // column layout of the reduced camera system: [speed-bias blocks (9 each, keyframe order) | pad to a tile | pose
+  // blocks (6 each)] — see cam_col()
+  const int TT = cvb_chol::T;
+  const int n_sb_pad = E.visual_only ? 0 : ((9 * K + TT - 1) / TT) * TT;
+  E.h_off_pose.resize(K); E.h_off_sb.resize(K);
+  for (int k = 0; k < K; k++) {
+    E.h_off_sb[k] = E.visual_only ? 0 : 9 * k;
+    E.h_off_pose[k] = n_sb_pad + 6 * k;
+  }
+  E.n_c_pad = ((n_sb_pad + 6 * K + TT - 1) / TT) * TT;
   E.n_vec = E.n_c_pad + 3 * E.L_in;
+  auto col_of = [&](int kf, int c) { return c < 6 ? E.h_off_pose[kf] + c : E.h_off_sb[kf] + (c - 6); };
+  // ---- tile-level structure of S (every rank needs the structure of the WHOLE problem: S is all-reduced) ----
+  const int nt = E.n_c_pad / TT;
+  std::vector<uint8_t> tmask((size_t)nt * nt, 0);
+  auto mark = [&](int a0, int alen, int b0, int blen) {
+    for (int ta = a0 / TT; ta <= (a0 + alen - 1) / TT; ta++)
+      for (int tb = b0 / TT; tb <= (b0 + blen - 1) / TT; tb++) tmask[(size_t)std::max(ta, tb) * nt + std::min(ta, tb)] = 1;
+  };
+  for (int l = 0; l < p->L; l++) {
+    if (lm_compact[l] < 0) continue;
+    for (int a = p->lm_obs_ptr[l]; a < p->lm_obs_ptr[l + 1]; a++) {
+      if (p->obs_skip && p->obs_skip[a]) continue;
+      for (int b = p->lm_obs_ptr[l]; b <= a; b++) {
+        if (p->obs_skip && p->obs_skip[b]) continue;
+        mark(E.h_off_pose[p->obs_kf[a]], 6, E.h_off_pose[p->obs_kf[b]], 6);
+      }
+    }
+  }
+  if (!E.visual_only)
+    for (int f = 0; f < p->n_imu; f++) {
+      const int ij[2] = {p->imu_i[f], p->imu_j[f]};
+      for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++) {
+          mark(E.h_off_pose[ij[a]], 6, E.h_off_pose[ij[b]], 6);
+          mark(E.h_off_pose[ij[a]], 6, E.h_off_sb[ij[b]], 9);
+          mark(E.h_off_sb[ij[a]], 9, E.h_off_sb[ij[b]], 9);
+        }
+    }
+  for (int e = 0; e < p->n_edge; e++) {
+    mark(E.h_off_pose[p->edge_i[e]], 6, E.h_off_pose[p->edge_j[e]], 6);
+    mark(E.h_off_pose[p->edge_i[e]], 6, E.h_off_pose[p->edge_i[e]], 6);
+    mark(E.h_off_pose[p->edge_j[e]], 6, E.h_off_pose[p->edge_j[e]], 6);
+  }
+  E.plan.build(nt, tmask);
   // ---- by-keyframe CSR ----
   std::vector<int> h_kf_ptr(K + 1, 0), h_kf_obs(E.n_obs);
   for (int ob = 0; ob < E.n_obs; ob++) h_kf_ptr[h_obs_kf[ob] + 1]++;
@@ -1151,14 +1215,16 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   std::vector<double> h_scale(E.n_vec, 0.0);
   for (int k = 0; k < K; k++) {
     if (!p->pose_const[k])
-      for (int c = 0; c < 6; c++) h_scale[(size_t)k * E.per + c] = 1.0;
+      for (int c = 0; c < 6; c++) h_scale[(size_t)col_of(k, c)] = 1.0;
     if (!E.visual_only)
-      for (int c = 6; c < 15; c++) h_scale[(size_t)k * E.per + c] = 1.0;
+      for (int c = 6; c < 15; c++) h_scale[(size_t)col_of(k, c)] = 1.0;
   }
   for (int c = 0; c < E.L_in; c++)   // landmark blocks are owned by rank (c % world); others stay inactive here
     if (c % E.world == E.rank)
       for (int a = 0; a < 3; a++) h_scale[(size_t)E.n_c_pad + 3 * (size_t)c + a] = 1.0;
   if ((rc = upload(E, E.scale, h_scale))) return rc;
+  if ((rc = upload(E, E.off_pose, E.h_off_pose)) || (rc = upload(E, E.off_sb, E.h_off_sb))) return rc;
+  if ((rc = E.plan.upload(E.ctx, E.st))) return rc;
   DevArr<double>* vecs[] = {&E.colsq, &E.diag, &E.gvec, &E.grad, &E.sgrad, &E.gn, &E.step, &E.xsol, &E.yb, &E.gs, &E.tmp};
   for (auto* v : vecs)
     if ((rc = zalloc(E, *v, (size_t)E.n_vec))) return rc;
@@ -1175,14 +1241,14 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
 int evaluate(Engine& E, int b, int mode, double* cost_out) {
   const int rg = RED_BLOCKS;
   lin_obs_kernel<<<rg, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.obs_uv.p, E.obs_sigma.p, E.pose[b].p, E.lm[b].p,
-                                       E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.scale.p, E.per, E.n_c_pad, E.a2_reproj, mode,
+                                       E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.scale.p, E.off_pose.p, E.n_c_pad, E.a2_reproj, mode,
                                        E.lin.p, E.wy.p, nullptr, E.partials.p, 0);
   ENG_LAUNCH();
-  lin_imu_kernel<<<rg, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.pre.p, E.pose[b].p, E.sb[b].p, E.scale.p, E.per, E.g,
+  lin_imu_kernel<<<rg, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.pre.p, E.pose[b].p, E.sb[b].p, E.scale.p, E.off_pose.p, E.off_sb.p, E.g,
                                        mode, E.Jimu.p, E.rimu.p, E.partials.p, 1);
   ENG_LAUNCH();
   lin_edge_kernel<<<rg, 256, 0, E.st>>>(E.n_edge, E.edge_i.p, E.edge_j.p, E.edge_q.p, E.edge_t.p, E.edge_S.p, E.edge_robust.p,
-                                        E.pose[b].p, E.scale.p, E.per, E.a2_edge, mode, E.Jedge.p, E.redge.p, E.partials.p, 2);
+                                        E.pose[b].p, E.scale.p, E.off_pose.p, E.a2_edge, mode, E.Jedge.p, E.redge.p, E.partials.p, 2);
   ENG_LAUNCH();
   int rc = read_scalars(E, 3);
   if (rc) return rc;
@@ -1221,11 +1287,11 @@ int cam_blocks(Engine& E) {
   ENG_CUDA(cudaMemsetAsync(E.S.p, 0, ld * ld * sizeof(double), E.st));
   ENG_CUDA(cudaMemsetAsync(E.gvec.p, 0, ld * sizeof(double), E.st));
   kf_visual_kernel<<<grid1((size_t)E.K * 32, 128), 128, 0, E.st>>>(E.K, E.kf_ptr.p, E.kf_obs.p, E.obs_lm.p, E.lin.p, E.wy.p,
-                                                                  E.bl.p, E.per, ld, E.S.p, E.gvec.p, E.yb.p, 0);
+                                                                  E.bl.p, E.off_pose.p, ld, E.S.p, E.gvec.p, E.yb.p, 0);
   ENG_LAUNCH();
   if (E.n_fb > 0) {
     factor_gather_kernel<<<E.n_fb, 256, 0, E.st>>>(E.n_fb, E.fb_hi.p, E.fb_lo.p, E.fb_ptr.p, E.ft_type.p, E.ft_fac.p,
-                                                   E.ft_rhi.p, E.ft_rlo.p, E.Jimu.p, E.rimu.p, E.Jedge.p, E.redge.p, E.per, ld,
+                                                   E.ft_rhi.p, E.ft_rlo.p, E.Jimu.p, E.rimu.p, E.Jedge.p, E.redge.p, E.off_pose.p, E.off_sb.p, E.per, ld,
                                                    E.S.p, E.gvec.p);
     ENG_LAUNCH();
   }
@@ -1252,11 +1318,11 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
   }
   ENG_CUDA(cudaMemsetAsync(E.yb.p, 0, ld * sizeof(double), E.st));
   kf_visual_kernel<<<grid1((size_t)E.K * 32, 128), 128, 0, E.st>>>(E.K, E.kf_ptr.p, E.kf_obs.p, E.obs_lm.p, E.lin.p, E.wy.p,
-                                                                  E.bl.p, E.per, ld, E.S.p, E.gvec.p, E.yb.p, 1);
+                                                                  E.bl.p, E.off_pose.p, ld, E.S.p, E.gvec.p, E.yb.p, 1);
   ENG_LAUNCH();
   if (E.n_sb > 0) {
     schur_kernel<<<grid1((size_t)E.n_sb * 32, 128), 128, 0, E.st>>>(E.n_sb, E.sb_hi.p, E.sb_lo.p, E.sb_ptr.p, E.sp_a.p,
-                                                                   E.sp_b.p, E.wy.p, E.per, ld, E.S.p);
+                                                                   E.sp_b.p, E.wy.p, E.off_pose.p, ld, E.S.p);
     ENG_LAUNCH();
   }
   // the one exchange of the data path: sum the rank-partial reduced normal equations over NVLink
@@ -1266,7 +1332,7 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
   cam_finish_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, ld, E.S.p, E.diag.p, E.gvec.p, E.yb.p, E.gs.p, mu);
   ENG_LAUNCH();
   tick(E, 1);
-  rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.st);
+  rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st);
   if (rc) return rc;
   tick(E, 2);
   int flag = 0;
@@ -1274,7 +1340,7 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
   ENG_CUDA(cudaStreamSynchronize(E.st));
   tock(E, 0, 1, 1);
   tock(E, 1, 2, 2);
-  E.chol_flops += (double)E.n_c_pad * E.n_c_pad * E.n_c_pad / 3.0;
+  E.chol_flops += E.plan.flops;
   *ok = (flag & 1) == 0;
   return CVB_OK;
 }
@@ -1301,7 +1367,7 @@ int engine_begin(Engine& E) {
   // |x| over the non-constant parameter blocks
   ENG_CUDA(cudaMemsetAsync(E.step.p, 0, (size_t)E.n_vec * sizeof(double), E.st));
   const int nxt = E.cur ^ 1;
-  plus_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.K, E.L_in, E.per, E.n_c_pad, E.visual_only, E.pose_const.p, E.step.p, E.scale.p,
+  plus_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.K, E.L_in, E.off_pose.p, E.off_sb.p, E.n_c_pad, E.visual_only, E.pose_const.p, E.step.p, E.scale.p,
                                             E.pose[E.cur].p, E.sb[E.cur].p, E.lm[E.cur].p, E.pose[nxt].p, E.sb[nxt].p,
                                             E.lm[nxt].p, E.rank == 0 ? 1.0 : 0.0, E.partials.p, 0);
   ENG_LAUNCH();
@@ -1335,11 +1401,11 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
   max_final_kernel<<<1, 1, 0, E.st>>>(E.partials.p, E.scalars.p, 7);
   ENG_LAUNCH();
   // Cauchy point: alpha = |grad|^2 / |J (grad / diag)|^2
-  jv_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.lin.p, E.sgrad.p, E.per, E.n_c_pad,
+  jv_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.lin.p, E.sgrad.p, E.off_pose.p, E.n_c_pad,
                                               E.partials.p, 3);
   ENG_LAUNCH();
   jv_factor_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.Jimu.p, E.rimu.p, E.n_edge, E.edge_i.p,
-                                                 E.edge_j.p, E.Jedge.p, E.redge.p, E.sgrad.p, E.per, E.partials.p, 5);
+                                                 E.edge_j.p, E.Jedge.p, E.redge.p, E.sgrad.p, E.off_pose.p, E.off_sb.p, E.partials.p, 5);
   ENG_LAUNCH();
   tick(E, 6);
   bool cam_fresh = true;
@@ -1360,9 +1426,9 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
       continue;
     }
     tick(E, 3);
-    if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.st))) return rc;
+    if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st))) return rc;
     if (E.L_in > 0) {
-      backsub_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.lm_ptr.p, E.obs_kf.p, E.wy.p, E.HllInv.p, E.bl.p, E.xsol.p, E.per,
+      backsub_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.lm_ptr.p, E.obs_kf.p, E.wy.p, E.HllInv.p, E.bl.p, E.xsol.p, E.off_pose.p,
                                                       E.xsol.p + E.n_c_pad);
       ENG_LAUNCH();
     }
@@ -1433,15 +1499,15 @@ int engine_iterate(Engine& E, bool* done) {
     dogleg_combine_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_vec, ca, cb, E.grad.p, E.gn.p, E.diag.p, E.scale.p, E.step.p,
                                                         E.n_c_pad, E.rank == 0 ? 1.0 : 0.0, E.partials.p, 0);
     ENG_LAUNCH();
-    jv_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.lin.p, E.step.p, E.per, E.n_c_pad,
+    jv_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.lin.p, E.step.p, E.off_pose.p, E.n_c_pad,
                                                 E.partials.p, 1);
     ENG_LAUNCH();
     jv_factor_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.Jimu.p, E.rimu.p, E.n_edge, E.edge_i.p,
-                                                   E.edge_j.p, E.Jedge.p, E.redge.p, E.step.p, E.per, E.partials.p, 3);
+                                                   E.edge_j.p, E.Jedge.p, E.redge.p, E.step.p, E.off_pose.p, E.off_sb.p, E.partials.p, 3);
     ENG_LAUNCH();
     // candidate state + its cost in the same sync
     const int nxt = E.cur ^ 1;
-    plus_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.K, E.L_in, E.per, E.n_c_pad, E.visual_only, E.pose_const.p, E.step.p, E.scale.p,
+    plus_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.K, E.L_in, E.off_pose.p, E.off_sb.p, E.n_c_pad, E.visual_only, E.pose_const.p, E.step.p, E.scale.p,
                                               E.pose[E.cur].p, E.sb[E.cur].p, E.lm[E.cur].p, E.pose[nxt].p, E.sb[nxt].p,
                                               E.lm[nxt].p, E.rank == 0 ? 1.0 : 0.0, E.partials.p, 5);
     ENG_LAUNCH();
@@ -1513,7 +1579,7 @@ int engine_corrected_norms(Engine& E, double* h_norms_full, int n_obs_full) {
   DevArr<double> d;
   if (d.alloc((size_t)E.n_obs)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed");
   lin_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.obs_uv.p, E.obs_sigma.p, E.pose[E.cur].p,
-                                               E.lm[E.cur].p, E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.scale.p, E.per, E.n_c_pad,
+                                               E.lm[E.cur].p, E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.scale.p, E.off_pose.p, E.n_c_pad,
                                                E.a2_reproj, 2, E.lin.p, E.wy.p, d.p, E.partials.p, 0);
   ENG_LAUNCH();
   std::vector<double> h(E.n_obs);
@@ -1631,17 +1697,22 @@ int cvb_ba_reproj_norms(cvb_ba* h, double* norms, int n_obs) {
 
 // diagnostic: copy an internal vector ([camera part n_c_pad | landmark part 3 L_in]) to the host.
 // which: 0 scale, 1 colsq, 2 diag, 3 gradient g, 4 grad/diag, 5 gn, 6 step, 7 x (linear solve), 8 reduced rhs
-int cvb_ba_debug_vector(cvb_ba* h, int which, double* out, int64_t cap, int64_t* n_cam_pad, int64_t* n_total) {
+int cvb_ba_debug_vector(cvb_ba* h, int which, double* out, int64_t cap, int64_t* n_cam, int64_t* n_total) {
   if (!h) return CVB_ERR_INVALID;
   Engine& E = h->E;
   const DevArr<double>* v[] = {&E.scale, &E.colsq, &E.diag, &E.gvec, &E.grad, &E.gn, &E.step, &E.xsol, &E.gs};
   if (which < 0 || which > 8) return CVB_ERR_INVALID;
-  if (n_cam_pad) *n_cam_pad = E.n_c_pad;
-  if (n_total) *n_total = E.n_vec;
-  const int64_t n = cap < E.n_vec ? cap : E.n_vec;
-  if (out && n > 0) {
-    if (cudaMemcpyAsync(out, v[which]->p, n * sizeof(double), cudaMemcpyDeviceToHost, E.st) != cudaSuccess) return CVB_ERR_CUDA;
+  const int64_t nc = (int64_t)E.K * E.per, tot = nc + 3 * (int64_t)E.L_in;
+  if (n_cam) *n_cam = nc;
+  if (n_total) *n_total = tot;
+  if (out && cap >= tot) {
+    std::vector<double> hv((size_t)E.n_vec);
+    if (cudaMemcpyAsync(hv.data(), v[which]->p, hv.size() * sizeof(double), cudaMemcpyDeviceToHost, E.st) != cudaSuccess)
+      return CVB_ERR_CUDA;
     cudaStreamSynchronize(E.st);
+    for (int k = 0; k < E.K; k++)       // canonical order: keyframe-major [pose 6 | speed-bias 9]
+      for (int c = 0; c < E.per; c++) out[(size_t)k * E.per + c] = hv[c < 6 ? E.h_off_pose[k] + c : E.h_off_sb[k] + (c - 6)];
+    for (int64_t i = 0; i < 3 * (int64_t)E.L_in; i++) out[nc + i] = hv[(size_t)E.n_c_pad + i];
   }
   return CVB_OK;
 }

@@ -13,11 +13,10 @@
 //   syrk_kernel        trailing tiles (i >= j > k): A(i,j) -= A(i,k) A(j,k)^T (128^3 DMMA GEMM per CTA)
 // Solves use the stored tile inverses: forward L y = b, backward L^T x = y, one launch per tile column.
 // All reductions have a fixed order → bit-reproducible run to run.
-#include "cvb_internal.cuh"
+#include "cholesky.cuh"
 
 namespace cvb_chol {
 
-constexpr int T = 128;        // tile edge
 constexpr int KC = 32;        // K chunk staged in shared memory
 constexpr int LDS = KC + 4;   // padded row stride (doubles): conflict-free m8n8k4 fragment loads
 constexpr int GEMM_THREADS = 512;
@@ -90,11 +89,12 @@ __device__ __forceinline__ void gemm_abt_128(const double* __restrict__ A, size_
 
 constexpr size_t kGemmSmem = (size_t)4 * T * LDS * sizeof(double);  // 147456 B
 
-// A(i,k) <- A(i,k) * Linv_k^T for row tiles i = k+1 .. nt-1
+// A(i,k) <- A(i,k) * Linv_k^T for the structurally non-zero row tiles i of tile column k (rows[])
 __global__ void __launch_bounds__(GEMM_THREADS, 1) trsm_kernel(double* __restrict__ S, size_t ld, int k,
-                                                                const double* __restrict__ linv_k) {
+                                                                const double* __restrict__ linv_k,
+                                                                const int* __restrict__ rows) {
   extern __shared__ __align__(16) double smem_d[];
-  const int i = k + 1 + blockIdx.x;
+  const int i = rows[blockIdx.x];
   double* At = S + (size_t)i * T * ld + (size_t)k * T;
   double acc[4][4][2];
   gemm_abt_128(At, ld, linv_k, T, acc, smem_d);
@@ -108,17 +108,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trsm_kernel(double* __restric
     }
 }
 
-// A(i,j) -= A(i,k) A(j,k)^T for all tile pairs i >= j > k; blockIdx.x enumerates the pairs of the trailing
-// (m x m) lower triangle, m = nt-k-1.
-__global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(double* __restrict__ S, size_t ld, int k, int m) {
+// A(i,j) -= A(i,k) A(j,k)^T for the tile pairs (i >= j) of column k's non-zero rows: pi[]/pj[] enumerate them.
+__global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(double* __restrict__ S, size_t ld, int k,
+                                                                const int* __restrict__ pi, const int* __restrict__ pj) {
   extern __shared__ __align__(16) double smem_d[];
-  // unrank blockIdx.x → (ri >= rj) in the lower triangle, row-major enumeration
-  int ri = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
-  while ((ri + 1) * (ri + 2) / 2 <= (int)blockIdx.x) ri++;
-  while (ri * (ri + 1) / 2 > (int)blockIdx.x) ri--;
-  const int rj = blockIdx.x - ri * (ri + 1) / 2;
-  if (ri >= m) return;
-  const int i = k + 1 + ri, j = k + 1 + rj;
+  const int i = pi[blockIdx.x], j = pj[blockIdx.x];
   const double* Ai = S + (size_t)i * T * ld + (size_t)k * T;
   const double* Aj = S + (size_t)j * T * ld + (size_t)k * T;
   double* C = S + (size_t)i * T * ld + (size_t)j * T;
@@ -198,7 +192,7 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ 
 // forward step k: y_k = Linv_k b_k (written by CTA 0), b_i -= L(i,k) y_k for i > k (CTA i-k)
 __global__ void __launch_bounds__(T) fwd_kernel(const double* __restrict__ L, size_t ld, int k,
                                                 const double* __restrict__ linv, double* __restrict__ b,
-                                                double* __restrict__ y) {
+                                                double* __restrict__ y, const int* __restrict__ rows) {
   __shared__ double bk[T], yk[T];
   const int tid = threadIdx.x;
   bk[tid] = b[(size_t)k * T + tid];
@@ -212,7 +206,7 @@ __global__ void __launch_bounds__(T) fwd_kernel(const double* __restrict__ L, si
     y[(size_t)k * T + tid] = yk[tid];
     return;
   }
-  const int i = k + blockIdx.x;
+  const int i = rows[blockIdx.x - 1];
   const double* row = L + ((size_t)i * T + tid) * ld + (size_t)k * T;
   double acc = 0.0;
 #pragma unroll 8
@@ -220,10 +214,10 @@ __global__ void __launch_bounds__(T) fwd_kernel(const double* __restrict__ L, si
   b[(size_t)i * T + tid] -= acc;
 }
 
-// backward step k: x_k = Linv_k^T y_k (CTA 0), y_i -= L(k,i)^T x_k for i < k (CTA 1+i)
+// backward step k: x_k = Linv_k^T y_k (CTA 0), y_i -= L(k,i)^T x_k for the non-zero column tiles i < k of row k (cols[])
 __global__ void __launch_bounds__(T) bwd_kernel(const double* __restrict__ L, size_t ld, int k,
                                                 const double* __restrict__ linv, double* __restrict__ y,
-                                                double* __restrict__ x) {
+                                                double* __restrict__ x, const int* __restrict__ cols) {
   __shared__ double ykk[T], xk[T];
   const int tid = threadIdx.x;
   ykk[tid] = y[(size_t)k * T + tid];
@@ -237,7 +231,7 @@ __global__ void __launch_bounds__(T) bwd_kernel(const double* __restrict__ L, si
     x[(size_t)k * T + tid] = xk[tid];
     return;
   }
-  const int i = blockIdx.x - 1;
+  const int i = cols[blockIdx.x - 1];
   const double* tile = L + (size_t)k * T * ld + (size_t)i * T;  // L(k,i): rows m of tile k, cols of tile i
   double acc = 0.0;
 #pragma unroll 8
@@ -245,7 +239,62 @@ __global__ void __launch_bounds__(T) bwd_kernel(const double* __restrict__ L, si
   y[(size_t)i * T + tid] -= acc;
 }
 
-int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, cudaStream_t st) {
+// Symbolic phase (host): tile-level structure of L from the tile-level structure of S (lower, nt x nt, row-major
+// bools, diagonal forced).  Right-looking elimination: the non-zero rows of column k become a clique.
+void TilePlan::build(int nt_, std::vector<uint8_t> mask) {
+  nt = nt_;
+  h_col_ptr.assign(1, 0); h_row_idx.clear(); h_pair_ptr.assign(1, 0); h_pair_i.clear(); h_pair_j.clear();
+  for (int k = 0; k < nt; k++) mask[(size_t)k * nt + k] = 1;
+  for (int k = 0; k < nt; k++) {
+    std::vector<int> rows;
+    for (int i = k + 1; i < nt; i++)
+      if (mask[(size_t)i * nt + k]) rows.push_back(i);
+    for (size_t a = 0; a < rows.size(); a++)
+      for (size_t b = 0; b <= a; b++) {
+        mask[(size_t)rows[a] * nt + rows[b]] = 1;
+        h_pair_i.push_back(rows[a]);
+        h_pair_j.push_back(rows[b]);
+      }
+    h_row_idx.insert(h_row_idx.end(), rows.begin(), rows.end());
+    h_col_ptr.push_back((int)h_row_idx.size());
+    h_pair_ptr.push_back((int)h_pair_i.size());
+  }
+  h_rowc_ptr.assign(1, 0); h_rowc_idx.clear();
+  for (int k = 0; k < nt; k++) {
+    for (int i = 0; i < k; i++)
+      if (mask[(size_t)k * nt + i]) h_rowc_idx.push_back(i);
+    h_rowc_ptr.push_back((int)h_rowc_idx.size());
+  }
+  n_tiles_L = (long)h_row_idx.size() + nt;
+  // flops actually executed: one 128^3 GEMM (2 flop per MAC) per trsm tile and per syrk pair
+  flops = 2.0 * T * T * T * ((double)h_row_idx.size() + (double)h_pair_i.size());
+}
+
+int TilePlan::upload(cvb_ctx* ctx, cudaStream_t st) {
+  release();
+  auto up = [&](int** d, const std::vector<int>& h) -> int {
+    const size_t n = h.size() ? h.size() : 1;
+    CVB_CUDA(ctx, cudaMalloc(d, n * sizeof(int)));
+    if (h.size()) CVB_CUDA(ctx, cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    return CVB_OK;
+  };
+  int rc;
+  if ((rc = up(&d_row_idx, h_row_idx)) || (rc = up(&d_pair_i, h_pair_i)) || (rc = up(&d_pair_j, h_pair_j)) ||
+      (rc = up(&d_rowc_idx, h_rowc_idx)))
+    return rc;
+  CVB_CUDA(ctx, cudaStreamSynchronize(st));
+  return CVB_OK;
+}
+
+void TilePlan::release() {
+  if (d_row_idx) cudaFree(d_row_idx);
+  if (d_pair_i) cudaFree(d_pair_i);
+  if (d_pair_j) cudaFree(d_pair_j);
+  if (d_rowc_idx) cudaFree(d_rowc_idx);
+  d_row_idx = d_pair_i = d_pair_j = d_rowc_idx = nullptr;
+}
+
+int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
@@ -254,15 +303,19 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, cudaSt
     attr = true;
   }
   const int nt = n_pad / T;
+  CVB_REQUIRE(ctx, plan.nt == nt, "tile plan does not match the matrix");
   CVB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
   for (int k = 0; k < nt; k++) {
     potrf_inv_kernel<<<1, 256, kPotrfSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag);
     CVB_CHECK_LAUNCH(ctx);
-    const int m = nt - k - 1;
+    const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
     if (m > 0) {
-      trsm_kernel<<<m, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T);
+      trsm_kernel<<<m, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T,
+                                                      plan.d_row_idx + plan.h_col_ptr[k]);
       CVB_CHECK_LAUNCH(ctx);
-      syrk_kernel<<<m * (m + 1) / 2, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, m);
+      const int np = plan.h_pair_ptr[k + 1] - plan.h_pair_ptr[k];
+      syrk_kernel<<<np, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, plan.d_pair_i + plan.h_pair_ptr[k],
+                                                       plan.d_pair_j + plan.h_pair_ptr[k]);
       CVB_CHECK_LAUNCH(ctx);
     }
   }
@@ -271,14 +324,16 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, cudaSt
 
 // solves L L^T x = b; b is destroyed, tmp is scratch (n_pad), result in x
 int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
-          cudaStream_t st) {
+          const TilePlan& plan, cudaStream_t st) {
   const int nt = n_pad / T;
   for (int k = 0; k < nt; k++) {
-    fwd_kernel<<<nt - k, T, 0, st>>>(L, (size_t)n_pad, k, linv, b, tmp);
+    const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
+    fwd_kernel<<<1 + m, T, 0, st>>>(L, (size_t)n_pad, k, linv, b, tmp, plan.d_row_idx + plan.h_col_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
   for (int k = nt - 1; k >= 0; k--) {
-    bwd_kernel<<<k + 1, T, 0, st>>>(L, (size_t)n_pad, k, linv, tmp, x);
+    const int m = plan.h_rowc_ptr[k + 1] - plan.h_rowc_ptr[k];
+    bwd_kernel<<<1 + m, T, 0, st>>>(L, (size_t)n_pad, k, linv, tmp, x, plan.d_rowc_idx + plan.h_rowc_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
   return CVB_OK;
@@ -308,11 +363,21 @@ extern "C" int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, co
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
+  // tile structure of the input (zero tiles are skipped) → symbolic fill
+  const int nt = np / T;
+  std::vector<uint8_t> mask((size_t)nt * nt, 0);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++)
+      if (hs[(size_t)i * np + j] != 0.0) mask[(size_t)(i / T) * nt + (j / T)] = 1;
+  TilePlan plan;
+  plan.build(nt, mask);
+  int rc = plan.upload(ctx, st);
+  if (rc) return rc;
   cudaEventRecord(e0, st);
-  int rc = factor(ctx, dS, np, dl, dflag, st);
+  rc = factor(ctx, dS, np, dl, dflag, plan, st);
   cudaEventRecord(e1, st);
   if (rc) return rc;
-  rc = solve(ctx, dS, np, dl, dv, dv + np, dv + 2 * np, st);
+  rc = solve(ctx, dS, np, dl, dv, dv + np, dv + 2 * np, plan, st);
   if (rc) return rc;
   int flag = 0;
   CVB_CUDA(ctx, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -323,6 +388,7 @@ extern "C" int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, co
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (factor_ms) *factor_ms = ms;
+  plan.release();
   if (flag) return cvb_fail(ctx, CVB_ERR_NUMERIC, "matrix is not positive definite");
   for (int i = 0; i < n; i++) x[i] = hb[i];
   return CVB_OK;

@@ -1,0 +1,29 @@
+// cholesky.cuh — interface of the tiled FP64 Cholesky (cholesky.cu) used by the BA engine.
+#pragma once
+#include <vector>
+
+#include "cvb_internal.cuh"
+
+namespace cvb_chol {
+
+constexpr int T = 128;  // tile edge
+
+// Tile-level structure of the factor: which 128x128 tiles of L are structurally non-zero, as launch lists.
+struct TilePlan {
+  int nt = 0;
+  std::vector<int> h_col_ptr, h_row_idx;           // per tile column k: non-zero row tiles i > k
+  std::vector<int> h_pair_ptr, h_pair_i, h_pair_j; // per tile column k: (i >= j) pairs of those rows (trailing updates)
+  std::vector<int> h_rowc_ptr, h_rowc_idx;         // per tile row k: non-zero column tiles i < k (backward solve)
+  int *d_row_idx = nullptr, *d_pair_i = nullptr, *d_pair_j = nullptr, *d_rowc_idx = nullptr;
+  long n_tiles_L = 0;
+  double flops = 0.0;   // flops of one numeric factorisation with this plan
+  void build(int nt, std::vector<uint8_t> lower_mask);
+  int upload(cvb_ctx* ctx, cudaStream_t st);
+  void release();
+};
+
+int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st);
+int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
+          const TilePlan& plan, cudaStream_t st);
+
+}  // namespace cvb_chol

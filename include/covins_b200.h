@@ -233,9 +233,9 @@ CVB_API int cvb_ba_result_get(cvb_ba* h, const cvb_ba_problem* p, cvb_ba_result*
 /* problem.Evaluate(residual_ids) of optimization_be.cpp:270-274: loss-corrected reprojection residual norm per
  * observation at the current state (-1 for observations that are not in the problem) */
 CVB_API int cvb_ba_reproj_norms(cvb_ba* h, double* norms, int n_obs);
-/* diagnostic: internal vector [camera part n_c_pad | landmark part]: 0 Jacobi scale, 1 column sq-norms, 2 dogleg
+/* diagnostic: internal vector in canonical order [K x (pose 6 [+ speed-bias 9]) | landmarks 3 each]: 0 Jacobi scale, 1 column sq-norms, 2 dogleg
  * diagonal, 3 gradient, 4 gradient/diag, 5 Gauss-Newton step (scaled), 6 trust-region step, 7 linear-solve x, 8 reduced rhs */
-CVB_API int cvb_ba_debug_vector(cvb_ba* h, int which, double* out, int64_t cap, int64_t* n_cam_pad, int64_t* n_total);
+CVB_API int cvb_ba_debug_vector(cvb_ba* h, int which, double* out, int64_t cap, int64_t* n_cam, int64_t* n_total);
 /* accumulated device time (ms, CUDA events) per phase: [0] linearise, [1] block build + Schur, [2] Cholesky factor,
  * [3] triangular solves + back-substitution, [4] dogleg / J*step / Plus / candidate cost; [5] dense-equivalent
  * factorisation flops.  reset != 0 clears the counters. */

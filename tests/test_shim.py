@@ -1,0 +1,103 @@
+"""The C++ host shim (covins_b200/csrc/host/covins_b200_shim.hpp) on mock containers.
+CPU: it compiles and links against libcovins_b200.so with -Wall -Werror (host-logic check, no GPU).
+GPU: GlobalBundleAdjustment / PoseGraphOptimization / MatchCandidatesORB called through the reference-shaped C++
+surface give the same states as the flat-problem API (they differ only by the container → flat conversion and the
+map's idpair keyframe order, i.e. by floating-point reordering)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "shim_test")
+
+
+def build_shim_test():
+    import covins_b200
+    if not os.path.exists(covins_b200.LIB_PATH):
+        covins_b200.build()
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-Werror", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "shim_test.cpp"),
+                           "-L" + os.path.join(ROOT, "covins_b200"), "-lcovins_b200", "-Wl,-rpath,$ORIGIN/../../covins_b200"])
+
+
+def test_shim_compiles_and_links():
+    build_shim_test()
+    assert os.path.exists(EXE)
+
+
+def _dump(p, d):
+    for k, v in p.items():
+        if isinstance(v, np.ndarray):
+            np.ascontiguousarray(v).tofile(os.path.join(d, k + ".bin"))
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,visual_only", [("gba", False), ("gba_visual", True)])
+def test_shim_gba_equals_flat_api(ctx, tmp_path, mode, visual_only):
+    from covins_b200 import optimization as O, synth_map
+    if not os.path.exists(EXE):
+        build_shim_test()
+    p = synth_map.make_config("small")
+    _dump(p, str(tmp_path))
+    subprocess.check_call([EXE, str(tmp_path), mode])
+    ref = O.global_bundle_adjustment(ctx, p, iterations_limit=4, visual_only=visual_only)
+    pose = np.fromfile(tmp_path / "out_pose.bin").reshape(-1, 7)
+    lm = np.fromfile(tmp_path / "out_lm.bin").reshape(-1, 3)
+    sb = np.fromfile(tmp_path / "out_sb.bin").reshape(-1, 9)
+    sign = np.sign((pose[:, :4] * ref["pose"][:, :4]).sum(1))[:, None]      # q and -q are the same rotation
+    assert _rel(pose[:, :4] * sign, ref["pose"][:, :4]) < 1e-6 and _rel(pose[:, 4:], ref["pose"][:, 4:]) < 1e-6
+    if not visual_only:
+        assert _rel(sb, ref["speedbias"]) < 1e-6
+    well = (ref["lm_owner"] >= 0) & (np.abs(ref["lm"]).max(1) < 100)
+    assert _rel(lm[well], ref["lm"][well]) < 1e-6
+    # round-1 outliers were erased from the containers (optimization_be.cpp:282-288)
+    nobs = np.fromfile(tmp_path / "out_nobs.bin", dtype=np.int32)
+    removed_per_lm = np.add.reduceat(ref["obs_removed"].astype(np.int64), p["lm_obs_ptr"][:-1])
+    assert np.array_equal(nobs, np.diff(p["lm_obs_ptr"]) - removed_per_lm)
+
+
+@pytest.mark.gpu
+def test_shim_pgo_equals_flat_api(ctx, tmp_path):
+    from covins_b200 import optimization as O, synth_map
+    from oracle import ba_oracle as bo
+    if not os.path.exists(EXE):
+        build_shim_test()
+    p = synth_map.make_map(seed=5, n_agents=3, kf_per_agent=40, n_lm=50, drift_trans=0.01, drift_yaw_deg=0.1)
+    _dump(p, str(tmp_path))
+    subprocess.check_call([EXE, str(tmp_path), "pgo"])
+    edges = bo.pgo_edges(p, p["pose"], covins_mode=True)       # the edge list the reference builds (:886-1021)
+    ref = O.pose_graph_optimization(ctx, p, edges, iterations=10)
+    pose = np.fromfile(tmp_path / "out_pose.bin").reshape(-1, 7)
+    sign = np.sign((pose[:, :4] * ref["pose"][:, :4]).sum(1))[:, None]
+    assert _rel(pose[:, :4] * sign, ref["pose"][:, :4]) < 1e-6 and _rel(pose[:, 4:], ref["pose"][:, 4:]) < 1e-6
+    assert np.abs(pose[:, 4:] - p["pose"][:, 4:]).max() > 1e-3      # it did move
+
+
+@pytest.mark.gpu
+def test_shim_match_candidates_equals_oracle(tmp_path):
+    from covins_b200 import synth
+    from oracle import knn as ora
+    if not os.path.exists(EXE):
+        build_shim_test()
+    desc, _ = synth.orb_keyframes(seed=12, n_kf=7, n_feat=400, n_lm=600, window=600)
+    lens = [400, 400, 0, 399, 57, 400]
+    t = np.concatenate([desc[i + 1][:l] for i, l in enumerate(lens)])
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    desc[0].tofile(tmp_path / "q.bin"); t.tofile(tmp_path / "t.bin"); seg.tofile(tmp_path / "seg.bin")
+    subprocess.check_call([EXE, str(tmp_path), "match"])
+    out = np.fromfile(tmp_path / "match_out.bin", dtype=np.int32)
+    i2, d2 = ora.knn_hamming_batch(desc[0], t, seg, 2)
+    mt, md, cnt = ora.ratio_filter(i2, d2.astype(np.float32), 40.0, 0.8)
+    pos = 0
+    for s in range(len(lens)):
+        n, disc = out[pos], out[pos + 1]; pos += 2
+        assert n == cnt[s]
+        assert disc == (1 if n < 25 else 0)                       # matches_thres / matches_thres_merge = 25
+        q = np.flatnonzero(mt[s] >= 0)
+        got = out[pos:pos + 3 * n].reshape(-1, 3); pos += 3 * n
+        assert np.array_equal(got[:, 0], q) and np.array_equal(got[:, 1], mt[s][q]) and np.array_equal(got[:, 2], md[s][q].astype(np.int32))
