@@ -999,12 +999,34 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   // column layout of the reduced camera system: [speed-bias blocks (9 each, keyframe order) | pad to a tile | pose
   // blocks (6 each)] — see cam_col()
   const int TT = cvb_chol::T;
-  const int n_sb_pad = E.visual_only ? 0 : ((9 * K + TT - 1) / TT) * TT;
-  E.h_off_pose.resize(K); E.h_off_sb.resize(K);
-  for (int k = 0; k < K; k++) {
-    E.h_off_sb[k] = E.visual_only ? 0 : 9 * k;
-    E.h_off_pose[k] = n_sb_pad + 6 * k;
+  // Speed-bias layout: every IMU chain (connected component of the IMU factor graph, i.e. one agent's trajectory)
+  // starts on a tile boundary, so that the tile-level elimination of one chain never touches another chain's tiles
+  // (a tile shared by two chains would carry the first chain's pose clique along the whole second chain).
+  E.h_off_pose.resize(K); E.h_off_sb.assign(K, 0);
+  int n_sb_pad = 0;
+  if (!E.visual_only) {
+    std::vector<int> parent(K);
+    std::iota(parent.begin(), parent.end(), 0);
+    std::function<int(int)> find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (int f = 0; f < p->n_imu; f++) {
+      const int a = find(p->imu_i[f]), b = find(p->imu_j[f]);
+      if (a != b) parent[std::max(a, b)] = std::min(a, b);
+    }
+    std::vector<int> comp_size(K, 0);
+    for (int k = 0; k < K; k++) comp_size[find(k)]++;
+    int cursor = 0;
+    for (int root = 0; root < K; root++) {          // chains with >= 2 keyframes, in order of their first keyframe
+      if (find(root) != root || comp_size[root] < 2) continue;
+      cursor = ((cursor + TT - 1) / TT) * TT;
+      for (int k = root; k < K; k++)
+        if (find(k) == root) { E.h_off_sb[k] = cursor; cursor += 9; }
+    }
+    cursor = ((cursor + TT - 1) / TT) * TT;
+    for (int k = 0; k < K; k++)                     // keyframes without an IMU factor: isolated speed-bias blocks
+      if (comp_size[find(k)] < 2) { E.h_off_sb[k] = cursor; cursor += 9; }
+    n_sb_pad = ((cursor + TT - 1) / TT) * TT;
   }
+  for (int k = 0; k < K; k++) E.h_off_pose[k] = n_sb_pad + 6 * k;
   E.n_c_pad = ((n_sb_pad + 6 * K + TT - 1) / TT) * TT;
   E.n_vec = E.n_c_pad + 3 * E.L_in;
   auto col_of = [&](int kf, int c) { return c < 6 ? E.h_off_pose[kf] + c : E.h_off_sb[kf] + (c - 6); };

@@ -132,86 +132,171 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(double* __restric
     }
 }
 
-// Factor the diagonal tile k in shared memory (left-looking, one thread per row), write L back, and write the
-// tile inverse (row-major, full 128x128 with zeros above the diagonal) to linv_k.  flag[0] = 1 on a
-// non-positive pivot (matrix not positive definite → caller raises mu, as Ceres does on LINEAR_SOLVER_FAILURE).
+// Factor the diagonal tile k in shared memory and invert the factor, one CTA of 512 threads.
+//   Cholesky: blocked left-looking, 16-wide block columns: (1) panel update with all threads, (2) 16x16 diagonal block
+//   by one warp, (3) panel triangular solve one thread per row → 3 barriers per block column instead of 2 per column.
+//   Inverse: in place by recursive doubling (16 → 32 → 64 → 128): X21 = -C^-1 (B A^-1) with a 32 KB scratch tile.
+// L is written back to S, the inverse (row-major 128x128, zeros above the diagonal) to linv_k.  flag[0] |= 1 on a
+// non-positive pivot (matrix not positive definite → the caller raises mu, as Ceres does on LINEAR_SOLVER_FAILURE).
 constexpr int LDP = T + 1;
-constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)T * (T + 1) / 2) * sizeof(double);
+constexpr int PB = 16;
+constexpr int POTRF_THREADS = 512;
+constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)64 * 64) * sizeof(double);
 
-__global__ void __launch_bounds__(256, 1) potrf_inv_kernel(double* __restrict__ S, size_t ld, int k,
-                                                           double* __restrict__ linv_k, int* __restrict__ flag) {
+__global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __restrict__ S, size_t ld, int k,
+                                                                     double* __restrict__ linv_k, int* __restrict__ flag) {
   extern __shared__ __align__(16) double smem_d[];
-  double* a = smem_d;               // [T][LDP]
-  double* x = smem_d + T * LDP;     // packed lower triangle of the inverse
-  const int tid = threadIdx.x;
+  double* a = smem_d;              // [T][LDP]
+  double* tmp = smem_d + T * LDP;  // 64 x 64 scratch
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* At = S + (size_t)k * T * ld + (size_t)k * T;
-  for (int u = tid; u < T * T; u += blockDim.x) {
+  for (int u = tid; u < T * T; u += POTRF_THREADS) {
     const int r = u / T, c = u % T;
     a[r * LDP + c] = (c <= r) ? At[(size_t)r * ld + c] : 0.0;
   }
   __syncthreads();
-  __shared__ double piv;
-  for (int j = 0; j < T; j++) {
-    double s = 0.0;
-    const int i = tid;
-    if (i >= j && i < T) {
-      s = a[i * LDP + j];
-      for (int m = 0; m < j; m++) s -= a[i * LDP + m] * a[j * LDP + m];
-      if (i == j) {
-        if (!(s > 0.0)) {
-          flag[0] = 1;
-          s = 1.0;
+  // ---------------- Cholesky ----------------
+  for (int jb = 0; jb < T / PB; jb++) {
+    const int c0 = jb * PB, nrows = T - c0;
+    if (jb > 0) {  // (1) A[c0.., c0..c0+15] -= L[c0.., 0..c0) L[c0..c0+15, 0..c0)^T
+      for (int u = tid; u < nrows * PB; u += POTRF_THREADS) {
+        const int r = c0 + (u % nrows), c = c0 + (u / nrows);
+        if (c > r) continue;
+        double s = 0.0;
+        const double* ar = a + r * LDP;
+        const double* ac = a + c * LDP;
+#pragma unroll 8
+        for (int m = 0; m < c0; m++) s += ar[m] * ac[m];
+        a[r * LDP + c] -= s;
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {  // (2) unblocked Cholesky of the 16x16 diagonal block
+      for (int j = 0; j < PB; j++) {
+        double s = 0.0;
+        if (lane >= j && lane < PB) {
+          s = a[(c0 + lane) * LDP + c0 + j];
+          for (int m = 0; m < j; m++) s -= a[(c0 + lane) * LDP + c0 + m] * a[(c0 + j) * LDP + c0 + m];
         }
-        piv = sqrt(s);
+        double piv = __shfl_sync(0xffffffffu, s, j);
+        if (!(piv > 0.0)) {
+          if (lane == 0) atomicOr(flag, 1);
+          piv = 1.0;
+        }
+        piv = sqrt(piv);
+        if (lane >= j && lane < PB) a[(c0 + lane) * LDP + c0 + j] = (lane == j) ? piv : s / piv;
+        __syncwarp();
       }
     }
     __syncthreads();
-    if (i >= j && i < T) a[i * LDP + j] = (i == j) ? piv : s / piv;
+    // (3) rows below the block: x = a_row * Ljj^-T (forward substitution along the 16 columns), one thread per row
+    for (int r = c0 + PB + tid; r < T; r += POTRF_THREADS) {
+      double x[PB];
+#pragma unroll
+      for (int j = 0; j < PB; j++) {
+        double s = a[r * LDP + c0 + j];
+#pragma unroll
+        for (int m = 0; m < PB; m++)
+          if (m < j) s -= x[m] * a[(c0 + j) * LDP + c0 + m];
+        x[j] = s / a[(c0 + j) * LDP + c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < PB; j++) a[r * LDP + c0 + j] = x[j];
+    }
     __syncthreads();
   }
-  for (int u = tid; u < T * T; u += blockDim.x) {
+  for (int u = tid; u < T * T; u += POTRF_THREADS) {
     const int r = u / T, c = u % T;
     if (c <= r) At[(size_t)r * ld + c] = a[r * LDP + c];
   }
-  // inverse: thread j computes column j of X = L^-1 by forward substitution
-  if (tid < T) {
-    const int j = tid;
-    for (int i = j; i < T; i++) {
-      double s = (i == j) ? 1.0 : 0.0;
-      for (int m = j; m < i; m++) s -= a[i * LDP + m] * x[m * (m + 1) / 2 + j];
-      x[i * (i + 1) / 2 + j] = s / a[i * LDP + i];
-    }
+  // ---------------- inverse of L, in place ----------------
+  // level 0: the eight 16x16 diagonal blocks, via a copy in tmp (thread (blk, c) → column c of the block inverse)
+  for (int u = tid; u < (T / PB) * PB * PB; u += POTRF_THREADS) {
+    const int blk = u / (PB * PB), r = (u / PB) % PB, c = u % PB;
+    tmp[u] = a[(blk * PB + r) * LDP + blk * PB + c];
   }
   __syncthreads();
-  for (int u = tid; u < T * T; u += blockDim.x) {
+  if (tid < (T / PB) * PB) {
+    const int blk = tid / PB, j = tid % PB;
+    const double* Lb = tmp + blk * PB * PB;
+    double x[PB];
+#pragma unroll
+    for (int i = 0; i < PB; i++) {
+      double s = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int m = 0; m < PB; m++)
+        if (m >= j && m < i) s -= Lb[i * PB + m] * x[m];
+      x[i] = (i >= j) ? s / Lb[i * PB + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < PB; i++) a[(blk * PB + i) * LDP + blk * PB + j] = x[i];
+  }
+  __syncthreads();
+  // levels 1..3: block size h = 16, 32, 64: for each pair (A = inv at [p,p], C = inv at [p+h,p+h], B at [p+h,p]):
+  //   tmp = B * A  (A lower triangular),  B <- -C * tmp  (C lower triangular)
+  for (int h = PB; h < T; h *= 2) {
+    const int npairs = T / (2 * h);
+    for (int u = tid; u < npairs * h * h; u += POTRF_THREADS) {
+      const int pr = u / (h * h), r = (u / h) % h, c = u % h;
+      const int p0 = pr * 2 * h;
+      const double* B = a + (p0 + h + r) * LDP + p0;   // row r of B
+      double s = 0.0;
+      for (int m = c; m < h; m++) s += B[m] * a[(p0 + m) * LDP + p0 + c];   // A[m][c], m >= c
+      tmp[pr * h * h + r * h + c] = s;
+    }
+    __syncthreads();
+    for (int u = tid; u < npairs * h * h; u += POTRF_THREADS) {
+      const int pr = u / (h * h), r = (u / h) % h, c = u % h;
+      const int p0 = pr * 2 * h;
+      const double* Crow = a + (p0 + h + r) * LDP + p0 + h;   // row r of C (inverse, lower)
+      double s = 0.0;
+      for (int m = 0; m <= r; m++) s += Crow[m] * tmp[pr * h * h + m * h + c];
+      a[(p0 + h + r) * LDP + p0 + c] = -s;
+    }
+    __syncthreads();
+  }
+  for (int u = tid; u < T * T; u += POTRF_THREADS) {
     const int r = u / T, c = u % T;
-    linv_k[u] = (c <= r) ? x[r * (r + 1) / 2 + c] : 0.0;
+    linv_k[u] = (c <= r) ? a[r * LDP + c] : 0.0;
   }
 }
 
-// forward step k: y_k = Linv_k b_k (written by CTA 0), b_i -= L(i,k) y_k for i > k (CTA i-k)
-__global__ void __launch_bounds__(T) fwd_kernel(const double* __restrict__ L, size_t ld, int k,
-                                                const double* __restrict__ linv, double* __restrict__ b,
-                                                double* __restrict__ y, const int* __restrict__ rows) {
+// forward step k: y_k = Linv_k b_k (written by CTA 0), b_i -= L(i,k) y_k for the non-zero row tiles i > k (rows[]).
+// One warp per matrix row, lanes across the 128 columns (coalesced), fixed-order shuffle reduction.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(256) fwd_kernel(const double* __restrict__ L, size_t ld, int k,
+                                                  const double* __restrict__ linv, double* __restrict__ b,
+                                                  double* __restrict__ y, const int* __restrict__ rows) {
   __shared__ double bk[T], yk[T];
-  const int tid = threadIdx.x;
-  bk[tid] = b[(size_t)k * T + tid];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < T) bk[tid] = b[(size_t)k * T + tid];
   __syncthreads();
-  const double* li = linv + (size_t)k * T * T + (size_t)tid * T;
-  double s = 0.0;
-  for (int m = 0; m <= tid; m++) s += li[m] * bk[m];
-  yk[tid] = s;
+  const double* lk = linv + (size_t)k * T * T;
+  for (int r = warp; r < T; r += 8) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = lane; c < T; c += 32) s += lk[(size_t)r * T + c] * bk[c];   // Linv is zero above the diagonal
+    s = warp_sum(s);
+    if (lane == 0) yk[r] = s;
+  }
   __syncthreads();
   if (blockIdx.x == 0) {
-    y[(size_t)k * T + tid] = yk[tid];
+    if (tid < T) y[(size_t)k * T + tid] = yk[tid];
     return;
   }
   const int i = rows[blockIdx.x - 1];
-  const double* row = L + ((size_t)i * T + tid) * ld + (size_t)k * T;
-  double acc = 0.0;
-#pragma unroll 8
-  for (int m = 0; m < T; m++) acc += row[m] * yk[m];
-  b[(size_t)i * T + tid] -= acc;
+  const double* tile = L + (size_t)i * T * ld + (size_t)k * T;
+  for (int r = warp; r < T; r += 8) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = lane; c < T; c += 32) s += tile[(size_t)r * ld + c] * yk[c];
+    s = warp_sum(s);
+    if (lane == 0) b[(size_t)i * T + r] -= s;
+  }
 }
 
 // backward step k: x_k = Linv_k^T y_k (CTA 0), y_i -= L(k,i)^T x_k for the non-zero column tiles i < k of row k (cols[])
@@ -306,7 +391,7 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
   CVB_REQUIRE(ctx, plan.nt == nt, "tile plan does not match the matrix");
   CVB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
   for (int k = 0; k < nt; k++) {
-    potrf_inv_kernel<<<1, 256, kPotrfSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag);
+    potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag);
     CVB_CHECK_LAUNCH(ctx);
     const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
     if (m > 0) {
@@ -328,7 +413,7 @@ int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* 
   const int nt = n_pad / T;
   for (int k = 0; k < nt; k++) {
     const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
-    fwd_kernel<<<1 + m, T, 0, st>>>(L, (size_t)n_pad, k, linv, b, tmp, plan.d_row_idx + plan.h_col_ptr[k]);
+    fwd_kernel<<<1 + m, 256, 0, st>>>(L, (size_t)n_pad, k, linv, b, tmp, plan.d_row_idx + plan.h_col_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
   for (int k = nt - 1; k >= 0; k--) {
