@@ -261,67 +261,79 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
   }
 }
 
-// forward step k: y_k = Linv_k b_k (written by CTA 0), b_i -= L(i,k) y_k for the non-zero row tiles i > k (rows[]).
-// One warp per matrix row, lanes across the 128 columns (coalesced), fixed-order shuffle reduction.
-__device__ __forceinline__ double warp_sum(double v) {
+// Triangular solves.  One launch per tile column; every CTA recomputes the tiny diagonal product (128x128 mat-vec with
+// the stored tile inverse) and then updates its own off-diagonal tile.  512 threads, all loads of a mat-vec are issued
+// before the first use (32 independent coalesced loads per thread) — these kernels are latency-, not bandwidth-bound.
+constexpr int SOLVE_THREADS = 512;
+
+// out[r] = sum_c A[r][c] x[c]   (A row-major 128x128 with leading dimension lda; lanes run along c)
+__device__ __forceinline__ void matvec_rows(const double* __restrict__ A, size_t lda, const double* x, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // 16 warps x 8 rows
+  double v[8][4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[i][j] = A[(size_t)(warp * 8 + i) * lda + lane + 32 * j];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    double s = (v[i][0] * x[lane] + v[i][1] * x[lane + 32]) + (v[i][2] * x[lane + 64] + v[i][3] * x[lane + 96]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[warp * 8 + i] = s;
+  }
 }
-__global__ void __launch_bounds__(256) fwd_kernel(const double* __restrict__ L, size_t ld, int k,
-                                                  const double* __restrict__ linv, double* __restrict__ b,
-                                                  double* __restrict__ y, const int* __restrict__ rows) {
-  __shared__ double bk[T], yk[T];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// out[c] = sum_m A[m][c] x[m]   (threads run along c; 4 groups of 128 threads split m, partials combined in order)
+__device__ __forceinline__ void matvec_cols(const double* __restrict__ A, size_t lda, const double* x, double* out,
+                                            double* part /*[4][128]*/) {
+  const int c = threadIdx.x & 127, g = threadIdx.x >> 7;
+  double v[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = A[(size_t)(g * 32 + i) * lda + c];
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) s += v[i] * x[g * 32 + i];
+  part[g * T + c] = s;
+  __syncthreads();
+  if (threadIdx.x < T) out[c] = (part[c] + part[T + c]) + (part[2 * T + c] + part[3 * T + c]);
+  __syncthreads();
+}
+
+// forward step k: y_k = Linv_k b_k (written by CTA 0), b_i -= L(i,k) y_k for the non-zero row tiles i > k (rows[])
+__global__ void __launch_bounds__(SOLVE_THREADS) fwd_kernel(const double* __restrict__ L, size_t ld, int k,
+                                                            const double* __restrict__ linv, double* __restrict__ b,
+                                                            double* __restrict__ y, const int* __restrict__ rows) {
+  __shared__ double bk[T], yk[T], upd[T];
+  const int tid = threadIdx.x;
   if (tid < T) bk[tid] = b[(size_t)k * T + tid];
   __syncthreads();
-  const double* lk = linv + (size_t)k * T * T;
-  for (int r = warp; r < T; r += 8) {
-    double s = 0.0;
-#pragma unroll
-    for (int c = lane; c < T; c += 32) s += lk[(size_t)r * T + c] * bk[c];   // Linv is zero above the diagonal
-    s = warp_sum(s);
-    if (lane == 0) yk[r] = s;
-  }
+  matvec_rows(linv + (size_t)k * T * T, T, bk, yk);   // Linv is stored with zeros above the diagonal
   __syncthreads();
   if (blockIdx.x == 0) {
     if (tid < T) y[(size_t)k * T + tid] = yk[tid];
     return;
   }
   const int i = rows[blockIdx.x - 1];
-  const double* tile = L + (size_t)i * T * ld + (size_t)k * T;
-  for (int r = warp; r < T; r += 8) {
-    double s = 0.0;
-#pragma unroll
-    for (int c = lane; c < T; c += 32) s += tile[(size_t)r * ld + c] * yk[c];
-    s = warp_sum(s);
-    if (lane == 0) b[(size_t)i * T + r] -= s;
-  }
+  matvec_rows(L + (size_t)i * T * ld + (size_t)k * T, ld, yk, upd);
+  __syncthreads();
+  if (tid < T) b[(size_t)i * T + tid] -= upd[tid];
 }
 
 // backward step k: x_k = Linv_k^T y_k (CTA 0), y_i -= L(k,i)^T x_k for the non-zero column tiles i < k of row k (cols[])
-__global__ void __launch_bounds__(T) bwd_kernel(const double* __restrict__ L, size_t ld, int k,
-                                                const double* __restrict__ linv, double* __restrict__ y,
-                                                double* __restrict__ x, const int* __restrict__ cols) {
-  __shared__ double ykk[T], xk[T];
+__global__ void __launch_bounds__(SOLVE_THREADS) bwd_kernel(const double* __restrict__ L, size_t ld, int k,
+                                                            const double* __restrict__ linv, double* __restrict__ y,
+                                                            double* __restrict__ x, const int* __restrict__ cols) {
+  __shared__ double ykk[T], xk[T], upd[T], part[4 * T];
   const int tid = threadIdx.x;
-  ykk[tid] = y[(size_t)k * T + tid];
+  if (tid < T) ykk[tid] = y[(size_t)k * T + tid];
   __syncthreads();
-  const double* lk = linv + (size_t)k * T * T;
-  double s = 0.0;
-  for (int m = tid; m < T; m++) s += lk[(size_t)m * T + tid] * ykk[m];  // column tid of Linv (coalesced over tid)
-  xk[tid] = s;
-  __syncthreads();
+  matvec_cols(linv + (size_t)k * T * T, T, ykk, xk, part);
   if (blockIdx.x == 0) {
-    x[(size_t)k * T + tid] = xk[tid];
+    if (tid < T) x[(size_t)k * T + tid] = xk[tid];
     return;
   }
   const int i = cols[blockIdx.x - 1];
-  const double* tile = L + (size_t)k * T * ld + (size_t)i * T;  // L(k,i): rows m of tile k, cols of tile i
-  double acc = 0.0;
-#pragma unroll 8
-  for (int m = 0; m < T; m++) acc += tile[(size_t)m * ld + tid] * xk[m];
-  y[(size_t)i * T + tid] -= acc;
+  matvec_cols(L + (size_t)k * T * ld + (size_t)i * T, ld, xk, upd, part);
+  if (tid < T) y[(size_t)i * T + tid] -= upd[tid];
 }
 
 // Symbolic phase (host): tile-level structure of L from the tile-level structure of S (lower, nt x nt, row-major
@@ -413,12 +425,12 @@ int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* 
   const int nt = n_pad / T;
   for (int k = 0; k < nt; k++) {
     const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
-    fwd_kernel<<<1 + m, 256, 0, st>>>(L, (size_t)n_pad, k, linv, b, tmp, plan.d_row_idx + plan.h_col_ptr[k]);
+    fwd_kernel<<<1 + m, SOLVE_THREADS, 0, st>>>(L, (size_t)n_pad, k, linv, b, tmp, plan.d_row_idx + plan.h_col_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
   for (int k = nt - 1; k >= 0; k--) {
     const int m = plan.h_rowc_ptr[k + 1] - plan.h_rowc_ptr[k];
-    bwd_kernel<<<1 + m, T, 0, st>>>(L, (size_t)n_pad, k, linv, tmp, x, plan.d_rowc_idx + plan.h_rowc_ptr[k]);
+    bwd_kernel<<<1 + m, SOLVE_THREADS, 0, st>>>(L, (size_t)n_pad, k, linv, tmp, x, plan.d_rowc_idx + plan.h_rowc_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
   return CVB_OK;
