@@ -83,7 +83,9 @@ struct Engine {
   // device state (double buffered)
   DevArr<double> pose[2], sb[2], lm[2];
   DevArr<uint8_t> pose_const;
-  DevArr<int> off_pose, off_sb;
+  DevArr<int> off_pose, off_sb, xt_i, xt_j;   // xt_*: tile list of the multi-GPU exchange
+  DevArr<double> xbuf;
+  int n_xt = 0;
   std::vector<int> h_off_pose, h_off_sb;
   cvb_chol::TilePlan plan;
   DevArr<double> extr_kf, intr_kf, dist_kf;
@@ -127,7 +129,7 @@ struct Engine {
   double chol_flops = 0.0;
   ~Engine() {
     for (int i = 0; i < 2; i++) { pose[i].free_(); sb[i].free_(); lm[i].free_(); }
-    pose_const.free_(); off_pose.free_(); off_sb.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
+    pose_const.free_(); off_pose.free_(); off_sb.free_(); xt_i.free_(); xt_j.free_(); xbuf.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
     obs_kf.free_(); obs_lm.free_(); lm_ptr.free_(); kf_ptr.free_(); kf_obs.free_(); obs_uv.free_(); obs_sigma.free_();
     lin.free_(); wy.free_(); Hll.free_(); HllInv.free_(); bl.free_();
     pre.free_(); imu_i.free_(); imu_j.free_(); Jimu.free_(); rimu.free_();
@@ -683,6 +685,21 @@ __global__ void __launch_bounds__(128) schur_kernel(int n_sb, const int* __restr
   }
 }
 
+// Multi-GPU exchange: only the structurally non-zero 128x128 tiles of the (pre-fill) lower triangle of S are summed
+// across ranks.  pack: S tiles → contiguous buffer; unpack: buffer → S tiles.
+__global__ void __launch_bounds__(256) pack_tiles_kernel(const double* __restrict__ S, size_t ld, const int* __restrict__ ti,
+                                                         const int* __restrict__ tj, double* __restrict__ buf, int unpack,
+                                                         double* __restrict__ Sw) {
+  const int t = blockIdx.x;
+  const size_t base = ((size_t)ti[t] * cvb_chol::T) * ld + (size_t)tj[t] * cvb_chol::T;
+  double* b = buf + (size_t)t * cvb_chol::T * cvb_chol::T;
+  for (int u = threadIdx.x; u < cvb_chol::T * cvb_chol::T; u += blockDim.x) {
+    const int r = u / cvb_chol::T, c = u % cvb_chol::T;
+    if (unpack) Sw[base + (size_t)r * ld + c] = b[u];
+    else b[u] = S[base + (size_t)r * ld + c];
+  }
+}
+
 // landmark back-substitution: x_l = Hll^-1 (b_l - sum W^T x_c)
 __global__ void backsub_kernel(int L, const int* __restrict__ lm_ptr, const int* __restrict__ obs_kf,
                                const ObsWY* __restrict__ wy, const double* __restrict__ HllInv, const double* __restrict__ bl,
@@ -1062,6 +1079,11 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     mark(E.h_off_pose[p->edge_i[e]], 6, E.h_off_pose[p->edge_i[e]], 6);
     mark(E.h_off_pose[p->edge_j[e]], 6, E.h_off_pose[p->edge_j[e]], 6);
   }
+  std::vector<int> h_xt_i, h_xt_j;
+  for (int i = 0; i < nt; i++)
+    for (int j = 0; j <= i; j++)
+      if (tmask[(size_t)i * nt + j] || i == j) { h_xt_i.push_back(i); h_xt_j.push_back(j); }
+  E.n_xt = (int)h_xt_i.size();
   E.plan.build(nt, tmask);
   // ---- by-keyframe CSR ----
   std::vector<int> h_kf_ptr(K + 1, 0), h_kf_obs(E.n_obs);
@@ -1247,6 +1269,10 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   if ((rc = upload(E, E.scale, h_scale))) return rc;
   if ((rc = upload(E, E.off_pose, E.h_off_pose)) || (rc = upload(E, E.off_sb, E.h_off_sb))) return rc;
   if ((rc = E.plan.upload(E.ctx, E.st))) return rc;
+  if (E.world > 1) {
+    if ((rc = upload(E, E.xt_i, h_xt_i)) || (rc = upload(E, E.xt_j, h_xt_j))) return rc;
+    if ((rc = zalloc(E, E.xbuf, (size_t)E.n_xt * cvb_chol::T * cvb_chol::T))) return rc;
+  }
   DevArr<double>* vecs[] = {&E.colsq, &E.diag, &E.gvec, &E.grad, &E.sgrad, &E.gn, &E.step, &E.xsol, &E.yb, &E.gs, &E.tmp};
   for (auto* v : vecs)
     if ((rc = zalloc(E, *v, (size_t)E.n_vec))) return rc;
@@ -1348,8 +1374,14 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
     ENG_LAUNCH();
   }
   // the one exchange of the data path: sum the rank-partial reduced normal equations over NVLink
-  int rc = ar(E, E.S.p, ld * ld);
-  if (rc) return rc;
+  int rc = CVB_OK;
+  if (E.allreduce && E.world > 1) {
+    pack_tiles_kernel<<<E.n_xt, 256, 0, E.st>>>(E.S.p, ld, E.xt_i.p, E.xt_j.p, E.xbuf.p, 0, nullptr);
+    ENG_LAUNCH();
+    if ((rc = ar(E, E.xbuf.p, (size_t)E.n_xt * cvb_chol::T * cvb_chol::T))) return rc;
+    pack_tiles_kernel<<<E.n_xt, 256, 0, E.st>>>(nullptr, ld, E.xt_i.p, E.xt_j.p, E.xbuf.p, 1, E.S.p);
+    ENG_LAUNCH();
+  }
   if ((rc = ar(E, E.yb.p, ld))) return rc;
   cam_finish_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, ld, E.S.p, E.diag.p, E.gvec.p, E.yb.p, E.gs.p, mu);
   ENG_LAUNCH();

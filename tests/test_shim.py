@@ -54,7 +54,7 @@ def test_shim_gba_equals_flat_api(ctx, tmp_path, mode, visual_only):
     if not visual_only:
         assert _rel(sb, ref["speedbias"]) < 2e-5   # keyframe order differs (idpair vs agent-major): fp reordering
     well = (ref["lm_owner"] >= 0) & (np.abs(ref["lm"]).max(1) < 100)
-    assert _rel(lm[well], ref["lm"][well]) < 1e-6
+    assert _rel(lm[well], ref["lm"][well]) < 2e-5
     # round-1 outliers were erased from the containers (optimization_be.cpp:282-288)
     nobs = np.fromfile(tmp_path / "out_nobs.bin", dtype=np.int32)
     removed_per_lm = np.add.reduceat(ref["obs_removed"].astype(np.int64), p["lm_obs_ptr"][:-1])
