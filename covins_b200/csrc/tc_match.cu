@@ -1,0 +1,394 @@
+// tc_match.cu — descriptor k-NN on the 5th-generation tensor cores (tcgen05, kind::i8, accumulators in TMEM).
+//
+// Same contract as scan_kernel in match_kernels.cu (K1 Hamming / K2 L2 / K3 DenseMatcher lists), different bound.
+// The POPC formulation tops out at 16 POPC/clk/SM (measured: 94 % of that roofline).  Here the pairwise term is a
+// u8 x u8 -> s32 GEMM:
+//     Hamming(a,b) = popc(a) + popc(b) - 2 <bits(a), bits(b)>      (bits expanded to 0/1 bytes in shared memory)
+//     |a-b|^2      = |a|^2 + |b|^2 - 2 <a, b>                      (u8 SIFT, exact in s32)
+// issued as tcgen05.mma.cta_group::1.kind::i8 (M = 128 queries, N = 128 train rows, K = 32 bytes per instruction) with
+// the 128x128 s32 accumulator in tensor memory.  One TMEM lane = one query row = one epilogue thread, which receives
+// the train rows of a tile in ascending order — so the per-query selection is the same sequential OpenCV /
+// DenseMatcher rule as in the scalar kernel and the result is bit-identical.
+//
+// Warp-specialised, persistent CTA (one per SM), 4-stage ring:
+//   warps 0-3  epilogue   wait tmem_full[s] → tcgen05.ld 32x32b.x32 → d = pt[j] - 2 acc (+ pq) → k-list → tmem_empty[s]
+//   warps 4-7  producers  wait empty[s] → read packed rows from HBM (coalesced 16-B loads) → expand / copy into the
+//                         canonical K-major no-swizzle UMMA layout → fence.proxy.async → full[s]
+//   warp 8     MMA        wait full[s], tmem_empty[s] → K/32 x tcgen05.mma → tcgen05.commit → empty[s], tmem_full[s]
+// A CTA owns one block of 128 queries (expanded once, 32 KB of shared memory) and streams a contiguous range of
+// candidate segments.
+#include <float.h>
+#include <limits.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "cvb_internal.cuh"
+#include "tc_match.cuh"
+
+namespace cvb_tc {
+
+constexpr int TM = 128;       // queries per CTA (UMMA M)
+constexpr int TN = 128;       // train rows per tile (UMMA N)
+constexpr int STAGES = 4;
+constexpr int NORM_RING = 8;
+constexpr int NUM_THREADS = 288;   // 4 epilogue + 4 producer + 1 MMA warp
+constexpr int kInf = 0x3FFFFFFF;   // list sentinel; rows that must never enter carry this as their norm term
+
+// ---- mbarrier / tcgen05 wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cvb_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cvb_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, no swizzle (canonical layout ((8,n),2):((16 B, SBO), LBO)); version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  return d;                 // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+// instruction descriptor, kind::i8: D = s32 (2), A = B = u8 (0), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc() {
+  return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+__device__ __forceinline__ uint4 ldg_nc(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// ---- metrics: how a packed row becomes a K-major operand row, and its additive norm term ----------------------
+struct TcHamming {
+  static constexpr int kRowBytes = 32;    // packed bytes in HBM
+  static constexpr int kKBytes = 256;     // operand bytes (one byte per bit)
+  static constexpr bool kIsL2 = false;
+  using dist_out_t = int32_t;
+  // writes the 256 operand bytes of one row (16 chunks of 16 B) and returns popc(row)
+  static __device__ __forceinline__ int expand_row(const uint8_t* __restrict__ src, uint8_t* dst_row0 /*chunk 0 of this row*/) {
+    const uint4 a = ldg_nc(src), b = ldg_nc(src + 16);
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    int pc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      pc += __popc(w[i]);
+      // byte j of output word k holds bit (k + 8 j) of w[i]; the same permutation is applied to queries and train rows
+      uint4 lo, hi;
+      lo.x = (w[i] >> 0) & 0x01010101u; lo.y = (w[i] >> 1) & 0x01010101u; lo.z = (w[i] >> 2) & 0x01010101u; lo.w = (w[i] >> 3) & 0x01010101u;
+      hi.x = (w[i] >> 4) & 0x01010101u; hi.y = (w[i] >> 5) & 0x01010101u; hi.z = (w[i] >> 6) & 0x01010101u; hi.w = (w[i] >> 7) & 0x01010101u;
+      *reinterpret_cast<uint4*>(dst_row0 + (2 * i) * 128) = lo;
+      *reinterpret_cast<uint4*>(dst_row0 + (2 * i + 1) * 128) = hi;
+    }
+    return pc;
+  }
+  static __device__ __forceinline__ bool less(int a, int b) { return a < b; }
+  static __device__ __forceinline__ int32_t out_dist(int d) { return d; }
+  static __device__ __forceinline__ float fdist(int d) { return (float)d; }
+  static __device__ __forceinline__ int32_t empty_dist() { return INT_MAX; }
+};
+struct TcL2 {
+  static constexpr int kRowBytes = 128;
+  static constexpr int kKBytes = 128;
+  static constexpr bool kIsL2 = true;
+  using dist_out_t = float;
+  static __device__ __forceinline__ int expand_row(const uint8_t* __restrict__ src, uint8_t* dst_row0) {
+    unsigned n2 = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const uint4 v = ldg_nc(src + 16 * c);
+      n2 = __dp4a(v.x, v.x, n2); n2 = __dp4a(v.y, v.y, n2); n2 = __dp4a(v.z, v.z, n2); n2 = __dp4a(v.w, v.w, n2);
+      *reinterpret_cast<uint4*>(dst_row0 + c * 128) = v;
+    }
+    return (int)n2;
+  }
+  // OpenCV selects on sqrtf(d2): different d2 can round to the same float → tie (see match_kernels.cu L2Metric)
+  static __device__ __forceinline__ bool less(int a, int b) { return a < b && __fsqrt_rn((float)a) < __fsqrt_rn((float)b); }
+  static __device__ __forceinline__ float out_dist(int d) { return __fsqrt_rn((float)d); }
+  static __device__ __forceinline__ float fdist(int d) { return __fsqrt_rn((float)d); }
+  static __device__ __forceinline__ float empty_dist() { return FLT_MAX; }
+};
+
+template <class M, int K>
+__device__ __forceinline__ void insert_bf(int (&wd)[K], int (&wi)[K], int d, int idx) {
+  if (!M::less(d, wd[K - 1])) return;
+  bool placed = false;
+#pragma unroll
+  for (int p = K - 1; p >= 1; --p) {
+    if (!placed) {
+      if (M::less(d, wd[p - 1])) { wd[p] = wd[p - 1]; wi[p] = wi[p - 1]; }
+      else { wd[p] = d; wi[p] = idx; placed = true; }
+    }
+  }
+  if (!placed) { wd[0] = d; wi[0] = idx; }
+}
+template <int K>
+__device__ __forceinline__ void insert_dm(int (&wd)[K], int (&wi)[K], int d, int idx) {
+  if (!(d < wd[K - 1])) return;
+  bool placed = false;
+#pragma unroll
+  for (int p = K - 1; p >= 1; --p) {
+    if (!placed) {
+      if (!(wd[p - 1] < d)) { wd[p] = wd[p - 1]; wi[p] = wi[p - 1]; }
+      else { wd[p] = d; wi[p] = idx; placed = true; }
+    }
+  }
+  if (!placed) { wd[0] = d; wi[0] = idx; }
+}
+
+template <class M>
+constexpr size_t smem_bytes() {
+  return (size_t)TM * M::kKBytes + (size_t)STAGES * TN * M::kKBytes + (size_t)NORM_RING * TN * sizeof(int) + 64 * sizeof(uint64_t);
+}
+
+// operand row r of a tile with KB operand bytes per row: byte offset of its chunk 0
+template <int KB>
+__device__ __forceinline__ uint32_t row_offset(int r) {
+  return (uint32_t)(r >> 3) * (KB * 8) + (uint32_t)(r & 7) * 16;
+}
+
+template <class M, int K, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int KB = M::kKBytes;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)TM * KB;
+  int* sNorm = reinterpret_cast<int*>(sB + (size_t)STAGES * TN * KB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + NORM_RING * TN);
+  uint64_t* full = bars;                 // [STAGES] producers → MMA (count 128)
+  uint64_t* empty = bars + STAGES;       // [STAGES] MMA completion → producers (tcgen05.commit)
+  uint64_t* tfull = bars + 2 * STAGES;   // [STAGES] MMA completion → epilogue (tcgen05.commit)
+  uint64_t* tempty = bars + 3 * STAGES;  // [STAGES] epilogue → MMA (count 128)
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qb = blockIdx.x % p.nqb, part = blockIdx.x / p.nqb;
+  const int seg0 = (int)((long)part * p.n_seg / p.parts), seg1 = (int)((long)(part + 1) * p.n_seg / p.parts);
+
+  // ---- one-time setup: barriers, TMEM, the query operand ----
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      cvb_mbar_init(&full[s], 128);
+      cvb_mbar_init(&empty[s], 1);
+      cvb_mbar_init(&tfull[s], 1);
+      cvb_mbar_init(&tempty[s], 128);
+    }
+    cvb_fence_mbar_init();
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(cvb_smem_addr(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  int my_norm = 0;   // epilogue thread: norm term of its query
+  if (tid < TM) {
+    const int q = qb * TM + tid;
+    uint8_t* dst = sA + row_offset<KB>(tid);
+    if (q < p.nq) {
+      my_norm = M::expand_row(p.q + (size_t)q * M::kRowBytes, dst);
+    } else {
+      for (int c = 0; c < KB / 16; c++) *reinterpret_cast<uint4*>(dst + c * 128) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp >= 4 && warp < 8) {
+    // =================================== producers ===================================
+    const int pt = tid - 128;   // 0..127 → one train row of the tile
+    int n = 0;
+    for (int seg = seg0; seg < seg1; seg++) {
+      const int s_begin = p.seg_ptr[seg], len = p.seg_ptr[seg + 1] - s_begin;
+      for (int r0 = 0; r0 < len; r0 += TN, n++) {
+        const int s = n % STAGES;
+        if (n >= STAGES) cvb_mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
+        uint8_t* dst = sB + (size_t)s * TN * KB + row_offset<KB>(pt);
+        int nrm = 0;
+        const int row = r0 + pt;
+        bool valid = row < len;
+        if (MODE == 1 && valid && p.skipB) valid = p.skipB[s_begin + row] == 0;
+        if (row < len) {
+          nrm = M::expand_row(p.t + (size_t)(s_begin + row) * M::kRowBytes, dst);
+        } else {
+          for (int c = 0; c < KB / 16; c++) *reinterpret_cast<uint4*>(dst + c * 128) = make_uint4(0, 0, 0, 0);
+        }
+        sNorm[(n % NORM_RING) * TN + pt] = valid ? nrm : kInf;   // tail / skipped rows can never enter a list (d >= kInf)
+        fence_proxy_async();
+        mbar_arrive(&full[s]);
+      }
+    }
+  } else if (warp == 8) {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc();
+      const uint32_t a_addr = cvb_smem_addr(sA);
+      int n = 0;
+      for (int seg = seg0; seg < seg1; seg++) {
+        const int len = p.seg_ptr[seg + 1] - p.seg_ptr[seg];
+        for (int r0 = 0; r0 < len; r0 += TN, n++) {
+          const int s = n % STAGES;
+          const uint32_t ph = (n / STAGES) & 1;
+          cvb_mbar_wait(&full[s], ph);
+          if (n >= STAGES) cvb_mbar_wait(&tempty[s], ((n / STAGES) - 1) & 1);
+          tc_fence_after();
+          const uint32_t b_addr = cvb_smem_addr(sB + (size_t)s * TN * KB);
+          const uint32_t d_tmem = tmem_base + (uint32_t)s * TN;
+#pragma unroll
+          for (int k = 0; k < KB / 32; k++) {
+            const uint64_t ad = make_desc(a_addr + k * 256, 128, KB * 8);
+            const uint64_t bd = make_desc(b_addr + k * 256, 128, KB * 8);
+            tc_mma_i8(d_tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);   // shared-memory slot reusable once these MMAs have read it
+          tc_commit(&tfull[s]);   // accumulator ready
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================== epilogue (warps 0-3) ===================================
+    const int q = qb * TM + tid;
+    bool active = q < p.nq;
+    if (MODE == 1 && active && p.skipA) active = p.skipA[q] == 0;
+    int wd[K], wi[K];
+    int n = 0;
+    for (int seg = seg0; seg < seg1; seg++) {
+      const int len = p.seg_ptr[seg + 1] - p.seg_ptr[seg];
+#pragma unroll
+      for (int c = 0; c < K; c++) { wd[c] = (MODE == 1) ? p.ithr : kInf; wi[c] = -1; }
+      for (int r0 = 0; r0 < len; r0 += TN, n++) {
+        const int s = n % STAGES;
+        cvb_mbar_wait(&tfull[s], (n / STAGES) & 1);
+        tc_fence_after();
+        const int* nrm = sNorm + (n % NORM_RING) * TN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)s * TN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          uint32_t acc[32];
+          tc_ld32(taddr + c0, acc);
+          if (active) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              const int d = my_norm + nrm[c0 + i] - 2 * (int)acc[i];
+              if (d < wd[K - 1]) {
+                if (MODE == 1) insert_dm<K>(wd, wi, d, r0 + c0 + i);
+                else insert_bf<M, K>(wd, wi, d, r0 + c0 + i);
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[s]);
+      }
+      // ---- segment finished: write this query's result ----
+      const bool valid = q < p.nq;
+      if (MODE == 1) {
+        if (valid) {
+          const size_t o = ((size_t)seg * p.nq + q) * K;
+#pragma unroll
+          for (int c = 0; c < K; c++) {
+            const bool has = active && wi[c] >= 0;
+            p.out_idx[o + c] = has ? wi[c] : -1;
+            reinterpret_cast<int32_t*>(p.out_dist)[o + c] = has ? wd[c] : p.ithr;
+          }
+        }
+      } else if (p.filter) {
+        bool ok = false;
+        if (K >= 2 && valid) {
+          const float dm = M::fdist(wd[0]), dn = M::fdist(wd[K >= 2 ? 1 : 0]);
+          ok = wi[0] >= 0 && wi[K >= 2 ? 1 : 0] >= 0 && dm <= p.thr && dm < __fmul_rn(p.ratio, dn);
+          const size_t o = (size_t)seg * p.nq + q;
+          p.match_train[o] = ok ? wi[0] : -1;
+          p.match_dist[o] = ok ? dm : FLT_MAX;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0 && b) atomicAdd(&p.n_matches[seg], __popc(b));
+      } else if (valid) {
+        const size_t o = ((size_t)seg * p.nq + q) * K;
+#pragma unroll
+        for (int c = 0; c < K; c++) {
+          p.out_idx[o + c] = wi[c];
+          reinterpret_cast<typename M::dist_out_t*>(p.out_dist)[o + c] = wi[c] >= 0 ? M::out_dist(wd[c]) : M::empty_dist();
+        }
+      }
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+template <class M, int K, int MODE>
+int launch_tc(cvb_ctx* ctx, const TcParams& p, cudaStream_t st) {
+  static bool attr = false;
+  const size_t smem = smem_bytes<M>();
+  if (!attr) {
+    CVB_CUDA(ctx, cudaFuncSetAttribute(tc_scan_kernel<M, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  tc_scan_kernel<M, K, MODE><<<p.nqb * p.parts, NUM_THREADS, smem, st>>>(p);
+  CVB_CHECK_LAUNCH(ctx);
+  return CVB_OK;
+}
+
+bool profitable(const cvb_ctx* ctx, int nq, int n_seg, long total_rows) {
+  const char* e = getenv("COVINS_B200_MATCH_KERNEL");
+  if (e && !strcmp(e, "popc")) return false;
+  if (e && !strcmp(e, "tc")) return n_seg >= 1 && nq >= 1;
+  const int nqb = (nq + TM - 1) / TM;
+  const int want_parts = ctx->sm_count / nqb > 0 ? ctx->sm_count / nqb : 1;
+  return n_seg >= want_parts && (long)nq * total_rows >= (1L << 26);
+}
+
+int launch(cvb_ctx* ctx, TcParams p, int metric, int k, int mode, cudaStream_t st) {
+  p.nqb = (p.nq + TM - 1) / TM;
+  int parts = ctx->sm_count / p.nqb;
+  if (parts < 1) parts = 1;
+  if (parts > p.n_seg) parts = p.n_seg;
+  p.parts = parts;
+#define TC_CASE(MM, KK, MD) return launch_tc<MM, KK, MD>(ctx, p, st)
+  if (metric == 0) {
+    if (mode == 1) {
+      switch (k) { case 1: TC_CASE(TcHamming, 1, 1); case 2: TC_CASE(TcHamming, 2, 1); case 3: TC_CASE(TcHamming, 3, 1); default: TC_CASE(TcHamming, 4, 1); }
+    }
+    switch (k) { case 1: TC_CASE(TcHamming, 1, 0); case 2: TC_CASE(TcHamming, 2, 0); case 3: TC_CASE(TcHamming, 3, 0); default: TC_CASE(TcHamming, 4, 0); }
+  }
+  switch (k) { case 1: TC_CASE(TcL2, 1, 0); case 2: TC_CASE(TcL2, 2, 0); case 3: TC_CASE(TcL2, 3, 0); default: TC_CASE(TcL2, 4, 0); }
+#undef TC_CASE
+}
+
+}  // namespace cvb_tc

@@ -1,0 +1,32 @@
+// tc_match.cuh — interface of the tcgen05 (tensor-core) matching kernel, see tc_match.cu
+#pragma once
+#include "cvb_internal.cuh"
+
+namespace cvb_tc {
+
+struct TcParams {
+  const uint8_t* q;
+  int nq;
+  const uint8_t* t;
+  const int32_t* seg_ptr;
+  int n_seg;
+  int nqb, parts;           // filled by launch()
+  int32_t* out_idx;
+  void* out_dist;
+  const uint8_t* skipA;
+  const uint8_t* skipB;
+  int ithr;
+  int filter;
+  float thr, ratio;
+  int32_t* match_train;
+  float* match_dist;
+  int32_t* n_matches;
+};
+
+// metric 0 = Hamming (32-byte rows), 1 = L2 on u8 (128-byte rows); mode 0 = OpenCV k-NN rule, 1 = DenseMatcher lists
+int launch(cvb_ctx* ctx, TcParams p, int metric, int k, int mode, cudaStream_t st);
+
+// true when the tensor-core kernel fills the GPU for this shape (enough candidate segments per query block)
+bool profitable(const cvb_ctx* ctx, int nq, int n_seg, long total_rows);
+
+}  // namespace cvb_tc
