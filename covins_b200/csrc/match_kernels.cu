@@ -651,7 +651,7 @@ int knn_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, const 
     tp.q = d_q; tp.nq = nq; tp.t = d_t; tp.seg_ptr = d_seg_ptr; tp.n_seg = n_seg;
     tp.out_idx = d_idx; tp.out_dist = d_dist; tp.filter = filter ? 1 : 0; tp.thr = thr; tp.ratio = ratio;
     tp.match_train = d_match_train; tp.match_dist = d_match_dist; tp.n_matches = d_n_matches;
-    return cvb_tc::launch(ctx, tp, M::kIsL2 ? 1 : 0, k, 0, st);
+    return cvb_tc::launch(ctx, tp, M::kIsL2 ? 1 : 0, k, st);
   }
   const Plan pl = make_plan<M>(nq, n_seg, max_len, ctx->sm_count, QPT_BIG, true);
   ScanParams sp{};
@@ -865,13 +865,6 @@ int cvb_landmark_match_batch_dev(cvb_ctx* ctx, const uint8_t* d_A, const uint8_t
   int32_t* li = (int32_t*)cvb_ws(ctx, WS_LIST_I, ln * 4);
   int32_t* ld = (int32_t*)cvb_ws(ctx, WS_LIST_D, ln * 4);
   if (!li || !ld) return CVB_ERR_CUDA;
-  if (cvb_tc::profitable(ctx, nA, n_seg, (long)total)) {
-    cvb_tc::TcParams tp{};
-    tp.q = d_A; tp.nq = nA; tp.t = d_B; tp.seg_ptr = d_seg_ptr; tp.n_seg = n_seg;
-    tp.out_idx = li; tp.out_dist = ld; tp.skipA = d_skipA; tp.skipB = d_skipB; tp.ithr = ithr;
-    rc = cvb_tc::launch(ctx, tp, 0, num_best, 1, st);
-    if (rc) return rc;
-  } else {
   Plan pl = make_plan<HammingMetric>(nA, n_seg, max_len, ctx->sm_count, 4, false);
   ScanParams sp{};
   sp.q = d_A; sp.nq = nA; sp.t = d_B; sp.seg_ptr = d_seg_ptr; sp.n_seg = n_seg;
@@ -879,7 +872,6 @@ int cvb_landmark_match_batch_dev(cvb_ctx* ctx, const uint8_t* d_A, const uint8_t
   sp.skipA = d_skipA; sp.skipB = d_skipB; sp.ithr = ithr;
   rc = dispatch_scan<HammingMetric, 4, MODE_DM>(ctx, sp, pl, num_best, st);
   if (rc) return rc;
-  }
   const size_t smem = ((size_t)2 * nA * num_best + (size_t)2 * max_len) * sizeof(int32_t);
   if (smem <= 200 * 1024) {
     static size_t attr = 0;

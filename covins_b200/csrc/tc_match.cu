@@ -31,7 +31,6 @@ constexpr int TM = 128;       // queries per CTA (UMMA M)
 constexpr int TN = 128;       // train rows per tile (UMMA N)
 constexpr int STAGES = 4;
 constexpr int NORM_RING = 8;
-constexpr int NUM_THREADS = 288;   // 4 epilogue + 4 producer + 1 MMA warp
 constexpr int kInf = 0x3FFFFFFF;   // list sentinel; rows that must never enter carry this as their norm term
 
 // ---- mbarrier / tcgen05 wrappers -------------------------------------------------------------------------------
@@ -137,36 +136,47 @@ struct TcL2 {
   static __device__ __forceinline__ float empty_dist() { return FLT_MAX; }
 };
 
-template <class M, int K>
-__device__ __forceinline__ void insert_bf(int (&wd)[K], int (&wi)[K], int d, int idx) {
-  if (!M::less(d, wd[K - 1])) return;
-  bool placed = false;
-#pragma unroll
-  for (int p = K - 1; p >= 1; --p) {
-    if (!placed) {
-      if (M::less(d, wd[p - 1])) { wd[p] = wd[p - 1]; wi[p] = wi[p - 1]; }
-      else { wd[p] = d; wi[p] = idx; placed = true; }
-    }
-  }
-  if (!placed) { wd[0] = d; wi[0] = idx; }
-}
+// k-list of (key, idx) kept sorted ascending by (key, idx); OpenCV rule for a stream with ascending idx:
+// enter iff key < worst key; placed after all entries with key <= new key.
 template <int K>
-__device__ __forceinline__ void insert_dm(int (&wd)[K], int (&wi)[K], int d, int idx) {
-  if (!(d < wd[K - 1])) return;
+__device__ __forceinline__ void insert_key(int (&wk)[K], int (&wi)[K], int key, int idx) {
+  if (!(key < wk[K - 1])) return;
   bool placed = false;
 #pragma unroll
   for (int p = K - 1; p >= 1; --p) {
     if (!placed) {
-      if (!(wd[p - 1] < d)) { wd[p] = wd[p - 1]; wi[p] = wi[p - 1]; }
-      else { wd[p] = d; wi[p] = idx; placed = true; }
+      if (key < wk[p - 1]) { wk[p] = wk[p - 1]; wi[p] = wi[p - 1]; }
+      else { wk[p] = key; wi[p] = idx; placed = true; }
     }
   }
-  if (!placed) { wd[0] = d; wi[0] = idx; }
+  if (!placed) { wk[0] = key; wi[0] = idx; }
+}
+// merge rule for partial lists of disjoint row subsets: k smallest by (key, idx)
+template <int K>
+__device__ __forceinline__ void insert_lex(int (&wk)[K], int (&wi)[K], int key, int idx) {
+  auto lt = [](int k1, int i1, int k2, int i2) { return k1 < k2 || (k1 == k2 && (unsigned)i1 < (unsigned)i2); };
+  if (!lt(key, idx, wk[K - 1], wi[K - 1])) return;
+  bool placed = false;
+#pragma unroll
+  for (int p = K - 1; p >= 1; --p) {
+    if (!placed) {
+      if (lt(key, idx, wk[p - 1], wi[p - 1])) { wk[p] = wk[p - 1]; wi[p] = wi[p - 1]; }
+      else { wk[p] = key; wi[p] = idx; placed = true; }
+    }
+  }
+  if (!placed) { wk[0] = key; wi[0] = idx; }
 }
 
-template <class M>
+constexpr int GROUPS = 4;                       // epilogue column groups: group g owns columns [32 g, 32 g + 32) of every tile
+constexpr int EPI_THREADS = 128 * GROUPS;       // 16 epilogue warps
+constexpr int PROD_WARP0 = EPI_THREADS / 32;    // producer warps 16..19
+constexpr int MMA_WARP = PROD_WARP0 + 4;        // warp 20
+constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;
+
+template <class M, int K>
 constexpr size_t smem_bytes() {
-  return (size_t)TM * M::kKBytes + (size_t)STAGES * TN * M::kKBytes + (size_t)NORM_RING * TN * sizeof(int) + 64 * sizeof(uint64_t);
+  return (size_t)TM * M::kKBytes + (size_t)STAGES * TN * M::kKBytes + (size_t)NORM_RING * TN * sizeof(int) +
+         (size_t)2 * TM * GROUPS * K * 2 * sizeof(int) + 64 * sizeof(uint64_t);
 }
 
 // operand row r of a tile with KB operand bytes per row: byte offset of its chunk 0
@@ -175,19 +185,25 @@ __device__ __forceinline__ uint32_t row_offset(int r) {
   return (uint32_t)(r >> 3) * (KB * 8) + (uint32_t)(r & 7) * 16;
 }
 
-template <class M, int K, int MODE>
+// keys: Hamming → the distance; L2 → the bit pattern of sqrtf(d2) (non-negative floats order like their bits), which
+// is what OpenCV compares.  kInfKey is larger than any real key of either kind.
+constexpr int kInfKey = 0x7F000000;
+
+template <class M, int K>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int KB = M::kKBytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)TM * KB;
   int* sNorm = reinterpret_cast<int*>(sB + (size_t)STAGES * TN * KB);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + NORM_RING * TN);
+  int* sList = sNorm + NORM_RING * TN;                       // [2][TM][GROUPS][K][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sList + 2 * TM * GROUPS * K * 2);
   uint64_t* full = bars;                 // [STAGES] producers → MMA (count 128)
   uint64_t* empty = bars + STAGES;       // [STAGES] MMA completion → producers (tcgen05.commit)
   uint64_t* tfull = bars + 2 * STAGES;   // [STAGES] MMA completion → epilogue (tcgen05.commit)
-  uint64_t* tempty = bars + 3 * STAGES;  // [STAGES] epilogue → MMA (count 128)
+  uint64_t* tempty = bars + 3 * STAGES;  // [STAGES] epilogue → MMA (count EPI_THREADS)
   __shared__ uint32_t tmem_base_s;
+  __shared__ int sQNorm[TM];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qb = blockIdx.x % p.nqb, part = blockIdx.x / p.nqb;
@@ -199,23 +215,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
       cvb_mbar_init(&full[s], 128);
       cvb_mbar_init(&empty[s], 1);
       cvb_mbar_init(&tfull[s], 1);
-      cvb_mbar_init(&tempty[s], 128);
+      cvb_mbar_init(&tempty[s], EPI_THREADS);
     }
     cvb_fence_mbar_init();
   }
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(cvb_smem_addr(&tmem_base_s)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  int my_norm = 0;   // epilogue thread: norm term of its query
   if (tid < TM) {
     const int q = qb * TM + tid;
     uint8_t* dst = sA + row_offset<KB>(tid);
+    int nrm = 0;
     if (q < p.nq) {
-      my_norm = M::expand_row(p.q + (size_t)q * M::kRowBytes, dst);
+      nrm = M::expand_row(p.q + (size_t)q * M::kRowBytes, dst);
     } else {
       for (int c = 0; c < KB / 16; c++) *reinterpret_cast<uint4*>(dst + c * 128) = make_uint4(0, 0, 0, 0);
     }
+    sQNorm[tid] = nrm;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -223,9 +240,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= PROD_WARP0 && warp < MMA_WARP) {
     // =================================== producers ===================================
-    const int pt = tid - 128;   // 0..127 → one train row of the tile
+    const int pt = tid - PROD_WARP0 * 32;   // 0..127 → one train row of the tile
     int n = 0;
     for (int seg = seg0; seg < seg1; seg++) {
       const int s_begin = p.seg_ptr[seg], len = p.seg_ptr[seg + 1] - s_begin;
@@ -233,21 +250,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
         const int s = n % STAGES;
         if (n >= STAGES) cvb_mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
         uint8_t* dst = sB + (size_t)s * TN * KB + row_offset<KB>(pt);
-        int nrm = 0;
+        int nrm = kInf;   // tail rows can never enter a list
         const int row = r0 + pt;
-        bool valid = row < len;
-        if (MODE == 1 && valid && p.skipB) valid = p.skipB[s_begin + row] == 0;
         if (row < len) {
           nrm = M::expand_row(p.t + (size_t)(s_begin + row) * M::kRowBytes, dst);
         } else {
           for (int c = 0; c < KB / 16; c++) *reinterpret_cast<uint4*>(dst + c * 128) = make_uint4(0, 0, 0, 0);
         }
-        sNorm[(n % NORM_RING) * TN + pt] = valid ? nrm : kInf;   // tail / skipped rows can never enter a list (d >= kInf)
+        sNorm[(n % NORM_RING) * TN + pt] = nrm;
         fence_proxy_async();
         mbar_arrive(&full[s]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // =================================== MMA issuer ===================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc();
@@ -276,69 +291,91 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
     }
     __syncwarp();
   } else {
-    // =================================== epilogue (warps 0-3) ===================================
-    const int q = qb * TM + tid;
-    bool active = q < p.nq;
-    if (MODE == 1 && active && p.skipA) active = p.skipA[q] == 0;
-    int wd[K], wi[K];
-    int n = 0;
-    for (int seg = seg0; seg < seg1; seg++) {
+    // =================================== epilogue (warps 0..15) ===================================
+    const int grp = warp >> 2;                  // column group
+    const int row = (warp & 3) * 32 + lane;     // TMEM lane = query row inside the block
+    const int q = qb * TM + row;
+    const bool valid = q < p.nq;
+    const int qn = sQNorm[row];
+    int wk[K], wi[K], wd2[K];                   // key, index, raw integer distance (pre-test only)
+    int n = 0, segc = 0;
+    for (int seg = seg0; seg < seg1; seg++, segc++) {
       const int len = p.seg_ptr[seg + 1] - p.seg_ptr[seg];
 #pragma unroll
-      for (int c = 0; c < K; c++) { wd[c] = (MODE == 1) ? p.ithr : kInf; wi[c] = -1; }
+      for (int c = 0; c < K; c++) { wk[c] = kInfKey; wi[c] = -1; wd2[c] = kInf; }
       for (int r0 = 0; r0 < len; r0 += TN, n++) {
         const int s = n % STAGES;
         cvb_mbar_wait(&tfull[s], (n / STAGES) & 1);
         tc_fence_after();
-        const int* nrm = sNorm + (n % NORM_RING) * TN;
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)s * TN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-          uint32_t acc[32];
-          tc_ld32(taddr + c0, acc);
-          if (active) {
+        const int4* nrm4 = reinterpret_cast<const int4*>(sNorm + (n % NORM_RING) * TN + grp * 32);
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)s * TN + grp * 32;
+        uint32_t acc[32];
+        tc_ld32(taddr, acc);
+        if (valid) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-              const int d = my_norm + nrm[c0 + i] - 2 * (int)acc[i];
-              if (d < wd[K - 1]) {
-                if (MODE == 1) insert_dm<K>(wd, wi, d, r0 + c0 + i);
-                else insert_bf<M, K>(wd, wi, d, r0 + c0 + i);
+          for (int i4 = 0; i4 < 8; i4++) {
+            const int4 nn = nrm4[i4];
+            const int nv[4] = {nn.x, nn.y, nn.z, nn.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int i = 4 * i4 + j;
+              const int d = qn + nv[j] - 2 * (int)acc[i];
+              if (d < wd2[K - 1]) {
+                const int key = M::kIsL2 ? __float_as_int(__fsqrt_rn((float)d)) : d;
+                if (key < wk[K - 1]) {
+                  insert_key<K>(wk, wi, key, r0 + grp * 32 + i);
+                  // raw distance of the current worst entry, for the integer pre-test
+                  if (M::kIsL2) {
+                    const float f = __int_as_float(wk[K - 1]);
+                    wd2[K - 1] = wk[K - 1] == kInfKey ? kInf : (int)ceilf(f * f * 1.000001f) + 1;
+                  } else {
+                    wd2[K - 1] = wk[K - 1] == kInfKey ? kInf : wk[K - 1];
+                  }
+                }
               }
             }
           }
         }
         tc_fence_before();
-        mbar_arrive(&tempty[s]);
+        mbar_arrive(&tempty[s]);   // accumulator and norms consumed: the MMA warp may overwrite this TMEM stage
       }
-      // ---- segment finished: write this query's result ----
-      const bool valid = q < p.nq;
-      if (MODE == 1) {
-        if (valid) {
+      // ---- segment finished: combine the 4 column-group lists of each query (k smallest by (key, idx)) ----
+      int* lst = sList + (size_t)(segc & 1) * TM * GROUPS * K * 2;
+#pragma unroll
+      for (int c = 0; c < K; c++) {
+        lst[((row * GROUPS + grp) * K + c) * 2 + 0] = wk[c];
+        lst[((row * GROUPS + grp) * K + c) * 2 + 1] = wi[c];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (grp == 0) {
+#pragma unroll
+        for (int c = 0; c < K; c++) { wk[c] = kInfKey; wi[c] = -1; }
+        for (int g2 = 0; g2 < GROUPS; g2++)
+#pragma unroll
+          for (int c = 0; c < K; c++) {
+            const int kk = lst[((row * GROUPS + g2) * K + c) * 2], ii = lst[((row * GROUPS + g2) * K + c) * 2 + 1];
+            if (ii >= 0) insert_lex<K>(wk, wi, kk, ii);
+          }
+        if (p.filter) {
+          bool ok = false;
+          if (K >= 2 && valid) {
+            const float dm = M::kIsL2 ? __int_as_float(wk[0]) : (float)wk[0];
+            const float dn = M::kIsL2 ? __int_as_float(wk[K >= 2 ? 1 : 0]) : (float)wk[K >= 2 ? 1 : 0];
+            ok = wi[0] >= 0 && wi[K >= 2 ? 1 : 0] >= 0 && dm <= p.thr && dm < __fmul_rn(p.ratio, dn);
+            const size_t o = (size_t)seg * p.nq + q;
+            p.match_train[o] = ok ? wi[0] : -1;
+            p.match_dist[o] = ok ? dm : FLT_MAX;
+          }
+          const unsigned b = __ballot_sync(0xffffffffu, ok);
+          if (lane == 0 && b) atomicAdd(&p.n_matches[seg], __popc(b));
+        } else if (valid) {
           const size_t o = ((size_t)seg * p.nq + q) * K;
 #pragma unroll
           for (int c = 0; c < K; c++) {
-            const bool has = active && wi[c] >= 0;
-            p.out_idx[o + c] = has ? wi[c] : -1;
-            reinterpret_cast<int32_t*>(p.out_dist)[o + c] = has ? wd[c] : p.ithr;
+            p.out_idx[o + c] = wi[c];
+            if (M::kIsL2) reinterpret_cast<float*>(p.out_dist)[o + c] = wi[c] >= 0 ? __int_as_float(wk[c]) : FLT_MAX;
+            else reinterpret_cast<int32_t*>(p.out_dist)[o + c] = wi[c] >= 0 ? wk[c] : INT_MAX;
           }
-        }
-      } else if (p.filter) {
-        bool ok = false;
-        if (K >= 2 && valid) {
-          const float dm = M::fdist(wd[0]), dn = M::fdist(wd[K >= 2 ? 1 : 0]);
-          ok = wi[0] >= 0 && wi[K >= 2 ? 1 : 0] >= 0 && dm <= p.thr && dm < __fmul_rn(p.ratio, dn);
-          const size_t o = (size_t)seg * p.nq + q;
-          p.match_train[o] = ok ? wi[0] : -1;
-          p.match_dist[o] = ok ? dm : FLT_MAX;
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0 && b) atomicAdd(&p.n_matches[seg], __popc(b));
-      } else if (valid) {
-        const size_t o = ((size_t)seg * p.nq + q) * K;
-#pragma unroll
-        for (int c = 0; c < K; c++) {
-          p.out_idx[o + c] = wi[c];
-          reinterpret_cast<typename M::dist_out_t*>(p.out_dist)[o + c] = wi[c] >= 0 ? M::out_dist(wd[c]) : M::empty_dist();
         }
       }
     }
@@ -346,21 +383,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
   }
 }
 
-template <class M, int K, int MODE>
+template <class M, int K>
 int launch_tc(cvb_ctx* ctx, const TcParams& p, cudaStream_t st) {
   static bool attr = false;
-  const size_t smem = smem_bytes<M>();
+  const size_t smem = smem_bytes<M, K>();
   if (!attr) {
-    CVB_CUDA(ctx, cudaFuncSetAttribute(tc_scan_kernel<M, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CVB_CUDA(ctx, cudaFuncSetAttribute(tc_scan_kernel<M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  tc_scan_kernel<M, K, MODE><<<p.nqb * p.parts, NUM_THREADS, smem, st>>>(p);
+  tc_scan_kernel<M, K><<<p.nqb * p.parts, NUM_THREADS, smem, st>>>(p);
   CVB_CHECK_LAUNCH(ctx);
   return CVB_OK;
 }
@@ -374,20 +411,17 @@ bool profitable(const cvb_ctx* ctx, int nq, int n_seg, long total_rows) {
   return n_seg >= want_parts && (long)nq * total_rows >= (1L << 26);
 }
 
-int launch(cvb_ctx* ctx, TcParams p, int metric, int k, int mode, cudaStream_t st) {
+int launch(cvb_ctx* ctx, TcParams p, int metric, int k, cudaStream_t st) {
   p.nqb = (p.nq + TM - 1) / TM;
   int parts = ctx->sm_count / p.nqb;
   if (parts < 1) parts = 1;
   if (parts > p.n_seg) parts = p.n_seg;
   p.parts = parts;
-#define TC_CASE(MM, KK, MD) return launch_tc<MM, KK, MD>(ctx, p, st)
+#define TC_CASE(MM, KK) return launch_tc<MM, KK>(ctx, p, st)
   if (metric == 0) {
-    if (mode == 1) {
-      switch (k) { case 1: TC_CASE(TcHamming, 1, 1); case 2: TC_CASE(TcHamming, 2, 1); case 3: TC_CASE(TcHamming, 3, 1); default: TC_CASE(TcHamming, 4, 1); }
-    }
-    switch (k) { case 1: TC_CASE(TcHamming, 1, 0); case 2: TC_CASE(TcHamming, 2, 0); case 3: TC_CASE(TcHamming, 3, 0); default: TC_CASE(TcHamming, 4, 0); }
+    switch (k) { case 1: TC_CASE(TcHamming, 1); case 2: TC_CASE(TcHamming, 2); case 3: TC_CASE(TcHamming, 3); default: TC_CASE(TcHamming, 4); }
   }
-  switch (k) { case 1: TC_CASE(TcL2, 1, 0); case 2: TC_CASE(TcL2, 2, 0); case 3: TC_CASE(TcL2, 3, 0); default: TC_CASE(TcL2, 4, 0); }
+  switch (k) { case 1: TC_CASE(TcL2, 1); case 2: TC_CASE(TcL2, 2); case 3: TC_CASE(TcL2, 3); default: TC_CASE(TcL2, 4); }
 #undef TC_CASE
 }
 

@@ -23,8 +23,9 @@ struct TcParams {
   int32_t* n_matches;
 };
 
-// metric 0 = Hamming (32-byte rows), 1 = L2 on u8 (128-byte rows); mode 0 = OpenCV k-NN rule, 1 = DenseMatcher lists
-int launch(cvb_ctx* ctx, TcParams p, int metric, int k, int mode, cudaStream_t st);
+// metric 0 = Hamming (32-byte rows), 1 = L2 on u8 (128-byte rows); OpenCV k-NN rule (the DenseMatcher list rule is
+// order dependent and stays on the scalar kernel)
+int launch(cvb_ctx* ctx, TcParams p, int metric, int k, cudaStream_t st);
 
 // true when the tensor-core kernel fills the GPU for this shape (enough candidate segments per query block)
 bool profitable(const cvb_ctx* ctx, int nq, int n_seg, long total_rows);
