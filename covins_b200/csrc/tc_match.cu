@@ -87,53 +87,53 @@ __device__ __forceinline__ uint4 ldg_nc(const void* p) {
 }
 
 // ---- metrics: how a packed row becomes a K-major operand row, and its additive norm term ----------------------
+// A row is handled by TWO threads (half = 0/1), each loading kLoads 16-byte pieces of the packed row (so that the loads
+// of several tiles can be kept in flight in registers) and writing its share of the operand chunks.
 struct TcHamming {
   static constexpr int kRowBytes = 32;    // packed bytes in HBM
   static constexpr int kKBytes = 256;     // operand bytes (one byte per bit)
+  static constexpr int kLoads = 1;        // uint4 per half row
+  static constexpr int kPrefetch = 3;     // tiles in flight per producer thread
   static constexpr bool kIsL2 = false;
-  using dist_out_t = int32_t;
-  // writes the 256 operand bytes of one row (16 chunks of 16 B) and returns popc(row)
-  static __device__ __forceinline__ int expand_row(const uint8_t* __restrict__ src, uint8_t* dst_row0 /*chunk 0 of this row*/) {
-    const uint4 a = ldg_nc(src), b = ldg_nc(src + 16);
-    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  static __device__ __forceinline__ void load_half(const uint8_t* __restrict__ row, int half, uint4 (&v)[kLoads]) {
+    v[0] = ldg_nc(row + 16 * half);
+  }
+  // writes operand chunks 8 half .. 8 half + 7 of the row and returns the partial popcount
+  static __device__ __forceinline__ int store_half(const uint4 (&v)[kLoads], int half, uint8_t* dst_row0) {
+    const uint32_t w[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
     int pc = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < 4; i++) {
       pc += __popc(w[i]);
       // byte j of output word k holds bit (k + 8 j) of w[i]; the same permutation is applied to queries and train rows
       uint4 lo, hi;
       lo.x = (w[i] >> 0) & 0x01010101u; lo.y = (w[i] >> 1) & 0x01010101u; lo.z = (w[i] >> 2) & 0x01010101u; lo.w = (w[i] >> 3) & 0x01010101u;
       hi.x = (w[i] >> 4) & 0x01010101u; hi.y = (w[i] >> 5) & 0x01010101u; hi.z = (w[i] >> 6) & 0x01010101u; hi.w = (w[i] >> 7) & 0x01010101u;
-      *reinterpret_cast<uint4*>(dst_row0 + (2 * i) * 128) = lo;
-      *reinterpret_cast<uint4*>(dst_row0 + (2 * i + 1) * 128) = hi;
+      *reinterpret_cast<uint4*>(dst_row0 + (8 * half + 2 * i) * 128) = lo;
+      *reinterpret_cast<uint4*>(dst_row0 + (8 * half + 2 * i + 1) * 128) = hi;
     }
     return pc;
   }
-  static __device__ __forceinline__ bool less(int a, int b) { return a < b; }
-  static __device__ __forceinline__ int32_t out_dist(int d) { return d; }
-  static __device__ __forceinline__ float fdist(int d) { return (float)d; }
-  static __device__ __forceinline__ int32_t empty_dist() { return INT_MAX; }
 };
 struct TcL2 {
   static constexpr int kRowBytes = 128;
   static constexpr int kKBytes = 128;
+  static constexpr int kLoads = 4;
+  static constexpr int kPrefetch = 2;
   static constexpr bool kIsL2 = true;
-  using dist_out_t = float;
-  static __device__ __forceinline__ int expand_row(const uint8_t* __restrict__ src, uint8_t* dst_row0) {
+  static __device__ __forceinline__ void load_half(const uint8_t* __restrict__ row, int half, uint4 (&v)[kLoads]) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) v[c] = ldg_nc(row + 64 * half + 16 * c);
+  }
+  static __device__ __forceinline__ int store_half(const uint4 (&v)[kLoads], int half, uint8_t* dst_row0) {
     unsigned n2 = 0;
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-      const uint4 v = ldg_nc(src + 16 * c);
-      n2 = __dp4a(v.x, v.x, n2); n2 = __dp4a(v.y, v.y, n2); n2 = __dp4a(v.z, v.z, n2); n2 = __dp4a(v.w, v.w, n2);
-      *reinterpret_cast<uint4*>(dst_row0 + c * 128) = v;
+    for (int c = 0; c < 4; c++) {
+      n2 = __dp4a(v[c].x, v[c].x, n2); n2 = __dp4a(v[c].y, v[c].y, n2); n2 = __dp4a(v[c].z, v[c].z, n2); n2 = __dp4a(v[c].w, v[c].w, n2);
+      *reinterpret_cast<uint4*>(dst_row0 + (4 * half + c) * 128) = v[c];
     }
     return (int)n2;
   }
-  // OpenCV selects on sqrtf(d2): different d2 can round to the same float → tie (see match_kernels.cu L2Metric)
-  static __device__ __forceinline__ bool less(int a, int b) { return a < b && __fsqrt_rn((float)a) < __fsqrt_rn((float)b); }
-  static __device__ __forceinline__ float out_dist(int d) { return __fsqrt_rn((float)d); }
-  static __device__ __forceinline__ float fdist(int d) { return __fsqrt_rn((float)d); }
-  static __device__ __forceinline__ float empty_dist() { return FLT_MAX; }
 };
 
 // k-list of (key, idx) kept sorted ascending by (key, idx); OpenCV rule for a stream with ascending idx:
@@ -169,8 +169,9 @@ __device__ __forceinline__ void insert_lex(int (&wk)[K], int (&wi)[K], int key, 
 
 constexpr int GROUPS = 4;                       // epilogue column groups: group g owns columns [32 g, 32 g + 32) of every tile
 constexpr int EPI_THREADS = 128 * GROUPS;       // 16 epilogue warps
-constexpr int PROD_WARP0 = EPI_THREADS / 32;    // producer warps 16..19
-constexpr int MMA_WARP = PROD_WARP0 + 4;        // warp 20
+constexpr int PROD_WARP0 = EPI_THREADS / 32;    // producer warps 16..23 (two threads per train row)
+constexpr int PROD_THREADS = 256;
+constexpr int MMA_WARP = PROD_WARP0 + PROD_THREADS / 32;   // warp 24
 constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;
 
 template <class M, int K>
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
   // ---- one-time setup: barriers, TMEM, the query operand ----
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
-      cvb_mbar_init(&full[s], 128);
+      cvb_mbar_init(&full[s], PROD_THREADS);
       cvb_mbar_init(&empty[s], 1);
       cvb_mbar_init(&tfull[s], 1);
       cvb_mbar_init(&tempty[s], EPI_THREADS);
@@ -223,16 +224,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(cvb_smem_addr(&tmem_base_s)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid < TM) {
-    const int q = qb * TM + tid;
-    uint8_t* dst = sA + row_offset<KB>(tid);
+  if (tid < 2 * TM) {
+    const int r = tid >> 1, half = tid & 1;
+    const int q = qb * TM + r;
+    uint8_t* dst = sA + row_offset<KB>(r);
     int nrm = 0;
     if (q < p.nq) {
-      nrm = M::expand_row(p.q + (size_t)q * M::kRowBytes, dst);
+      uint4 v[M::kLoads];
+      M::load_half(p.q + (size_t)q * M::kRowBytes, half, v);
+      nrm = M::store_half(v, half, dst);
     } else {
-      for (int c = 0; c < KB / 16; c++) *reinterpret_cast<uint4*>(dst + c * 128) = make_uint4(0, 0, 0, 0);
+      for (int c = 0; c < KB / 32; c++) *reinterpret_cast<uint4*>(dst + (half * (KB / 32) + c) * 128) = make_uint4(0, 0, 0, 0);
     }
-    sQNorm[tid] = nrm;
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);
+    if (half == 0) sQNorm[r] = nrm;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -242,24 +247,65 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
 
   if (warp >= PROD_WARP0 && warp < MMA_WARP) {
     // =================================== producers ===================================
-    const int pt = tid - PROD_WARP0 * 32;   // 0..127 → one train row of the tile
+    // Two threads per train row; the packed rows of the next kPrefetch tiles are held in registers so that the HBM
+    // latency (~1 us) of a tile overlaps the expansion of the previous ones.
+    const int pt = tid - PROD_WARP0 * 32;   // 0..255
+    const int prow = pt >> 1, half = pt & 1;
+    struct TileIt {
+      int seg, r0, s_begin, len, seg1;
+      const int32_t* sp;
+      bool done;
+      __device__ void next_seg() {
+        do {
+          seg++;
+          if (seg >= seg1) { done = true; return; }
+          s_begin = sp[seg];
+          len = sp[seg + 1] - s_begin;
+        } while (len == 0);
+        r0 = 0;
+      }
+      __device__ void advance() { r0 += TN; if (r0 >= len) next_seg(); }
+    };
+    TileIt it{seg0 - 1, 0, 0, 0, seg1, p.seg_ptr, false}, ld = it;
+    it.next_seg();
+    ld.next_seg();
+    constexpr int PF = M::kPrefetch;
+    uint4 pf[PF][M::kLoads];
+    auto issue_load = [&](uint4 (&v)[M::kLoads]) {
+      if (!ld.done) {
+        const int row = ld.r0 + prow;
+        if (row < ld.len) M::load_half(p.t + (size_t)(ld.s_begin + row) * M::kRowBytes, half, v);
+        ld.advance();
+      }
+    };
+#pragma unroll
+    for (int u = 0; u < PF; u++) issue_load(pf[u]);
     int n = 0;
-    for (int seg = seg0; seg < seg1; seg++) {
-      const int s_begin = p.seg_ptr[seg], len = p.seg_ptr[seg + 1] - s_begin;
-      for (int r0 = 0; r0 < len; r0 += TN, n++) {
+    while (!it.done) {
+#pragma unroll
+      for (int u = 0; u < PF; u++) {
+        if (it.done) break;
+        uint4 cur[M::kLoads];
+#pragma unroll
+        for (int c = 0; c < M::kLoads; c++) cur[c] = pf[u][c];
+        issue_load(pf[u]);   // refill this register slot with the tile PF steps ahead
         const int s = n % STAGES;
         if (n >= STAGES) cvb_mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
-        uint8_t* dst = sB + (size_t)s * TN * KB + row_offset<KB>(pt);
-        int nrm = kInf;   // tail rows can never enter a list
-        const int row = r0 + pt;
-        if (row < len) {
-          nrm = M::expand_row(p.t + (size_t)(s_begin + row) * M::kRowBytes, dst);
+        uint8_t* dst = sB + (size_t)s * TN * KB + row_offset<KB>(prow);
+        const bool rv = it.r0 + prow < it.len;
+        int part = 0;
+        if (rv) {
+          part = M::store_half(cur, half, dst);
         } else {
-          for (int c = 0; c < KB / 16; c++) *reinterpret_cast<uint4*>(dst + c * 128) = make_uint4(0, 0, 0, 0);
+          for (int c = 0; c < KB / 32; c++) *reinterpret_cast<uint4*>(dst + (half * (KB / 32) + c) * 128) = make_uint4(0, 0, 0, 0);
         }
-        sNorm[(n % NORM_RING) * TN + pt] = nrm;
+        part += __shfl_xor_sync(0xffffffffu, part, 1);   // the two halves of a row sit in adjacent lanes
+        const int nrm = rv ? part : kInf;                // tail rows can never enter a list
+        if (half == 0) sNorm[(n % NORM_RING) * TN + prow] = nrm;
         fence_proxy_async();
         mbar_arrive(&full[s]);
+        it.advance();
+        n++;
       }
     }
   } else if (warp == MMA_WARP) {
