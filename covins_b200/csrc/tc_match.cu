@@ -105,10 +105,12 @@ struct TcHamming {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       pc += __popc(w[i]);
-      // byte j of output word k holds bit (k + 8 j) of w[i]; the same permutation is applied to queries and train rows
+      // byte j of output word k is 0x80 if bit (k + 8 j) of w[i] is set, else 0 (the same permutation and the same
+      // 0/128 encoding on both operands → accumulator = 16384 * popc(a & b)).  The left shift is a multiply so that it
+      // issues on the FMA pipe; only the mask uses the (narrower) ALU pipe.
       uint4 lo, hi;
-      lo.x = (w[i] >> 0) & 0x01010101u; lo.y = (w[i] >> 1) & 0x01010101u; lo.z = (w[i] >> 2) & 0x01010101u; lo.w = (w[i] >> 3) & 0x01010101u;
-      hi.x = (w[i] >> 4) & 0x01010101u; hi.y = (w[i] >> 5) & 0x01010101u; hi.z = (w[i] >> 6) & 0x01010101u; hi.w = (w[i] >> 7) & 0x01010101u;
+      lo.x = (w[i] * 128u) & 0x80808080u; lo.y = (w[i] * 64u) & 0x80808080u; lo.z = (w[i] * 32u) & 0x80808080u; lo.w = (w[i] * 16u) & 0x80808080u;
+      hi.x = (w[i] * 8u) & 0x80808080u; hi.y = (w[i] * 4u) & 0x80808080u; hi.z = (w[i] * 2u) & 0x80808080u; hi.w = w[i] & 0x80808080u;
       *reinterpret_cast<uint4*>(dst_row0 + (8 * half + 2 * i) * 128) = lo;
       *reinterpret_cast<uint4*>(dst_row0 + (8 * half + 2 * i + 1) * 128) = hi;
     }
@@ -189,6 +191,7 @@ __device__ __forceinline__ uint32_t row_offset(int r) {
 // keys: Hamming → the distance; L2 → the bit pattern of sqrtf(d2) (non-negative floats order like their bits), which
 // is what OpenCV compares.  kInfKey is larger than any real key of either kind.
 constexpr int kInfKey = 0x7F000000;
+constexpr int kIdxBits = 22;   // Hamming packed key: distance << 22 | segment-local train index (segments < 4 Mi rows)
 
 template <class M, int K>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams p) {
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid < 2 * TM) {
-    const int r = tid >> 1, half = tid & 1;
+    const int r = (tid & 7) | ((tid >> 4) << 3), half = (tid >> 3) & 1;   // quarter-warp = 8 rows of one half: conflict-free STS.128
     const int q = qb * TM + r;
     uint8_t* dst = sA + row_offset<KB>(r);
     int nrm = 0;
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
     } else {
       for (int c = 0; c < KB / 32; c++) *reinterpret_cast<uint4*>(dst + (half * (KB / 32) + c) * 128) = make_uint4(0, 0, 0, 0);
     }
-    nrm += __shfl_xor_sync(0xffffffffu, nrm, 1);
+    nrm += __shfl_xor_sync(0xffffffffu, nrm, 8);
     if (half == 0) sQNorm[r] = nrm;
   }
   fence_proxy_async();
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
     // Two threads per train row; the packed rows of the next kPrefetch tiles are held in registers so that the HBM
     // latency (~1 us) of a tile overlaps the expansion of the previous ones.
     const int pt = tid - PROD_WARP0 * 32;   // 0..255
-    const int prow = pt >> 1, half = pt & 1;
+    const int prow = (pt & 7) | ((pt >> 4) << 3), half = (pt >> 3) & 1;
     struct TileIt {
       int seg, r0, s_begin, len, seg1;
       const int32_t* sp;
@@ -299,8 +302,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
         } else {
           for (int c = 0; c < KB / 32; c++) *reinterpret_cast<uint4*>(dst + (half * (KB / 32) + c) * 128) = make_uint4(0, 0, 0, 0);
         }
-        part += __shfl_xor_sync(0xffffffffu, part, 1);   // the two halves of a row sit in adjacent lanes
-        const int nrm = rv ? part : kInf;                // tail rows can never enter a list
+        part += __shfl_xor_sync(0xffffffffu, part, 8);   // the two halves of a row sit 8 lanes apart
+        // Hamming: packed column term (popc(row) << 22 | segment-local index), L2: |row|^2; tail rows never enter a list
+        const int nrm = M::kIsL2 ? (rv ? part : kInf) : (rv ? ((part << kIdxBits) | (it.r0 + prow)) : INT_MAX);
         if (half == 0) sNorm[(n % NORM_RING) * TN + prow] = nrm;
         fence_proxy_async();
         mbar_arrive(&full[s]);
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
     for (int seg = seg0; seg < seg1; seg++, segc++) {
       const int len = p.seg_ptr[seg + 1] - p.seg_ptr[seg];
 #pragma unroll
-      for (int c = 0; c < K; c++) { wk[c] = kInfKey; wi[c] = -1; wd2[c] = kInf; }
+      for (int c = 0; c < K; c++) { wk[c] = M::kIsL2 ? kInfKey : INT_MAX; wi[c] = -1; wd2[c] = kInf; }
       for (int r0 = 0; r0 < len; r0 += TN, n++) {
         const int s = n % STAGES;
         cvb_mbar_wait(&tfull[s], (n / STAGES) & 1);
@@ -365,17 +369,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
 #pragma unroll
             for (int j = 0; j < 4; j++) {
               const int i = 4 * i4 + j;
-              const int d = qn + nv[j] - 2 * (int)acc[i];
-              if (d < wd2[K - 1]) {
-                const int key = M::kIsL2 ? __float_as_int(__fsqrt_rn((float)d)) : d;
-                if (key < wk[K - 1]) {
-                  insert_key<K>(wk, wi, key, r0 + grp * 32 + i);
-                  // raw distance of the current worst entry, for the integer pre-test
-                  if (M::kIsL2) {
-                    const float f = __int_as_float(wk[K - 1]);
+              if (!M::kIsL2) {
+                // packed key in the "t domain" (without the per-query constant): numeric order == (distance, index)
+                // order, so the k smallest keys ARE OpenCV's k-NN list.  Branch-free min/max insertion network.
+                int x = (int)((unsigned)nv[j] - acc[i] * 512u);   // (popc(t) - 2 popc(q & t)) << 22 | idx (wraps mod 2^32)
+#pragma unroll
+                for (int c = 0; c < K; c++) {
+                  const int lo = min(wk[c], x);
+                  x = max(wk[c], x);
+                  wk[c] = lo;
+                }
+              } else {
+                const int d = qn + nv[j] - 2 * (int)acc[i];
+                if (d < wd2[K - 1]) {
+                  const int key = __float_as_int(__fsqrt_rn((float)d));
+                  if (key < wk[K - 1]) {
+                    insert_key<K>(wk, wi, key, r0 + grp * 32 + i);
+                    const float f = __int_as_float(wk[K - 1]);   // raw-distance bound of the worst entry (pre-test)
                     wd2[K - 1] = wk[K - 1] == kInfKey ? kInf : (int)ceilf(f * f * 1.000001f) + 1;
-                  } else {
-                    wd2[K - 1] = wk[K - 1] == kInfKey ? kInf : wk[K - 1];
                   }
                 }
               }
@@ -387,26 +398,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
       }
       // ---- segment finished: combine the 4 column-group lists of each query (k smallest by (key, idx)) ----
       int* lst = sList + (size_t)(segc & 1) * TM * GROUPS * K * 2;
+      if (!M::kIsL2) {
+        const int qq = qn << kIdxBits;
 #pragma unroll
-      for (int c = 0; c < K; c++) {
-        lst[((row * GROUPS + grp) * K + c) * 2 + 0] = wk[c];
-        lst[((row * GROUPS + grp) * K + c) * 2 + 1] = wi[c];
+        for (int c = 0; c < K; c++) lst[(row * GROUPS + grp) * K + c] = wk[c] == INT_MAX ? INT_MAX : wk[c] + qq;
+      } else {
+#pragma unroll
+        for (int c = 0; c < K; c++) {
+          lst[((row * GROUPS + grp) * K + c) * 2 + 0] = wk[c];
+          lst[((row * GROUPS + grp) * K + c) * 2 + 1] = wi[c];
+        }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
       if (grp == 0) {
+        float fd[K];   // final distances as float (DMatch::distance)
+        if (!M::kIsL2) {
 #pragma unroll
-        for (int c = 0; c < K; c++) { wk[c] = kInfKey; wi[c] = -1; }
-        for (int g2 = 0; g2 < GROUPS; g2++)
+          for (int c = 0; c < K; c++) wk[c] = INT_MAX;
+          for (int e = 0; e < GROUPS * K; e++) {
+            int x = lst[row * GROUPS * K + e];
+#pragma unroll
+            for (int c = 0; c < K; c++) {
+              const int lo = min(wk[c], x);
+              x = max(wk[c], x);
+              wk[c] = lo;
+            }
+          }
 #pragma unroll
           for (int c = 0; c < K; c++) {
-            const int kk = lst[((row * GROUPS + g2) * K + c) * 2], ii = lst[((row * GROUPS + g2) * K + c) * 2 + 1];
-            if (ii >= 0) insert_lex<K>(wk, wi, kk, ii);
+            wi[c] = wk[c] == INT_MAX ? -1 : (wk[c] & ((1 << kIdxBits) - 1));
+            wk[c] = wk[c] == INT_MAX ? INT_MAX : (wk[c] >> kIdxBits);
+            fd[c] = (float)wk[c];
           }
+        } else {
+#pragma unroll
+          for (int c = 0; c < K; c++) { wk[c] = kInfKey; wi[c] = -1; }
+          for (int g2 = 0; g2 < GROUPS; g2++)
+#pragma unroll
+            for (int c = 0; c < K; c++) {
+              const int kk = lst[((row * GROUPS + g2) * K + c) * 2], ii = lst[((row * GROUPS + g2) * K + c) * 2 + 1];
+              if (ii >= 0) insert_lex<K>(wk, wi, kk, ii);
+            }
+#pragma unroll
+          for (int c = 0; c < K; c++) fd[c] = __int_as_float(wk[c]);
+        }
         if (p.filter) {
           bool ok = false;
           if (K >= 2 && valid) {
-            const float dm = M::kIsL2 ? __int_as_float(wk[0]) : (float)wk[0];
-            const float dn = M::kIsL2 ? __int_as_float(wk[K >= 2 ? 1 : 0]) : (float)wk[K >= 2 ? 1 : 0];
+            const float dm = fd[0], dn = fd[K >= 2 ? 1 : 0];
             ok = wi[0] >= 0 && wi[K >= 2 ? 1 : 0] >= 0 && dm <= p.thr && dm < __fmul_rn(p.ratio, dn);
             const size_t o = (size_t)seg * p.nq + q;
             p.match_train[o] = ok ? wi[0] : -1;
@@ -419,7 +458,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
 #pragma unroll
           for (int c = 0; c < K; c++) {
             p.out_idx[o + c] = wi[c];
-            if (M::kIsL2) reinterpret_cast<float*>(p.out_dist)[o + c] = wi[c] >= 0 ? __int_as_float(wk[c]) : FLT_MAX;
+            if (M::kIsL2) reinterpret_cast<float*>(p.out_dist)[o + c] = wi[c] >= 0 ? fd[c] : FLT_MAX;
             else reinterpret_cast<int32_t*>(p.out_dist)[o + c] = wi[c] >= 0 ? wk[c] : INT_MAX;
           }
         }
@@ -448,7 +487,8 @@ int launch_tc(cvb_ctx* ctx, const TcParams& p, cudaStream_t st) {
   return CVB_OK;
 }
 
-bool profitable(const cvb_ctx* ctx, int nq, int n_seg, long total_rows) {
+bool profitable(const cvb_ctx* ctx, int nq, int n_seg, long total_rows, int max_seg_len) {
+  if (max_seg_len >= (1 << kIdxBits)) return false;   // packed (distance, index) keys need < 4 Mi rows per segment
   const char* e = getenv("COVINS_B200_MATCH_KERNEL");
   if (e && !strcmp(e, "popc")) return false;
   if (e && !strcmp(e, "tc")) return n_seg >= 1 && nq >= 1;

@@ -28,6 +28,6 @@ struct TcParams {
 int launch(cvb_ctx* ctx, TcParams p, int metric, int k, cudaStream_t st);
 
 // true when the tensor-core kernel fills the GPU for this shape (enough candidate segments per query block)
-bool profitable(const cvb_ctx* ctx, int nq, int n_seg, long total_rows);
+bool profitable(const cvb_ctx* ctx, int nq, int n_seg, long total_rows, int max_seg_len);
 
 }  // namespace cvb_tc
