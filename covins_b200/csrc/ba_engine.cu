@@ -125,6 +125,8 @@ struct Engine {
   // phase timing (CUDA events on the engine stream): 0 linearise, 1 block build + Schur, 2 Cholesky factor,
   // 3 triangular solves + back-substitution, 4 dogleg / J*step / plus / candidate cost
   cudaEvent_t ev[8] = {};
+  cudaGraphExec_t g_factor = nullptr, g_solve = nullptr;   // the ~700 / ~480 launches of one factorisation / solve, captured once
+  int n_factor_calls = 0, n_solve_calls = 0;
   double phase_ms[5] = {0, 0, 0, 0, 0};
   double chol_flops = 0.0;
   ~Engine() {
@@ -142,6 +144,8 @@ struct Engine {
     scalars.free_();
     if (h_scalars) cudaFreeHost(h_scalars);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (g_factor) cudaGraphExecDestroy(g_factor);
+    if (g_solve) cudaGraphExecDestroy(g_solve);
   }
 };
 
@@ -1386,8 +1390,25 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
   cam_finish_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, ld, E.S.p, E.diag.p, E.gvec.p, E.yb.p, E.gs.p, mu);
   ENG_LAUNCH();
   tick(E, 1);
-  rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st);
-  if (rc) return rc;
+  // first call: plain launches (sets kernel attributes); second call: stream-capture into a graph; then replay
+  if (E.g_factor) {
+    ENG_CUDA(cudaGraphLaunch(E.g_factor, E.st));
+    E.ctx->launches += 1 + (int64_t)E.plan.nt * 3;
+  } else if (E.n_factor_calls == 1) {
+    cudaGraph_t g = nullptr;
+    ENG_CUDA(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
+    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st);
+    cudaError_t ce = cudaStreamEndCapture(E.st, &g);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return cvb_fail(E.ctx, CVB_ERR_CUDA, "graph capture of the factorisation failed: %s", cudaGetErrorString(ce));
+    ENG_CUDA(cudaGraphInstantiate(&E.g_factor, g, 0));
+    cudaGraphDestroy(g);
+    ENG_CUDA(cudaGraphLaunch(E.g_factor, E.st));
+  } else {
+    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st);
+    if (rc) return rc;
+  }
+  E.n_factor_calls++;
   tick(E, 2);
   int flag = 0;
   ENG_CUDA(cudaMemcpyAsync(&flag, E.flag.p, sizeof(int), cudaMemcpyDeviceToHost, E.st));
@@ -1480,7 +1501,23 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
       continue;
     }
     tick(E, 3);
-    if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st))) return rc;
+    if (E.g_solve) {
+      ENG_CUDA(cudaGraphLaunch(E.g_solve, E.st));
+      E.ctx->launches += (int64_t)E.plan.nt * 2;
+    } else if (E.n_solve_calls == 1) {
+      cudaGraph_t g = nullptr;
+      ENG_CUDA(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
+      rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st);
+      cudaError_t ce = cudaStreamEndCapture(E.st, &g);
+      if (rc) return rc;
+      if (ce != cudaSuccess) return cvb_fail(E.ctx, CVB_ERR_CUDA, "graph capture of the solve failed: %s", cudaGetErrorString(ce));
+      ENG_CUDA(cudaGraphInstantiate(&E.g_solve, g, 0));
+      cudaGraphDestroy(g);
+      ENG_CUDA(cudaGraphLaunch(E.g_solve, E.st));
+    } else {
+      if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st))) return rc;
+    }
+    E.n_solve_calls++;
     if (E.L_in > 0) {
       backsub_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.lm_ptr.p, E.obs_kf.p, E.wy.p, E.HllInv.p, E.bl.p, E.xsol.p, E.off_pose.p,
                                                       E.xsol.p + E.n_c_pad);

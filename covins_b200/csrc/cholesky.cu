@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
   extern __shared__ __align__(16) double smem_d[];
   double* a = smem_d;              // [T][LDP]
   double* tmp = smem_d + T * LDP;  // 64 x 64 scratch
+  __shared__ double rdiag[T];      // reciprocals of the diagonal of L
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* At = S + (size_t)k * T * ld + (size_t)k * T;
   for (int u = tid; u < T * T; u += POTRF_THREADS) {
@@ -183,8 +184,9 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
           if (lane == 0) atomicOr(flag, 1);
           piv = 1.0;
         }
-        piv = sqrt(piv);
-        if (lane >= j && lane < PB) a[(c0 + lane) * LDP + c0 + j] = (lane == j) ? piv : s / piv;
+        const double rinv = rsqrt(piv);   // one special-function sequence instead of sqrt + divide on the critical path
+        if (lane >= j && lane < PB) a[(c0 + lane) * LDP + c0 + j] = (lane == j) ? piv * rinv : s * rinv;
+        if (lane == j) rdiag[c0 + j] = rinv;
         __syncwarp();
       }
     }
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
 #pragma unroll
         for (int m = 0; m < PB; m++)
           if (m < j) s -= x[m] * a[(c0 + j) * LDP + c0 + m];
-        x[j] = s / a[(c0 + j) * LDP + c0 + j];
+        x[j] = s * rdiag[c0 + j];
       }
 #pragma unroll
       for (int j = 0; j < PB; j++) a[r * LDP + c0 + j] = x[j];
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
 #pragma unroll
       for (int m = 0; m < PB; m++)
         if (m >= j && m < i) s -= Lb[i * PB + m] * x[m];
-      x[i] = (i >= j) ? s / Lb[i * PB + i] : 0.0;
+      x[i] = (i >= j) ? s * rdiag[blk * PB + i] : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < PB; i++) a[(blk * PB + i) * LDP + blk * PB + j] = x[i];
