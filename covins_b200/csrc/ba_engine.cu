@@ -125,6 +125,8 @@ struct Engine {
   // phase timing (CUDA events on the engine stream): 0 linearise, 1 block build + Schur, 2 Cholesky factor,
   // 3 triangular solves + back-substitution, 4 dogleg / J*step / plus / candidate cost
   cudaEvent_t ev[8] = {};
+  cudaStream_t st2 = nullptr;            // lookahead stream of the factorisation
+  std::vector<cudaEvent_t> la_ev;
   cudaGraphExec_t g_factor = nullptr, g_solve = nullptr;   // the ~700 / ~480 launches of one factorisation / solve, captured once
   int n_factor_calls = 0, n_solve_calls = 0;
   double phase_ms[5] = {0, 0, 0, 0, 0};
@@ -144,6 +146,8 @@ struct Engine {
     scalars.free_();
     if (h_scalars) cudaFreeHost(h_scalars);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : la_ev) if (e) cudaEventDestroy(e);
+    if (st2) cudaStreamDestroy(st2);
     if (g_factor) cudaGraphExecDestroy(g_factor);
     if (g_solve) cudaGraphExecDestroy(g_solve);
   }
@@ -1285,6 +1289,9 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   if ((rc = zalloc(E, E.partials, (size_t)RED_SLOTS * RED_BLOCKS)) || (rc = zalloc(E, E.scalars, RED_SLOTS))) return rc;
   ENG_CUDA(cudaMallocHost(&E.h_scalars, RED_SLOTS * sizeof(double)));
   for (auto& e : E.ev) ENG_CUDA(cudaEventCreate(&e));
+  ENG_CUDA(cudaStreamCreateWithFlags(&E.st2, cudaStreamNonBlocking));
+  E.la_ev.assign((size_t)2 * E.plan.nt, nullptr);
+  for (auto& e : E.la_ev) ENG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   ENG_CUDA(cudaStreamSynchronize(E.st));
   return CVB_OK;
 }
@@ -1397,7 +1404,7 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
   } else if (E.n_factor_calls == 1) {
     cudaGraph_t g = nullptr;
     ENG_CUDA(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
-    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st);
+    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st, E.st2, E.la_ev.data());
     cudaError_t ce = cudaStreamEndCapture(E.st, &g);
     if (rc) return rc;
     if (ce != cudaSuccess) return cvb_fail(E.ctx, CVB_ERR_CUDA, "graph capture of the factorisation failed: %s", cudaGetErrorString(ce));
@@ -1405,7 +1412,7 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
     cudaGraphDestroy(g);
     ENG_CUDA(cudaGraphLaunch(E.g_factor, E.st));
   } else {
-    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st);
+    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st, E.st2, E.la_ev.data());
     if (rc) return rc;
   }
   E.n_factor_calls++;

@@ -172,35 +172,47 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
       }
       __syncthreads();
     }
-    if (warp == 0) {  // (2) unblocked Cholesky of the 16x16 diagonal block
+    if (warp == 0) {
+      // (2) 16x16 diagonal block, register resident: lane i (< 16) owns row i; right-looking rank-1 updates with the
+      // column broadcast by shuffles — no shared-memory round trip on the critical path.
+      const int i = lane & 15;
+      double row[PB];
+#pragma unroll
+      for (int c = 0; c < PB; c++) row[c] = a[(c0 + i) * LDP + c0 + c];
+#pragma unroll
       for (int j = 0; j < PB; j++) {
-        double s = 0.0;
-        if (lane >= j && lane < PB) {
-          s = a[(c0 + lane) * LDP + c0 + j];
-          for (int m = 0; m < j; m++) s -= a[(c0 + lane) * LDP + c0 + m] * a[(c0 + j) * LDP + c0 + m];
-        }
-        double piv = __shfl_sync(0xffffffffu, s, j);
+        double piv = __shfl_sync(0xffffffffu, row[j], j);
         if (!(piv > 0.0)) {
           if (lane == 0) atomicOr(flag, 1);
           piv = 1.0;
         }
-        const double rinv = rsqrt(piv);   // one special-function sequence instead of sqrt + divide on the critical path
-        if (lane >= j && lane < PB) a[(c0 + lane) * LDP + c0 + j] = (lane == j) ? piv * rinv : s * rinv;
+        const double rinv = rsqrt(piv);
+        const double lij = (i >= j) ? row[j] * rinv : 0.0;   // column j of L (rows >= j)
+        row[j] = lij;
+#pragma unroll
+        for (int c = j + 1; c < PB; c++) {
+          const double lcj = __shfl_sync(0xffffffffu, lij, c);
+          if (i >= c) row[c] -= lij * lcj;
+        }
         if (lane == j) rdiag[c0 + j] = rinv;
-        __syncwarp();
+      }
+      if (lane < PB) {
+#pragma unroll
+        for (int c = 0; c < PB; c++) a[(c0 + i) * LDP + c0 + c] = (c <= i) ? row[c] : 0.0;
       }
     }
     __syncthreads();
-    // (3) rows below the block: x = a_row * Ljj^-T (forward substitution along the 16 columns), one thread per row
+    // (3) rows below the block: x = a_row * Ljj^-T (forward substitution along the 16 columns), one thread per row;
+    // multiplications by the stored reciprocal diagonal instead of divisions
     for (int r = c0 + PB + tid; r < T; r += POTRF_THREADS) {
       double x[PB];
 #pragma unroll
       for (int j = 0; j < PB; j++) {
-        double s = a[r * LDP + c0 + j];
+        double s2 = a[r * LDP + c0 + j];
 #pragma unroll
         for (int m = 0; m < PB; m++)
-          if (m < j) s -= x[m] * a[(c0 + j) * LDP + c0 + m];
-        x[j] = s * rdiag[c0 + j];
+          if (m < j) s2 -= x[m] * a[(c0 + j) * LDP + c0 + m];
+        x[j] = s2 * rdiag[c0 + j];
       }
 #pragma unroll
       for (int j = 0; j < PB; j++) a[r * LDP + c0 + j] = x[j];
@@ -342,18 +354,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS) bwd_kernel(const double* __rest
 // bools, diagonal forced).  Right-looking elimination: the non-zero rows of column k become a clique.
 void TilePlan::build(int nt_, std::vector<uint8_t> mask) {
   nt = nt_;
-  h_col_ptr.assign(1, 0); h_row_idx.clear(); h_pair_ptr.assign(1, 0); h_pair_i.clear(); h_pair_j.clear();
+  h_col_ptr.assign(1, 0); h_row_idx.clear(); h_pair_ptr.assign(1, 0); h_pair_i.clear(); h_pair_j.clear(); h_pair_split.clear();
   for (int k = 0; k < nt; k++) mask[(size_t)k * nt + k] = 1;
   for (int k = 0; k < nt; k++) {
     std::vector<int> rows;
     for (int i = k + 1; i < nt; i++)
       if (mask[(size_t)i * nt + k]) rows.push_back(i);
-    for (size_t a = 0; a < rows.size(); a++)
-      for (size_t b = 0; b <= a; b++) {
-        mask[(size_t)rows[a] * nt + rows[b]] = 1;
-        h_pair_i.push_back(rows[a]);
-        h_pair_j.push_back(rows[b]);
-      }
+    // pairs whose column tile is k+1 first ("panel" part: all the next step's potrf/trsm depend on), then the rest
+    int n_a = 0;
+    for (int pass = 0; pass < 2; pass++)
+      for (size_t a = 0; a < rows.size(); a++)
+        for (size_t b = 0; b <= a; b++) {
+          const bool is_a = rows[b] == k + 1;
+          if ((pass == 0) != is_a) continue;
+          mask[(size_t)rows[a] * nt + rows[b]] = 1;
+          h_pair_i.push_back(rows[a]);
+          h_pair_j.push_back(rows[b]);
+          if (is_a) n_a++;
+        }
+    h_pair_split.push_back(n_a);
     h_row_idx.insert(h_row_idx.end(), rows.begin(), rows.end());
     h_col_ptr.push_back((int)h_row_idx.size());
     h_pair_ptr.push_back((int)h_pair_i.size());
@@ -393,7 +412,8 @@ void TilePlan::release() {
   d_row_idx = d_pair_i = d_pair_j = d_rowc_idx = nullptr;
 }
 
-int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st) {
+int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
+           cudaStream_t st2, cudaEvent_t* ev) {
   static bool attr = false;
   if (!attr) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
@@ -404,6 +424,11 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
   const int nt = n_pad / T;
   CVB_REQUIRE(ctx, plan.nt == nt, "tile plan does not match the matrix");
   CVB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  // Lookahead (depth 1) when a second stream is given: the diagonal-tile kernel and the panel solve of step k+1 only
+  // need the "panel" part of step k's trailing update (pairs in tile column k+1); the bulk of the update runs on the
+  // second stream concurrently.  ev[2k] = panel solve of step k done, ev[2k+1] = bulk update of step k done.
+  const bool la = st2 != nullptr && ev != nullptr;
+  int last_bulk = -1;
   for (int k = 0; k < nt; k++) {
     potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag);
     CVB_CHECK_LAUNCH(ctx);
@@ -412,12 +437,26 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
       trsm_kernel<<<m, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T,
                                                       plan.d_row_idx + plan.h_col_ptr[k]);
       CVB_CHECK_LAUNCH(ctx);
-      const int np = plan.h_pair_ptr[k + 1] - plan.h_pair_ptr[k];
-      syrk_kernel<<<np, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, plan.d_pair_i + plan.h_pair_ptr[k],
-                                                       plan.d_pair_j + plan.h_pair_ptr[k]);
-      CVB_CHECK_LAUNCH(ctx);
+      const int p0 = plan.h_pair_ptr[k], np = plan.h_pair_ptr[k + 1] - p0, na = la ? plan.h_pair_split[k] : np;
+      if (la) {
+        CVB_CUDA(ctx, cudaEventRecord(ev[2 * k], st));
+        if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[2 * last_bulk + 1], 0));
+      }
+      if (na > 0) {
+        syrk_kernel<<<na, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
+        CVB_CHECK_LAUNCH(ctx);
+      }
+      if (la && np - na > 0) {
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st2, ev[2 * k], 0));
+        syrk_kernel<<<np - na, GEMM_THREADS, kGemmSmem, st2>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0 + na,
+                                                               plan.d_pair_j + p0 + na);
+        CVB_CHECK_LAUNCH(ctx);
+        CVB_CUDA(ctx, cudaEventRecord(ev[2 * k + 1], st2));
+        last_bulk = k;
+      }
     }
   }
+  if (la && last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[2 * last_bulk + 1], 0));   // join
   return CVB_OK;
 }
 
@@ -473,7 +512,7 @@ extern "C" int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, co
   int rc = plan.upload(ctx, st);
   if (rc) return rc;
   cudaEventRecord(e0, st);
-  rc = factor(ctx, dS, np, dl, dflag, plan, st);
+  rc = factor(ctx, dS, np, dl, dflag, plan, st, nullptr, nullptr);
   cudaEventRecord(e1, st);
   if (rc) return rc;
   rc = solve(ctx, dS, np, dl, dv, dv + np, dv + 2 * np, plan, st);

@@ -13,6 +13,7 @@ struct TilePlan {
   int nt = 0;
   std::vector<int> h_col_ptr, h_row_idx;           // per tile column k: non-zero row tiles i > k
   std::vector<int> h_pair_ptr, h_pair_i, h_pair_j; // per tile column k: (i >= j) pairs of those rows (trailing updates)
+  std::vector<int> h_pair_split;                   // per tile column k: how many of its pairs (listed first) lie in tile column k+1
   std::vector<int> h_rowc_ptr, h_rowc_idx;         // per tile row k: non-zero column tiles i < k (backward solve)
   int *d_row_idx = nullptr, *d_pair_i = nullptr, *d_pair_j = nullptr, *d_rowc_idx = nullptr;
   long n_tiles_L = 0;
@@ -22,7 +23,9 @@ struct TilePlan {
   void release();
 };
 
-int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st);
+// st2/ev (2*nt events, timing disabled) enable depth-1 lookahead on a second stream; pass nullptr for a single stream
+int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
+           cudaStream_t st2, cudaEvent_t* ev);
 int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
           const TilePlan& plan, cudaStream_t st);
 
