@@ -133,22 +133,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(double* __restric
 }
 
 // Factor the diagonal tile k in shared memory and invert the factor, one CTA of 512 threads.
-//   Cholesky: blocked left-looking, 16-wide block columns: (1) panel update with all threads, (2) 16x16 diagonal block
-//   by one warp, (3) panel triangular solve one thread per row → 3 barriers per block column instead of 2 per column.
-//   Inverse: in place by recursive doubling (16 → 32 → 64 → 128): X21 = -C^-1 (B A^-1) with a 32 KB scratch tile.
+//   Cholesky: blocked right-looking, 16-wide block columns.  Per block column: (a) the 16x16 diagonal block is factored
+//   register-resident by one warp (rank-1 updates broadcast with shuffles) and inverted; (b) the panel below it is
+//   multiplied by that inverse (no division chains); (c) the trailing sub-matrix gets its rank-16 update with 4x4
+//   register tiles (0.5 shared-memory loads per multiply-add — the naive form is LDS-bandwidth bound).
+//   Inverse: in place by recursive doubling (16 → 32 → 64 → 128): X21 = -C^-1 (B A^-1), 4x4 register tiles, a 32 KB
+//   scratch tile; the 16x16 diagonal inverses come from the factorisation.
 // L is written back to S, the inverse (row-major 128x128, zeros above the diagonal) to linv_k.  flag[0] |= 1 on a
 // non-positive pivot (matrix not positive definite → the caller raises mu, as Ceres does on LINEAR_SOLVER_FAILURE).
 constexpr int LDP = T + 1;
 constexpr int PB = 16;
 constexpr int POTRF_THREADS = 512;
-constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)64 * 64) * sizeof(double);
+constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)64 * 64 + (size_t)(T / PB) * PB * PB) * sizeof(double);
+
+// C[4][4] (+)= sum_m P[i][m] * Q[j][m], rows of P/Q at stride ldp/ldq, m in [m0, m1)
+__device__ __forceinline__ void tile4x4(const double* __restrict__ P, int ldp, const double* __restrict__ Q, int ldq, int m0,
+                                        int m1, double (&c)[4][4]) {
+  for (int m = m0; m < m1; m++) {
+    double pv[4], qv[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { pv[i] = P[i * ldp + m]; qv[i] = Q[i * ldq + m]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) c[i][j] += pv[i] * qv[j];
+  }
+}
 
 __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __restrict__ S, size_t ld, int k,
                                                                      double* __restrict__ linv_k, int* __restrict__ flag) {
   extern __shared__ __align__(16) double smem_d[];
-  double* a = smem_d;              // [T][LDP]
-  double* tmp = smem_d + T * LDP;  // 64 x 64 scratch
-  __shared__ double rdiag[T];      // reciprocals of the diagonal of L
+  double* a = smem_d;                     // [T][LDP]
+  double* tmp = smem_d + T * LDP;         // 64 x 64 scratch
+  double* binv = tmp + 64 * 64;           // [8][16][16] inverses of the diagonal 16x16 blocks of L
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* At = S + (size_t)k * T * ld + (size_t)k * T;
   for (int u = tid; u < T * T; u += POTRF_THREADS) {
@@ -158,27 +175,14 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
   __syncthreads();
   // ---------------- Cholesky ----------------
   for (int jb = 0; jb < T / PB; jb++) {
-    const int c0 = jb * PB, nrows = T - c0;
-    if (jb > 0) {  // (1) A[c0.., c0..c0+15] -= L[c0.., 0..c0) L[c0..c0+15, 0..c0)^T
-      for (int u = tid; u < nrows * PB; u += POTRF_THREADS) {
-        const int r = c0 + (u % nrows), c = c0 + (u / nrows);
-        if (c > r) continue;
-        double s = 0.0;
-        const double* ar = a + r * LDP;
-        const double* ac = a + c * LDP;
-#pragma unroll 8
-        for (int m = 0; m < c0; m++) s += ar[m] * ac[m];
-        a[r * LDP + c] -= s;
-      }
-      __syncthreads();
-    }
+    const int c0 = jb * PB, nbelow = T - c0 - PB;
     if (warp == 0) {
-      // (2) 16x16 diagonal block, register resident: lane i (< 16) owns row i; right-looking rank-1 updates with the
-      // column broadcast by shuffles — no shared-memory round trip on the critical path.
+      // (a) 16x16 diagonal block: lane i (< 16; lanes 16-31 mirror) owns row i
       const int i = lane & 15;
       double row[PB];
 #pragma unroll
       for (int c = 0; c < PB; c++) row[c] = a[(c0 + i) * LDP + c0 + c];
+      double rd[PB];   // reciprocal diagonal (identical on all lanes)
 #pragma unroll
       for (int j = 0; j < PB; j++) {
         double piv = __shfl_sync(0xffffffffu, row[j], j);
@@ -187,85 +191,137 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
           piv = 1.0;
         }
         const double rinv = rsqrt(piv);
-        const double lij = (i >= j) ? row[j] * rinv : 0.0;   // column j of L (rows >= j)
+        rd[j] = rinv;
+        const double lij = (i >= j) ? row[j] * rinv : 0.0;   // column j of L
         row[j] = lij;
 #pragma unroll
         for (int c = j + 1; c < PB; c++) {
           const double lcj = __shfl_sync(0xffffffffu, lij, c);
           if (i >= c) row[c] -= lij * lcj;
         }
-        if (lane == j) rdiag[c0 + j] = rinv;
       }
       if (lane < PB) {
 #pragma unroll
         for (int c = 0; c < PB; c++) a[(c0 + i) * LDP + c0 + c] = (c <= i) ? row[c] : 0.0;
       }
+      __syncwarp();
+      // inverse of the block: lane j (< 16) builds column j by forward substitution (L read back from shared memory)
+      if (lane < PB) {
+        const int j = lane;
+        double x[PB];
+#pragma unroll
+        for (int r = 0; r < PB; r++) {
+          double sacc = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+          for (int m = 0; m < PB; m++)
+            if (m < r) sacc -= a[(c0 + r) * LDP + c0 + m] * ((m >= j) ? x[m] : 0.0);
+          x[r] = (r >= j) ? sacc * rd[r] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < PB; r++) binv[(jb * PB + r) * PB + j] = x[r];   // Linv_block[r][j]
+      }
     }
     __syncthreads();
-    // (3) rows below the block: x = a_row * Ljj^-T (forward substitution along the 16 columns), one thread per row;
-    // multiplications by the stored reciprocal diagonal instead of divisions
-    for (int r = c0 + PB + tid; r < T; r += POTRF_THREADS) {
-      double x[PB];
-#pragma unroll
-      for (int j = 0; j < PB; j++) {
-        double s2 = a[r * LDP + c0 + j];
+    if (nbelow > 0) {
+      // (b) panel: X[r][j] = sum_{m <= j} A[r][c0+m] * Linv_block[j][m]   (X Ljj^T = A)
+      for (int u = tid; u < nbelow * PB; u += POTRF_THREADS) {
+        const int r = c0 + PB + u / PB, j = u % PB;
+        const double* ar = a + r * LDP + c0;
+        const double* bj = binv + (jb * PB + j) * PB;
+        double sacc = 0.0;
 #pragma unroll
         for (int m = 0; m < PB; m++)
-          if (m < j) s2 -= x[m] * a[(c0 + j) * LDP + c0 + m];
-        x[j] = s2 * rdiag[c0 + j];
+          if (m <= j) sacc += ar[m] * bj[m];
+        tmp[u] = sacc;
       }
+      __syncthreads();
+      for (int u = tid; u < nbelow * PB; u += POTRF_THREADS) a[(c0 + PB + u / PB) * LDP + c0 + (u % PB)] = tmp[u];
+      __syncthreads();
+      // (c) trailing update A[r][c] -= sum_{m<16} L[r][c0+m] L[c][c0+m] for r >= c >= c0+16, 4x4 register tiles
+      const int nt4 = nbelow / 4, ntiles = nt4 * (nt4 + 1) / 2;
+      for (int u = tid; u < ntiles; u += POTRF_THREADS) {
+        int tr = (int)((sqrtf(8.0f * (float)u + 1.0f) - 1.0f) * 0.5f);
+        while ((tr + 1) * (tr + 2) / 2 <= u) tr++;
+        while (tr * (tr + 1) / 2 > u) tr--;
+        const int tc = u - tr * (tr + 1) / 2;
+        const int r0 = c0 + PB + 4 * tr, cc0 = c0 + PB + 4 * tc;
+        double c4[4][4];
 #pragma unroll
-      for (int j = 0; j < PB; j++) a[r * LDP + c0 + j] = x[j];
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) c4[i][j] = 0.0;
+        tile4x4(a + r0 * LDP + c0, LDP, a + cc0 * LDP + c0, LDP, 0, PB, c4);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (cc0 + j <= r0 + i) a[(r0 + i) * LDP + cc0 + j] -= c4[i][j];
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   for (int u = tid; u < T * T; u += POTRF_THREADS) {
     const int r = u / T, c = u % T;
     if (c <= r) At[(size_t)r * ld + c] = a[r * LDP + c];
   }
+  __syncthreads();
   // ---------------- inverse of L, in place ----------------
-  // level 0: the eight 16x16 diagonal blocks, via a copy in tmp (thread (blk, c) → column c of the block inverse)
+  // level 0: the diagonal 16x16 blocks were inverted during the factorisation
   for (int u = tid; u < (T / PB) * PB * PB; u += POTRF_THREADS) {
     const int blk = u / (PB * PB), r = (u / PB) % PB, c = u % PB;
-    tmp[u] = a[(blk * PB + r) * LDP + blk * PB + c];
+    a[(blk * PB + r) * LDP + blk * PB + c] = binv[u];
   }
   __syncthreads();
-  if (tid < (T / PB) * PB) {
-    const int blk = tid / PB, j = tid % PB;
-    const double* Lb = tmp + blk * PB * PB;
-    double x[PB];
-#pragma unroll
-    for (int i = 0; i < PB; i++) {
-      double s = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-      for (int m = 0; m < PB; m++)
-        if (m >= j && m < i) s -= Lb[i * PB + m] * x[m];
-      x[i] = (i >= j) ? s * rdiag[blk * PB + i] : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < PB; i++) a[(blk * PB + i) * LDP + blk * PB + j] = x[i];
-  }
-  __syncthreads();
-  // levels 1..3: block size h = 16, 32, 64: for each pair (A = inv at [p,p], C = inv at [p+h,p+h], B at [p+h,p]):
-  //   tmp = B * A  (A lower triangular),  B <- -C * tmp  (C lower triangular)
+  // levels h = 16, 32, 64: for each pair (A = inv at [p,p], C = inv at [p+h,p+h], B at [p+h,p]):
+  //   tmp = B * A  (A lower triangular),  B <- -C * tmp  (C lower triangular); 4x4 register tiles
   for (int h = PB; h < T; h *= 2) {
-    const int npairs = T / (2 * h);
-    for (int u = tid; u < npairs * h * h; u += POTRF_THREADS) {
-      const int pr = u / (h * h), r = (u / h) % h, c = u % h;
+    const int npairs = T / (2 * h), h4 = h / 4;
+    for (int u = tid; u < npairs * h4 * h4; u += POTRF_THREADS) {
+      const int pr = u / (h4 * h4), r0 = 4 * ((u / h4) % h4), cc0 = 4 * (u % h4);
       const int p0 = pr * 2 * h;
-      const double* B = a + (p0 + h + r) * LDP + p0;   // row r of B
-      double s = 0.0;
-      for (int m = c; m < h; m++) s += B[m] * a[(p0 + m) * LDP + p0 + c];   // A[m][c], m >= c
-      tmp[pr * h * h + r * h + c] = s;
+      double c4[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) c4[i][j] = 0.0;
+      // (B A)[r][c] = sum_m B[r][m] A[m][c], A[m][c] = 0 for m < c
+      for (int m = cc0; m < h; m++) {
+        double bv[4], av[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { bv[i] = a[(p0 + h + r0 + i) * LDP + p0 + m]; av[i] = a[(p0 + m) * LDP + p0 + cc0 + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) c4[i][j] += bv[i] * av[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) tmp[pr * h * h + (r0 + i) * h + cc0 + j] = c4[i][j];
     }
     __syncthreads();
-    for (int u = tid; u < npairs * h * h; u += POTRF_THREADS) {
-      const int pr = u / (h * h), r = (u / h) % h, c = u % h;
+    for (int u = tid; u < npairs * h4 * h4; u += POTRF_THREADS) {
+      const int pr = u / (h4 * h4), r0 = 4 * ((u / h4) % h4), cc0 = 4 * (u % h4);
       const int p0 = pr * 2 * h;
-      const double* Crow = a + (p0 + h + r) * LDP + p0 + h;   // row r of C (inverse, lower)
-      double s = 0.0;
-      for (int m = 0; m <= r; m++) s += Crow[m] * tmp[pr * h * h + m * h + c];
-      a[(p0 + h + r) * LDP + p0 + c] = -s;
+      double c4[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) c4[i][j] = 0.0;
+      // (C tmp)[r][c] = sum_{m <= r} C[r][m] tmp[m][c]
+      for (int m = 0; m < r0 + 4; m++) {
+        double cv[4], tv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { cv[i] = a[(p0 + h + r0 + i) * LDP + p0 + h + m]; tv[i] = tmp[pr * h * h + m * h + cc0 + i]; }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) c4[i][j] += cv[i] * tv[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[(p0 + h + r0 + i) * LDP + p0 + cc0 + j] = -c4[i][j];
     }
     __syncthreads();
   }
