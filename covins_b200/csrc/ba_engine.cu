@@ -125,7 +125,7 @@ struct Engine {
   // phase timing (CUDA events on the engine stream): 0 linearise, 1 block build + Schur, 2 Cholesky factor,
   // 3 triangular solves + back-substitution, 4 dogleg / J*step / plus / candidate cost
   cudaEvent_t ev[8] = {};
-  cudaStream_t st2 = nullptr;            // lookahead stream of the factorisation
+  cvb_chol::FactorStreams fs;            // lookahead / chain streams of the factorisation
   std::vector<cudaEvent_t> la_ev;
   cudaGraphExec_t g_factor = nullptr, g_solve = nullptr;   // the ~700 / ~480 launches of one factorisation / solve, captured once
   int n_factor_calls = 0, n_solve_calls = 0;
@@ -147,7 +147,9 @@ struct Engine {
     if (h_scalars) cudaFreeHost(h_scalars);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : la_ev) if (e) cudaEventDestroy(e);
-    if (st2) cudaStreamDestroy(st2);
+    if (fs.bulk) cudaStreamDestroy(fs.bulk);
+    for (int g = 0; g < fs.n_group; g++) { if (fs.group[g]) cudaStreamDestroy(fs.group[g]); if (fs.join[g]) cudaEventDestroy(fs.join[g]); }
+    if (fs.fork) cudaEventDestroy(fs.fork);
     if (g_factor) cudaGraphExecDestroy(g_factor);
     if (g_solve) cudaGraphExecDestroy(g_solve);
   }
@@ -1028,7 +1030,8 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   // starts on a tile boundary, so that the tile-level elimination of one chain never touches another chain's tiles
   // (a tile shared by two chains would carry the first chain's pose clique along the whole second chain).
   E.h_off_pose.resize(K); E.h_off_sb.assign(K, 0);
-  int n_sb_pad = 0;
+  int n_sb_pad = 0, n_total = 0;
+  std::vector<std::pair<int, int>> sb_ranges;   // [begin, end) column range of every chain (for the column groups)
   if (!E.visual_only) {
     std::vector<int> parent(K);
     std::iota(parent.begin(), parent.end(), 0);
@@ -1040,19 +1043,37 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     std::vector<int> comp_size(K, 0);
     for (int k = 0; k < K; k++) comp_size[find(k)]++;
     int cursor = 0;
+    std::vector<int> roots;
     for (int root = 0; root < K; root++) {          // chains with >= 2 keyframes, in order of their first keyframe
       if (find(root) != root || comp_size[root] < 2) continue;
+      roots.push_back(root);
       cursor = ((cursor + TT - 1) / TT) * TT;
+      const int begin = cursor;
       for (int k = root; k < K; k++)
         if (find(k) == root) { E.h_off_sb[k] = cursor; cursor += 9; }
+      sb_ranges.emplace_back(begin, cursor);
     }
     cursor = ((cursor + TT - 1) / TT) * TT;
     for (int k = 0; k < K; k++)                     // keyframes without an IMU factor: isolated speed-bias blocks
       if (comp_size[find(k)] < 2) { E.h_off_sb[k] = cursor; cursor += 9; }
     n_sb_pad = ((cursor + TT - 1) / TT) * TT;
+    // poses: chain by chain, each chain on its own tiles (so that the chains' eliminations touch disjoint tiles and
+    // can run concurrently), then the keyframes without IMU factors
+    cursor = n_sb_pad;
+    for (int root : roots) {
+      cursor = ((cursor + TT - 1) / TT) * TT;
+      for (int k = root; k < K; k++)
+        if (find(k) == root) { E.h_off_pose[k] = cursor; cursor += 6; }
+    }
+    cursor = ((cursor + TT - 1) / TT) * TT;
+    for (int k = 0; k < K; k++)
+      if (comp_size[find(k)] < 2) { E.h_off_pose[k] = cursor; cursor += 6; }
+    n_total = cursor;
+  } else {
+    for (int k = 0; k < K; k++) E.h_off_pose[k] = 6 * k;
+    n_total = 6 * K;
   }
-  for (int k = 0; k < K; k++) E.h_off_pose[k] = n_sb_pad + 6 * k;
-  E.n_c_pad = ((n_sb_pad + 6 * K + TT - 1) / TT) * TT;
+  E.n_c_pad = ((n_total + TT - 1) / TT) * TT;
   E.n_vec = E.n_c_pad + 3 * E.L_in;
   auto col_of = [&](int kf, int c) { return c < 6 ? E.h_off_pose[kf] + c : E.h_off_sb[kf] + (c - 6); };
   // ---- tile-level structure of S (every rank needs the structure of the WHOLE problem: S is all-reduced) ----
@@ -1093,6 +1114,9 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
       if (tmask[(size_t)i * nt + j] || i == j) { h_xt_i.push_back(i); h_xt_j.push_back(j); }
   E.n_xt = (int)h_xt_i.size();
   E.plan.build(nt, tmask);
+  E.plan.h_col_group.assign(nt, -1);
+  for (size_t g = 0; g < sb_ranges.size(); g++)
+    for (int t = sb_ranges[g].first / TT; t <= (sb_ranges[g].second - 1) / TT; t++) E.plan.h_col_group[t] = (int)g;
   // ---- by-keyframe CSR ----
   std::vector<int> h_kf_ptr(K + 1, 0), h_kf_obs(E.n_obs);
   for (int ob = 0; ob < E.n_obs; ob++) h_kf_ptr[h_obs_kf[ob] + 1]++;
@@ -1289,9 +1313,20 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   if ((rc = zalloc(E, E.partials, (size_t)RED_SLOTS * RED_BLOCKS)) || (rc = zalloc(E, E.scalars, RED_SLOTS))) return rc;
   ENG_CUDA(cudaMallocHost(&E.h_scalars, RED_SLOTS * sizeof(double)));
   for (auto& e : E.ev) ENG_CUDA(cudaEventCreate(&e));
-  ENG_CUDA(cudaStreamCreateWithFlags(&E.st2, cudaStreamNonBlocking));
-  E.la_ev.assign((size_t)2 * E.plan.nt, nullptr);
-  for (auto& e : E.la_ev) ENG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  {
+    int lo = 0, hi = 0;   // lo = numerically greatest = lowest priority
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    ENG_CUDA(cudaStreamCreateWithPriority(&E.fs.bulk, cudaStreamNonBlocking, lo));
+    E.la_ev.assign((size_t)2 * E.plan.nt, nullptr);
+    for (auto& e : E.la_ev) ENG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    E.fs.ev = E.la_ev.data();
+    E.fs.n_group = 8;
+    for (int g = 0; g < 8; g++) {
+      ENG_CUDA(cudaStreamCreateWithPriority(&E.fs.group[g], cudaStreamNonBlocking, hi));
+      ENG_CUDA(cudaEventCreateWithFlags(&E.fs.join[g], cudaEventDisableTiming));
+    }
+    ENG_CUDA(cudaEventCreateWithFlags(&E.fs.fork, cudaEventDisableTiming));
+  }
   ENG_CUDA(cudaStreamSynchronize(E.st));
   return CVB_OK;
 }
@@ -1404,7 +1439,7 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
   } else if (E.n_factor_calls == 1) {
     cudaGraph_t g = nullptr;
     ENG_CUDA(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
-    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st, E.st2, E.la_ev.data());
+    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st, &E.fs);
     cudaError_t ce = cudaStreamEndCapture(E.st, &g);
     if (rc) return rc;
     if (ce != cudaSuccess) return cvb_fail(E.ctx, CVB_ERR_CUDA, "graph capture of the factorisation failed: %s", cudaGetErrorString(ce));
@@ -1412,7 +1447,7 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
     cudaGraphDestroy(g);
     ENG_CUDA(cudaGraphLaunch(E.g_factor, E.st));
   } else {
-    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st, E.st2, E.la_ev.data());
+    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st, &E.fs);
     if (rc) return rc;
   }
   E.n_factor_calls++;

@@ -469,7 +469,7 @@ void TilePlan::release() {
 }
 
 int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
-           cudaStream_t st2, cudaEvent_t* ev) {
+           const FactorStreams* fs) {
   static bool attr = false;
   if (!attr) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
@@ -480,29 +480,58 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
   const int nt = n_pad / T;
   CVB_REQUIRE(ctx, plan.nt == nt, "tile plan does not match the matrix");
   CVB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  cudaStream_t st2 = fs ? fs->bulk : nullptr;
+  cudaEvent_t* ev = fs ? fs->ev : nullptr;
+  const int n_gs = (fs && !plan.h_col_group.empty()) ? fs->n_group : 0;
   // Lookahead (depth 1) when a second stream is given: the diagonal-tile kernel and the panel solve of step k+1 only
   // need the "panel" part of step k's trailing update (pairs in tile column k+1); the bulk of the update runs on the
-  // second stream concurrently.  ev[2k] = panel solve of step k done, ev[2k+1] = bulk update of step k done.
+  // second (low-priority) stream concurrently.  ev[2k] = panel solve of step k done, ev[2k+1] = bulk update done.
+  // Independent column groups (the IMU chains of different agents, see TilePlan::h_col_group) run on their own
+  // streams: their tile columns are pure latency chains (diagonal tile → panel → tiny update) that do not share tiles.
   const bool la = st2 != nullptr && ev != nullptr;
   int last_bulk = -1;
+  bool forked = false;
+  std::vector<char> used(n_gs > 0 ? n_gs : 1, 0);
   for (int k = 0; k < nt; k++) {
-    potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag);
+    const int grp = n_gs > 0 ? plan.h_col_group[k] : -1;
+    cudaStream_t s = st;
+    if (grp >= 0) {
+      if (!forked) {
+        CVB_CUDA(ctx, cudaEventRecord(fs->fork, st));
+        forked = true;
+      }
+      s = fs->group[grp % n_gs];
+      if (!used[grp % n_gs]) {
+        CVB_CUDA(ctx, cudaStreamWaitEvent(s, fs->fork, 0));
+        used[grp % n_gs] = 1;
+      }
+    } else if (forked) {   // first column after the grouped ones: join
+      for (int g = 0; g < n_gs; g++)
+        if (used[g]) {
+          CVB_CUDA(ctx, cudaEventRecord(fs->join[g], fs->group[g]));
+          CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->join[g], 0));
+          used[g] = 0;
+        }
+      forked = false;
+    }
+    potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, s>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag);
     CVB_CHECK_LAUNCH(ctx);
     const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
     if (m > 0) {
-      trsm_kernel<<<m, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T,
-                                                      plan.d_row_idx + plan.h_col_ptr[k]);
+      trsm_kernel<<<m, GEMM_THREADS, kGemmSmem, s>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T,
+                                                     plan.d_row_idx + plan.h_col_ptr[k]);
       CVB_CHECK_LAUNCH(ctx);
-      const int p0 = plan.h_pair_ptr[k], np = plan.h_pair_ptr[k + 1] - p0, na = la ? plan.h_pair_split[k] : np;
-      if (la) {
-        CVB_CUDA(ctx, cudaEventRecord(ev[2 * k], st));
-        if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[2 * last_bulk + 1], 0));
+      const bool la_k = la && grp < 0;
+      const int p0 = plan.h_pair_ptr[k], np = plan.h_pair_ptr[k + 1] - p0, na = la_k ? plan.h_pair_split[k] : np;
+      if (la_k) {
+        CVB_CUDA(ctx, cudaEventRecord(ev[2 * k], s));
+        if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(s, ev[2 * last_bulk + 1], 0));
       }
       if (na > 0) {
-        syrk_kernel<<<na, GEMM_THREADS, kGemmSmem, st>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
+        syrk_kernel<<<na, GEMM_THREADS, kGemmSmem, s>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
         CVB_CHECK_LAUNCH(ctx);
       }
-      if (la && np - na > 0) {
+      if (la_k && np - na > 0) {
         CVB_CUDA(ctx, cudaStreamWaitEvent(st2, ev[2 * k], 0));
         syrk_kernel<<<np - na, GEMM_THREADS, kGemmSmem, st2>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0 + na,
                                                                plan.d_pair_j + p0 + na);
@@ -512,6 +541,12 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
       }
     }
   }
+  if (forked)
+    for (int g = 0; g < n_gs; g++)
+      if (used[g]) {
+        CVB_CUDA(ctx, cudaEventRecord(fs->join[g], fs->group[g]));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->join[g], 0));
+      }
   if (la && last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[2 * last_bulk + 1], 0));   // join
   return CVB_OK;
 }
@@ -568,7 +603,7 @@ extern "C" int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, co
   int rc = plan.upload(ctx, st);
   if (rc) return rc;
   cudaEventRecord(e0, st);
-  rc = factor(ctx, dS, np, dl, dflag, plan, st, nullptr, nullptr);
+  rc = factor(ctx, dS, np, dl, dflag, plan, st, nullptr);
   cudaEventRecord(e1, st);
   if (rc) return rc;
   rc = solve(ctx, dS, np, dl, dv, dv + np, dv + 2 * np, plan, st);

@@ -15,6 +15,8 @@ struct TilePlan {
   std::vector<int> h_pair_ptr, h_pair_i, h_pair_j; // per tile column k: (i >= j) pairs of those rows (trailing updates)
   std::vector<int> h_pair_split;                   // per tile column k: how many of its pairs (listed first) lie in tile column k+1
   std::vector<int> h_rowc_ptr, h_rowc_idx;         // per tile row k: non-zero column tiles i < k (backward solve)
+  std::vector<int> h_col_group;                    // optional, per tile column: id (>= 0) of an independent column group
+                                                   // (its columns share no tile with other groups), -1 = main sequence
   int *d_row_idx = nullptr, *d_pair_i = nullptr, *d_pair_j = nullptr, *d_rowc_idx = nullptr;
   long n_tiles_L = 0;
   double flops = 0.0;   // flops of one numeric factorisation with this plan
@@ -23,9 +25,16 @@ struct TilePlan {
   void release();
 };
 
-// st2/ev (2*nt events, timing disabled) enable depth-1 lookahead on a second stream; pass nullptr for a single stream
+// Extra streams/events of a factorisation (all events with timing disabled); nullptr → everything on one stream.
+struct FactorStreams {
+  cudaStream_t bulk = nullptr;       // low-priority stream of the bulk trailing updates (depth-1 lookahead)
+  cudaEvent_t* ev = nullptr;         // 2 * nt events
+  cudaStream_t group[8] = {};        // streams of the independent column groups
+  int n_group = 0;
+  cudaEvent_t fork = nullptr, join[8] = {};
+};
 int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
-           cudaStream_t st2, cudaEvent_t* ev);
+           const FactorStreams* fs);
 int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
           const TilePlan& plan, cudaStream_t st);
 

@@ -73,7 +73,9 @@ int cvb_ctx_create(int device, cvb_ctx** out) {
     return CVB_ERR_CUDA;
   }
   c->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  int prio_lo = 0, prio_hi = 0;   // the ctx stream carries the critical path (diagonal tiles, panels): greatest priority
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     delete c;
     return CVB_ERR_CUDA;
   }
