@@ -1143,9 +1143,24 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
           pb.push_back(b);
         }
   }
-  std::vector<uint32_t> order(keys.size());
-  std::iota(order.begin(), order.end(), 0u);
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x] < keys[y]; });
+  // order the pairs by (hi keyframe, lo keyframe), stable w.r.t. the landmark order in which they were generated:
+  // two counting-sort passes (LSD radix over the two keyframe indices) — O(n), where std::stable_sort took ~1 s at C3
+  std::vector<uint32_t> order(keys.size()), tmp_order(keys.size());
+  {
+    std::vector<uint32_t> cnt((size_t)K + 1);
+    auto pass = [&](const std::vector<uint32_t>* in, std::vector<uint32_t>& out, int shift) {
+      std::fill(cnt.begin(), cnt.end(), 0u);
+      const size_t n = keys.size();
+      for (size_t i = 0; i < n; i++) cnt[(size_t)((keys[in ? (*in)[i] : i] >> shift) & 0xffffffffu) + 1]++;
+      for (int b = 0; b < K; b++) cnt[b + 1] += cnt[b];
+      for (size_t i = 0; i < n; i++) {
+        const uint32_t src = in ? (*in)[i] : (uint32_t)i;
+        out[cnt[(size_t)((keys[src] >> shift) & 0xffffffffu)]++] = src;
+      }
+    };
+    pass(nullptr, tmp_order, 0);      // by lo keyframe
+    pass(&tmp_order, order, 32);      // by hi keyframe (stable)
+  }
   std::vector<int> h_sb_hi, h_sb_lo, h_sb_ptr, h_sp_a(keys.size()), h_sp_b(keys.size());
   for (size_t i = 0; i < order.size(); i++) {
     const uint64_t k = keys[order[i]];
