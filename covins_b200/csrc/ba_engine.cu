@@ -691,7 +691,11 @@ __global__ void __launch_bounds__(128) schur_kernel(int n_sb, const int* __restr
 #pragma unroll
     for (int i = 0; i < 36; i++)
       if (i == e) v = acc[i];
-    S[((size_t)off_pose[hi] + r) * ld + (size_t)off_pose[lo] + c] -= v;
+    // the pose columns are laid out chain by chain, so a block of keyframes hi > lo may belong above the diagonal:
+    // store it transposed in the lower triangle then
+    const size_t br = (size_t)off_pose[hi], bc = (size_t)off_pose[lo];
+    if (br >= bc) S[(br + r) * ld + bc + c] -= v;
+    else S[(bc + c) * ld + br + r] -= v;
   }
 }
 

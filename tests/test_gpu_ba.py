@@ -115,3 +115,36 @@ def test_c1_full_size_properties(ctx):
     frac = a["obs_removed"].mean()
     assert 0.03 < frac < 0.15
     assert (a["obs_removed"] & p["obs_is_outlier"]).sum() > 0.8 * p["obs_is_outlier"].sum()
+
+
+def _permute_keyframes(p, perm):
+    """the same problem with keyframes renumbered: new index i holds old keyframe perm[i]"""
+    inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+    q = dict(p)
+    for k in ("pose", "speedbias", "pose_const", "cam_of_kf", "agent_of", "kf_id", "gt_pose", "gt_speedbias"):
+        if k in p:
+            q[k] = p[k][perm]
+    # observations of a landmark must stay sorted by (new) keyframe index
+    new_kf = inv[p["obs_kf"]]
+    lm = np.repeat(np.arange(p["L"]), np.diff(p["lm_obs_ptr"]))
+    order = np.lexsort((new_kf, lm))
+    q["obs_kf"] = new_kf[order].astype(np.int32)
+    for k in ("obs_uv", "obs_sigma", "obs_is_outlier"):
+        q[k] = p[k][order]
+    for k in ("imu_i", "imu_j", "loop_i", "loop_j"):
+        q[k] = inv[p[k]].astype(np.int32)
+    return q, inv
+
+
+@pytest.mark.parametrize("visual_only", [True, False])
+def test_interleaved_keyframe_order_matches_oracle(ctx, visual_only):
+    """keyframes of the two agents alternate (the idpair order a real COVINS map has): chain-wise column layout must
+    still put every block in the lower triangle"""
+    p = synth_map.make_map(seed=21, n_agents=2, kf_per_agent=40, n_lm=2000, outlier_frac=0.0)
+    K = p["K"]
+    perm = np.empty(K, np.int64); perm[0::2] = np.arange(0, K // 2); perm[1::2] = np.arange(K // 2, K)
+    q, inv = _permute_keyframes(p, perm)
+    assert q["pose_const"][0] == 1
+    got = O.solve(ctx, q, 6, visual_only=visual_only)
+    ref = bo.solve(bo.Problem(q, visual_only=visual_only, loop_loss=1.0), 6)
+    _compare(got, ref, q)
