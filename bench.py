@@ -346,6 +346,28 @@ def run_ours(args):
     barrier()
     dt = max_over_ranks(time.perf_counter() - t0)
     e2e_gp = pairs * world * e2e_steps / dt / 1e9
+    # e2e through the resident-map API (cvb_db_*): keyframes uploaded once when they join the map (outside the timed
+    # region, as in the server's life cycle), per request the query keyframe goes up and the accepted matches come down.
+    dbs = []
+    for c in range(N_COPIES):
+        db = M.DescriptorDatabase(ctx, reserve_rows=N_KF * N_FEAT)
+        db.append(h_maps_np[c % 2] if c < 2 else maps[c].cpu().numpy(), np.full(N_KF, N_FEAT, np.int32))
+        dbs.append(db)
+    h_queries = [np.ascontiguousarray(h_maps_np[0][k * N_FEAT:(k + 1) * N_FEAT]) for k in (123, 777, 1500, 42)]
+    db_steps = max(args.steps, 10)
+    d2h_db = 0
+    for i in range(3):
+        dbs[i % N_COPIES].match_hamming(h_queries[i % 4], THR, RATIO)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(db_steps):
+        out = dbs[i % N_COPIES].match_hamming(h_queries[i % 4], THR, RATIO)
+        d2h_db += out[0].nbytes + 4 + sum(o.nbytes for o in out[1:])
+    barrier()
+    dt_db = max_over_ranks(time.perf_counter() - t0)
+    e2e_db_gp = pairs * world * db_steps / dt_db / 1e9
+    for db in dbs:
+        db.close()
     alg_bytes = 32 * N_KF * N_FEAT + 32 * N_FEAT + 8 * N_KF * N_FEAT + 4 * N_KF   # 32 Nt + 32 Nq + outputs
     ms_step = ms_match / m_steps
     hbm_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
@@ -389,8 +411,16 @@ def run_ours(args):
                    "pairs_per_step_per_gpu": pairs,
                    "l2_policy": f"{N_COPIES} map copies (256 MB > 126 MB L2) rotated per step",
                    "parallelism": f"map sharded by keyframe x{world}, no data-path collective"},
-        "e2e": {"value": e2e_gp, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h_q.nbytes + h_maps_np[0].nbytes + h_seg.nbytes),
-                "d2h_bytes_per_step": N_KF * N_FEAT * 8 + N_KF * 4, "steps": e2e_steps},
+        "e2e": {"value": e2e_db_gp, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h_queries[0].nbytes),
+                "d2h_bytes_per_step": int(d2h_db // db_steps), "steps": db_steps, "ms_per_step": dt_db / db_steps * 1e3,
+                "api": "cvb_db_match_hamming: host query in, per-keyframe match counts + compacted accepted matches out; the "
+                       "map's descriptors were appended once with cvb_db_append (outside the timed region) and stay in HBM; "
+                       f"{N_COPIES} databases (256 MB > L2) rotated per step",
+                "upload_every_call": {"value": e2e_gp, "unit": "Gpairs/s",
+                                      "h2d_bytes_per_step": int(h_q.nbytes + h_maps_np[0].nbytes + h_seg.nbytes),
+                                      "d2h_bytes_per_step": N_KF * N_FEAT * 8 + N_KF * 4, "steps": e2e_steps,
+                                      "api": "cvb_match_hamming_batch: the whole 64 MB map re-uploaded from host memory on "
+                                             "every call and the dense [n_kf][nq] result matrices downloaded (PCIe-bound)"}},
         "gpu_launches": int(match_launches),
         "roofline": {"bound": "tensor", "achieved": tops, "peak": i8_peak, "unit": "TOP/s", "frac": tops / i8_peak, "traffic": None,
                      "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate); no measured int8 figure exists",

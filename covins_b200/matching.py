@@ -94,6 +94,63 @@ def match_candidates_hamming(ctx: Context, q, t, seg_ptr=None, thr: float = 40.0
     return mt, md, nm
 
 
+class DescriptorDatabase:
+    """The merged map's ORB descriptors resident in HBM (cvb_db_*): keyframes are appended once, a place-recognition
+    request (placerec_gen_be.cpp:60-135) uploads only the query keyframe and downloads only the accepted matches."""
+
+    def __init__(self, ctx: Context, reserve_rows: int = 0):
+        import ctypes as C
+        self.ctx = ctx
+        h = C.c_void_p()
+        ctx.check(lib().cvb_db_create(ctx.handle, 32, C.byref(h)))
+        self.handle = h
+        self._cap = 1 << 16
+        if reserve_rows:
+            ctx.check(lib().cvb_db_reserve(ctx.handle, self.handle, int(reserve_rows)))
+
+    def append(self, rows, rows_per_kf):
+        """rows u8 [sum(rows_per_kf), 32] = the descriptor matrices of the new keyframes, concatenated."""
+        rows = _np(rows, np.uint8).reshape(-1, 32)
+        rpk = np.ascontiguousarray(np.asarray(rows_per_kf, np.int32).reshape(-1))
+        assert int(rpk.sum()) == len(rows), "rows_per_kf does not add up to the number of rows"
+        self.ctx.check(lib().cvb_db_append(self.ctx.handle, self.handle, _ptr(rows), _ptr(rpk), len(rpk)))
+
+    def size(self):
+        import ctypes as C
+        n_kf, n_rows = C.c_int32(), C.c_int64()
+        self.ctx.check(lib().cvb_db_size(self.handle, C.byref(n_kf), C.byref(n_rows)))
+        return n_kf.value, n_rows.value
+
+    def match_hamming(self, q, thr: float = 40.0, ratio: float = 0.8):
+        """→ (n_matches [n_kf] i32, m_kf, m_query, m_train (keyframe-local), m_dist): the accepted matches ordered by
+        (keyframe, queryIdx) — per keyframe the reference's img_matches vector."""
+        import ctypes as C
+        q = _np(q, np.uint8).reshape(-1, 32)
+        n_kf, _ = self.size()
+        nm = np.zeros(n_kf, np.int32)
+        while True:
+            cap = self._cap
+            out = [np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.int32), np.empty(cap, np.float32)]
+            tot = C.c_int32()
+            self.ctx.check(lib().cvb_db_match_hamming(self.ctx.handle, self.handle, _ptr(q), len(q), thr, ratio,
+                                                      _ptr(nm), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]),
+                                                      cap, C.byref(tot)))
+            if tot.value <= cap:
+                return (nm,) + tuple(o[:tot.value] for o in out)
+            self._cap = int(tot.value * 1.25) + 16
+
+    def close(self):
+        if self.handle:
+            lib().cvb_db_destroy(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------
 # L2 k-NN (SIFT)
 # ------------------------------------------------------------------------------------------------

@@ -88,6 +88,31 @@ CVB_API int cvb_match_hamming_batch_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq
                                         int32_t* d_n_matches, void* stream);
 
 /*
+ * Resident descriptor database: the ORB descriptors of the merged map's keyframes stay in HBM.
+ * Replaces, for the place-recognition loop of placerec_gen_be.cpp:60-135 (one knnMatch + filter per
+ * candidate keyframe, :82-114), the per-call upload of the train descriptors: a keyframe's descriptor
+ * matrix is immutable once the keyframe exists (keyframe_be.cpp:106-137), so it is appended once
+ * (cvb_db_append, one segment per keyframe, in the caller's keyframe order) and a request moves only
+ * the query keyframe up (nq*32 B) and the ACCEPTED matches down.
+ *
+ * cvb_db_match_hamming: same semantics as cvb_match_hamming_batch against every keyframe of the
+ * database.  n_matches [n_kf] (may be NULL) = img_matches.size() per keyframe (:116-124); the accepted
+ * matches are returned compacted, ordered by (keyframe, queryIdx) — per keyframe exactly the
+ * reference's img_matches vector: m_kf / m_query / m_train (keyframe-local trainIdx) / m_dist.
+ * *n_total = number of accepted matches over all keyframes; at most `cap` are written (call again with
+ * a larger cap if *n_total > cap).
+ */
+typedef struct cvb_db cvb_db;
+CVB_API int cvb_db_create(cvb_ctx* ctx, int desc_bytes, cvb_db** out);
+CVB_API int cvb_db_destroy(cvb_ctx* ctx, cvb_db* db);
+CVB_API int cvb_db_reserve(cvb_ctx* ctx, cvb_db* db, int64_t rows);
+CVB_API int cvb_db_append(cvb_ctx* ctx, cvb_db* db, const uint8_t* rows, const int32_t* rows_per_kf, int n_kf);
+CVB_API int cvb_db_size(const cvb_db* db, int32_t* n_kf, int64_t* n_rows);
+CVB_API int cvb_db_match_hamming(cvb_ctx* ctx, cvb_db* db, const uint8_t* q, int nq, float thr, float ratio,
+                                 int32_t* n_matches, int32_t* m_kf, int32_t* m_query, int32_t* m_train,
+                                 float* m_dist, int cap, int32_t* n_total);
+
+/*
  * Replaces the SIFT branch, cv::FlannBasedMatcher()::knnMatch(query, train, out, 2)
  *   (placerec_gen_be.cpp:86-87,99; RelNonCentralPosSolver.cpp:310-311,323), with the EXACT brute-force
  *   result cv::BFMatcher(NORM_L2) gives (FLANN is approximate and randomised).

@@ -193,3 +193,35 @@ def test_full_size_properties_c3(ctx):
     tn = t.view(n_kf, nf, 32)[sample].reshape(-1, 32).cpu().numpy()
     ri, rd = ora.knn_hamming_batch(q.cpu().numpy(), tn, synth.seg_ptr_uniform(len(sample), nf), 2)
     assert np.array_equal(idx[sample].cpu().numpy(), ri) and np.array_equal(dist[sample].cpu().numpy(), rd)
+
+
+def test_descriptor_database_matches_batch_call_and_oracle(ctx):
+    """cvb_db_*: keyframes appended in several calls (ragged, one empty) stay resident; a query returns exactly the
+    accepted matches of cvb_match_hamming_batch, compacted in (keyframe, queryIdx) order (= img_matches per KF)."""
+    desc, _ = synth.orb_keyframes(seed=11, n_kf=14, n_feat=600, n_lm=900, window=900)
+    lens = [600, 0, 1, 333, 600, 257, 128, 600, 17, 600, 599, 64, 600]
+    t = np.concatenate([desc[i + 1][:l] for i, l in enumerate(lens)])
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    db = M.DescriptorDatabase(ctx)
+    assert db.size() == (0, 0)
+    cut = [0, 4, 5, 13]
+    for a, b in zip(cut[:-1], cut[1:]):
+        db.append(t[seg[a]:seg[b]], lens[a:b])
+    assert db.size() == (len(lens), int(seg[-1]))
+    for q in (desc[0], desc[0][:77], desc[5][:600]):
+        for thr, ratio in ((40.0, 0.8), (64.0, 0.95)):
+            nm, m_kf, m_q, m_t, m_d = db.match_hamming(q, thr, ratio)
+            mt, md, rn = M.match_candidates_hamming(ctx, q, t, seg, thr, ratio)
+            ri, rd = ora.knn_hamming_batch(q, t, seg, k=2)
+            omt, omd, onm = ora.ratio_filter(ri, rd.astype(np.float32), thr, ratio)
+            assert np.array_equal(mt, omt) and np.array_equal(rn, onm)
+            assert np.array_equal(nm, rn)
+            kf, qq = np.nonzero(mt >= 0)          # row-major = (keyframe, queryIdx) order
+            assert len(kf) == len(m_kf) == int(nm.sum())
+            assert np.array_equal(m_kf, kf) and np.array_equal(m_q, qq)
+            assert np.array_equal(m_t, mt[kf, qq]) and np.array_equal(m_d, md[kf, qq])
+    # capacity retry path: a tiny initial capacity must give the same answer
+    db._cap = 3
+    nm2, *rest = db.match_hamming(desc[0], 64.0, 0.95)
+    assert int(nm2.sum()) == len(rest[0]) > 3
+    db.close()
