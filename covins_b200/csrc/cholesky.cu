@@ -15,11 +15,11 @@
 // All reductions have a fixed order → bit-reproducible run to run.
 #include "cholesky.cuh"
 
-namespace cvb_chol {
+#include <stdlib.h>
 
-constexpr int KC = 32;        // K chunk staged in shared memory
-constexpr int LDS = KC + 4;   // padded row stride (doubles): conflict-free m8n8k4 fragment loads
-constexpr int GEMM_THREADS = 512;
+#include <algorithm>
+
+namespace cvb_chol {
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cvb_smem_addr(smem)), "l"(gmem) : "memory");
@@ -35,42 +35,52 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
-// acc(128x128) = A(128xT) * B(128xT)^T, both operands row-major with K contiguous (leading dims lda, ldb).
-// 16 warps in a 4x4 grid, 32x32 per warp = 4x4 m8n8k4 tiles; K staged in chunks of 32, double buffered.
-__device__ __forceinline__ void gemm_abt_128(const double* __restrict__ A, size_t lda, const double* __restrict__ B,
-                                             size_t ldb, double (&acc)[4][4][2], double* smem) {
-  double* As[2] = {smem, smem + 2 * T * LDS};
-  double* Bs[2] = {smem + T * LDS, smem + 3 * T * LDS};
+// acc(64 x BN) = A(64 x T) * B(BN x T)^T, both operands row-major with K contiguous (leading dims lda, ldb).
+// 2 x BN/32 warps, 32x32 per warp = 4x4 m8n8k4 tiles.  K is staged in chunks of 16 through a STAGES-deep cp.async ring
+// (one barrier per chunk).  Row stride 20 doubles (≡ 8 words mod 32): the fragment loads of a half-warp are
+// conflict-free.  The CTA is deliberately small (64 x 64 x 128 for the trailing update: 128 threads, 60 KB): three to
+// four CTAs share an SM, so one CTA's fixed costs — index fetch, pipeline fill, the C round trip of the epilogue, barrier
+// bubbles — overlap the others' main loops.  (One 128x128 tile per SM left the FP64 tensor pipe idle a third of the time.)
+constexpr int KC = 16;
+constexpr int LDS = KC + 4;
+constexpr int GEMM_STAGES = 3;
+
+template <int BN>
+__device__ __forceinline__ void gemm_abt_64(const double* __restrict__ A, size_t lda, const double* __restrict__ B,
+                                            size_t ldb, double (&acc)[4][4][2], double* smem) {
+  constexpr int WN = BN / 32, THREADS = 2 * WN * 32, STAGE = (64 + BN) * LDS, NCH = T / KC, UPR = KC / 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp / WN, wn = warp % WN;
 #pragma unroll
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  auto load_chunk = [&](int kc, int st) {
+  auto load_chunk = [&](int kc) {
+    if (kc < NCH) {
+      double* As = smem + (kc % GEMM_STAGES) * STAGE;
+      double* Bs = As + 64 * LDS;
 #pragma unroll
-    for (int it = 0; it < 4; it++) {
-      const int u = tid + it * GEMM_THREADS;  // 2048 16-byte units per operand
-      const int r = u >> 4, seg = u & 15;
-      cp_async16(As[st] + r * LDS + seg * 2, A + (size_t)r * lda + kc * KC + seg * 2);
-      cp_async16(Bs[st] + r * LDS + seg * 2, B + (size_t)r * ldb + kc * KC + seg * 2);
+      for (int it = 0; it < 64 * UPR / THREADS; it++) {
+        const int u = tid + it * THREADS, r = u / UPR, seg = u % UPR;
+        cp_async16(As + r * LDS + seg * 2, A + (size_t)r * lda + kc * KC + seg * 2);
+      }
+#pragma unroll
+      for (int it = 0; it < BN * UPR / THREADS; it++) {
+        const int u = tid + it * THREADS, r = u / UPR, seg = u % UPR;
+        cp_async16(Bs + r * LDS + seg * 2, B + (size_t)r * ldb + kc * KC + seg * 2);
+      }
     }
-    cp_async_commit();
+    cp_async_commit();   // always commit (possibly empty) so the wait count below is uniform
   };
-  constexpr int NCH = T / KC;
-  load_chunk(0, 0);
+#pragma unroll
+  for (int c = 0; c < GEMM_STAGES - 1; c++) load_chunk(c);
   for (int kc = 0; kc < NCH; kc++) {
-    const int st = kc & 1;
-    if (kc + 1 < NCH) {
-      load_chunk(kc + 1, st ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const double* a_base = As[st] + (wm * 32 + (lane >> 2)) * LDS + (lane & 3);
-    const double* b_base = Bs[st] + (wn * 32 + (lane >> 2)) * LDS + (lane & 3);
+    cp_async_wait<GEMM_STAGES - 2>();   // chunk kc has landed
+    __syncthreads();                    // ... for every thread, and chunk kc-1's stage is free again
+    load_chunk(kc + GEMM_STAGES - 1);
+    const double* As = smem + (kc % GEMM_STAGES) * STAGE;
+    const double* a_base = As + (wm * 32 + (lane >> 2)) * LDS + (lane & 3);
+    const double* b_base = As + 64 * LDS + (wn * 32 + (lane >> 2)) * LDS + (lane & 3);
 #pragma unroll
     for (int ks = 0; ks < KC / 4; ks++) {
       double a[4], b[4];
@@ -83,21 +93,24 @@ __device__ __forceinline__ void gemm_abt_128(const double* __restrict__ A, size_
 #pragma unroll
         for (int j = 0; j < 4; j++) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    __syncthreads();
   }
 }
 
-constexpr size_t kGemmSmem = (size_t)4 * T * LDS * sizeof(double);  // 147456 B
+constexpr int TRSM_THREADS = 256, SYRK_THREADS = 128;
+constexpr size_t kTrsmSmem = (size_t)GEMM_STAGES * (64 + 128) * LDS * sizeof(double);   //  92160 B → 2 CTAs / SM
+constexpr size_t kSyrkSmem = (size_t)GEMM_STAGES * (64 + 64) * LDS * sizeof(double);    //  61440 B → 3 CTAs / SM
 
-// A(i,k) <- A(i,k) * Linv_k^T for the structurally non-zero row tiles i of tile column k (rows[])
-__global__ void __launch_bounds__(GEMM_THREADS, 1) trsm_kernel(double* __restrict__ S, size_t ld, int k,
+// A(i,k) <- A(i,k) * Linv_k^T for the structurally non-zero row tiles i of tile column k (rows[]).  Two CTAs per tile,
+// each owns 64 full rows (it has consumed all of them as the A operand before it overwrites them).
+__global__ void __launch_bounds__(TRSM_THREADS, 2) trsm_kernel(double* __restrict__ S, size_t ld, int k,
                                                                 const double* __restrict__ linv_k,
                                                                 const int* __restrict__ rows) {
   extern __shared__ __align__(16) double smem_d[];
-  const int i = rows[blockIdx.x];
-  double* At = S + (size_t)i * T * ld + (size_t)k * T;
+  const int i = rows[blockIdx.x >> 1], half = blockIdx.x & 1;
+  double* At = S + ((size_t)i * T + half * 64) * ld + (size_t)k * T;
   double acc[4][4][2];
-  gemm_abt_128(At, ld, linv_k, T, acc, smem_d);
+  gemm_abt_64<128>(At, ld, linv_k, T, acc, smem_d);
+  __syncthreads();   // every warp is done reading this CTA's rows (they were all staged through shared memory)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 2, wn = warp & 3;
 #pragma unroll
   for (int a = 0; a < 4; a++)
@@ -109,162 +122,223 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) trsm_kernel(double* __restric
 }
 
 // A(i,j) -= A(i,k) A(j,k)^T for the tile pairs (i >= j) of column k's non-zero rows: pi[]/pj[] enumerate them.
-__global__ void __launch_bounds__(GEMM_THREADS, 1) syrk_kernel(double* __restrict__ S, size_t ld, int k,
+// Four CTAs per pair, one 64x64 quadrant each (consecutive CTAs share the pair's operands in L2); the quadrant above
+// the diagonal of a diagonal tile is skipped.
+__global__ void __launch_bounds__(SYRK_THREADS, 3) syrk_kernel(double* __restrict__ S, size_t ld, int k,
                                                                 const int* __restrict__ pi, const int* __restrict__ pj) {
   extern __shared__ __align__(16) double smem_d[];
-  const int i = pi[blockIdx.x], j = pj[blockIdx.x];
-  const double* Ai = S + (size_t)i * T * ld + (size_t)k * T;
-  const double* Aj = S + (size_t)j * T * ld + (size_t)k * T;
-  double* C = S + (size_t)i * T * ld + (size_t)j * T;
+  const int p = blockIdx.x >> 2, qr = (blockIdx.x >> 1) & 1, qc = blockIdx.x & 1;
+  const int i = pi[p], j = pj[p];
+  if (i == j && qc > qr) return;
+  const double* Ai = S + ((size_t)i * T + qr * 64) * ld + (size_t)k * T;
+  const double* Aj = S + ((size_t)j * T + qc * 64) * ld + (size_t)k * T;
+  double* C = S + ((size_t)i * T + qr * 64) * ld + (size_t)j * T + qc * 64;
   double acc[4][4][2];
-  gemm_abt_128(Ai, ld, Aj, ld, acc, smem_d);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 2, wn = warp & 3;
+  gemm_abt_64<64>(Ai, ld, Aj, ld, acc, smem_d);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 1, wn = warp & 1;
 #pragma unroll
   for (int a = 0; a < 4; a++)
 #pragma unroll
     for (int b = 0; b < 4; b++) {
       const int r = wm * 32 + a * 8 + (lane >> 2), c = wn * 32 + b * 8 + (lane & 3) * 2;
-      double2* p = reinterpret_cast<double2*>(C + (size_t)r * ld + c);
-      double2 v = *p;
+      double2* q = reinterpret_cast<double2*>(C + (size_t)r * ld + c);
+      double2 v = *q;
       v.x -= acc[a][b][0];
       v.y -= acc[a][b][1];
-      *p = v;
+      *q = v;
     }
 }
 
-// Factor the diagonal tile k in shared memory and invert the factor, one CTA of 512 threads.
-//   Cholesky: blocked right-looking, 16-wide block columns.  Per block column: (a) the 16x16 diagonal block is factored
-//   register-resident by one warp (rank-1 updates broadcast with shuffles) and inverted; (b) the panel below it is
-//   multiplied by that inverse (no division chains); (c) the trailing sub-matrix gets its rank-16 update with 4x4
-//   register tiles (0.5 shared-memory loads per multiply-add — the naive form is LDS-bandwidth bound).
-//   Inverse: in place by recursive doubling (16 → 32 → 64 → 128): X21 = -C^-1 (B A^-1), 4x4 register tiles, a 32 KB
-//   scratch tile; the 16x16 diagonal inverses come from the factorisation.
+// Factor the diagonal tile k in shared memory and invert the factor, one CTA of 512 threads.  This kernel is the serial
+// chain of the whole factorisation (one launch per tile column, nothing else can run before its panel is solved), so it
+// is organised around dependent-operation latency (measured on B200: DFMA 8.7, SHFL 30, STS→LDS 35, rsqrt 65 cycles):
+//   Cholesky: blocked right-looking, 16-wide block columns.  Per block column
+//     (a) warp 0 factors the 16x16 diagonal block register-resident (lane = 2*row + half).  Per pivot the *unscaled*
+//         column goes through 128 B of shared memory and the update uses a_rj * a_cj / pivot, so the chain per pivot is
+//         STS → LDS → reciprocal → DMUL → DFMA (≈ 100 cycles); rsqrt and the L values are computed off the chain;
+//     (b) one thread per row below solves its 16 unknowns by substitution against the block (in place, no scratch);
+//     (c) the trailing sub-matrix gets its rank-16 update with 4x4 register tiles whose rows are interleaved with stride
+//         n/4 (conflict-free shared-memory operand loads); one thread owns the product of row sets {tr+i*S} x {tc+j*S}
+//         and scatters it to both triangles' canonical (row >= col) positions;
+//     meanwhile warp 15 inverts the 16x16 diagonal block (needed only by the inverse phase) off the critical path.
+//   Inverse: in place by recursive doubling (16 → 32 → 64 → 128): X21 = -C^-1 (B A^-1), 4x4 register tiles with
+//   interleaved columns, a padded scratch tile; the 16x16 diagonal inverses come from the factorisation.
 // L is written back to S, the inverse (row-major 128x128, zeros above the diagonal) to linv_k.  flag[0] |= 1 on a
 // non-positive pivot (matrix not positive definite → the caller raises mu, as Ceres does on LINEAR_SOLVER_FAILURE).
 constexpr int LDP = T + 1;
 constexpr int PB = 16;
 constexpr int POTRF_THREADS = 512;
-constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)64 * 64 + (size_t)(T / PB) * PB * PB) * sizeof(double);
+constexpr int POTRF_WORKERS = POTRF_THREADS - 32;   // warp 15 inverts the diagonal blocks
+constexpr int TMP_DOUBLES = 64 * 65;
+constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)TMP_DOUBLES + (size_t)(T / PB) * PB * PB) * sizeof(double);
 
-// C[4][4] (+)= sum_m P[i][m] * Q[j][m], rows of P/Q at stride ldp/ldq, m in [m0, m1)
-__device__ __forceinline__ void tile4x4(const double* __restrict__ P, int ldp, const double* __restrict__ Q, int ldq, int m0,
-                                        int m1, double (&c)[4][4]) {
-  for (int m = m0; m < m1; m++) {
-    double pv[4], qv[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) { pv[i] = P[i * ldp + m]; qv[i] = Q[i * ldq + m]; }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-      for (int j = 0; j < 4; j++) c[i][j] += pv[i] * qv[j];
-  }
-}
+#define POTRF_MARK(i)                                     \
+  do {                                                    \
+    if (prof != nullptr && tid == 0) prof[i] = clock64(); \
+  } while (0)
 
 __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __restrict__ S, size_t ld, int k,
-                                                                     double* __restrict__ linv_k, int* __restrict__ flag) {
+                                                                     double* __restrict__ linv_k, int* __restrict__ flag,
+                                                                     long long* __restrict__ prof, int prof_fine) {
   extern __shared__ __align__(16) double smem_d[];
   double* a = smem_d;                     // [T][LDP]
-  double* tmp = smem_d + T * LDP;         // 64 x 64 scratch
-  double* binv = tmp + 64 * 64;           // [8][16][16] inverses of the diagonal 16x16 blocks of L
+  double* tmp = smem_d + T * LDP;         // scratch of the inverse phase
+  double* binv = tmp + TMP_DOUBLES;       // [8][16][16] inverses of the diagonal 16x16 blocks of L
+  __shared__ __align__(16) double colbuf[2][PB];
+  __shared__ double pivbuf[2];
+  __shared__ double rdbuf[PB];            // reciprocal diagonal of the current diagonal block
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* At = S + (size_t)k * T * ld + (size_t)k * T;
-  for (int u = tid; u < T * T; u += POTRF_THREADS) {
-    const int r = u / T, c = u % T;
-    a[r * LDP + c] = (c <= r) ? At[(size_t)r * ld + c] : 0.0;
+  POTRF_MARK(0);
+  {
+    // all 16 16-byte loads of a thread are in flight before the first use (one L2/HBM round trip for the tile)
+    double2 buf[T * T / 2 / POTRF_THREADS];
+#pragma unroll
+    for (int it = 0; it < T * T / 2 / POTRF_THREADS; it++) {
+      const int u = tid + it * POTRF_THREADS, r = u / (T / 2), c = (u % (T / 2)) * 2;
+      buf[it] = (c <= r) ? *reinterpret_cast<const double2*>(At + (size_t)r * ld + c) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int it = 0; it < T * T / 2 / POTRF_THREADS; it++) {
+      const int u = tid + it * POTRF_THREADS, r = u / (T / 2), c = (u % (T / 2)) * 2;
+      a[r * LDP + c] = buf[it].x;
+      a[r * LDP + c + 1] = (c + 1 <= r) ? buf[it].y : 0.0;
+    }
   }
   __syncthreads();
+  POTRF_MARK(1);
   // ---------------- Cholesky ----------------
+  long long t_a = 0, acc_a = 0, acc_ab = 0, acc_b = 0, acc_c = 0;   // fine profile (thread 0 only), kept in registers
   for (int jb = 0; jb < T / PB; jb++) {
     const int c0 = jb * PB, nbelow = T - c0 - PB;
+    if (prof_fine && tid == 0) t_a = clock64();
     if (warp == 0) {
-      // (a) 16x16 diagonal block: lane i (< 16; lanes 16-31 mirror) owns row i
-      const int i = lane & 15;
-      double row[PB];
+      // (a) the 16x16 diagonal block, treated as a full symmetric matrix (the upper half is mirrored in on load)
+      const int r = lane >> 1, hf = lane & 1;
+      double v[8];
 #pragma unroll
-      for (int c = 0; c < PB; c++) row[c] = a[(c0 + i) * LDP + c0 + c];
-      double rd[PB];   // reciprocal diagonal (identical on all lanes)
+      for (int c = 0; c < 8; c++) {
+        const int cc = hf * 8 + c;
+        v[c] = (cc <= r) ? a[(c0 + r) * LDP + c0 + cc] : a[(c0 + cc) * LDP + c0 + r];
+      }
 #pragma unroll
       for (int j = 0; j < PB; j++) {
-        double piv = __shfl_sync(0xffffffffu, row[j], j);
+        const int jh = j >> 3, jc = j & 7;
+        if (hf == jh) {
+          colbuf[j & 1][r] = (r > j) ? v[jc] : 0.0;    // unscaled column j below the pivot; zeros at and above it
+          if (r == j) pivbuf[j & 1] = v[jc];
+        }
+        __syncwarp();
+        double piv = pivbuf[j & 1];
+        const double own = colbuf[j & 1][r];
+        const double2* cb = reinterpret_cast<const double2*>(&colbuf[j & 1][hf * 8]);
+        const double2 l01 = cb[0], l23 = cb[1], l45 = cb[2], l67 = cb[3];
         if (!(piv > 0.0)) {
           if (lane == 0) atomicOr(flag, 1);
           piv = 1.0;
         }
-        const double rinv = rsqrt(piv);
-        rd[j] = rinv;
-        const double lij = (i >= j) ? row[j] * rinv : 0.0;   // column j of L
-        row[j] = lij;
-#pragma unroll
-        for (int c = j + 1; c < PB; c++) {
-          const double lcj = __shfl_sync(0xffffffffu, lij, c);
-          if (i >= c) row[c] -= lij * lcj;
-        }
+        const double t = own * (1.0 / piv);             // the chain: reciprocal → DMUL → DFMA
+        v[0] -= t * l01.x; v[1] -= t * l01.y; v[2] -= t * l23.x; v[3] -= t * l23.y;
+        v[4] -= t * l45.x; v[5] -= t * l45.y; v[6] -= t * l67.x; v[7] -= t * l67.y;
+        const double rinv = rsqrt(piv);                 // off the chain
+        if (hf == jh) v[jc] = (r > j) ? own * rinv : ((r == j) ? piv * rinv : 0.0);   // column j of L
+        if (lane == 0) rdbuf[j] = rinv;
       }
-      if (lane < PB) {
 #pragma unroll
-        for (int c = 0; c < PB; c++) a[(c0 + i) * LDP + c0 + c] = (c <= i) ? row[c] : 0.0;
-      }
-      __syncwarp();
-      // inverse of the block: lane j (< 16) builds column j by forward substitution (L read back from shared memory)
-      if (lane < PB) {
-        const int j = lane;
-        double x[PB];
-#pragma unroll
-        for (int r = 0; r < PB; r++) {
-          double sacc = (r == j) ? 1.0 : 0.0;
-#pragma unroll
-          for (int m = 0; m < PB; m++)
-            if (m < r) sacc -= a[(c0 + r) * LDP + c0 + m] * ((m >= j) ? x[m] : 0.0);
-          x[r] = (r >= j) ? sacc * rd[r] : 0.0;
-        }
-#pragma unroll
-        for (int r = 0; r < PB; r++) binv[(jb * PB + r) * PB + j] = x[r];   // Linv_block[r][j]
-      }
+      for (int c = 0; c < 8; c++) a[(c0 + r) * LDP + c0 + hf * 8 + c] = (hf * 8 + c <= r) ? v[c] : 0.0;
+      if (prof_fine && tid == 0) acc_a += clock64() - t_a;
     }
     __syncthreads();
+    if (prof_fine && tid == 0) { const long long tt = clock64(); acc_ab += tt - t_a; t_a = tt; }
+    if (warp == POTRF_THREADS / 32 - 1) {
+      // inverse of the diagonal block, off the critical path: lane j (< 16) builds column j of Ljj^-1 by forward
+      // substitution in axpy form (16 dependent steps, the row updates of a step are independent)
+      if (lane < PB) {
+        const int j = lane;
+        double res[PB];
+#pragma unroll
+        for (int q = 0; q < PB; q++) res[q] = (q == j) ? 1.0 : 0.0;
+#pragma unroll
+        for (int m = 0; m < PB; m++) {
+          const double xm = res[m] * rdbuf[m];       // rows m < j stay exactly zero
+          res[m] = xm;
+#pragma unroll
+          for (int q = m + 1; q < PB; q++) res[q] -= a[(c0 + q) * LDP + c0 + m] * xm;
+        }
+#pragma unroll
+        for (int q = 0; q < PB; q++) binv[(jb * PB + q) * PB + j] = res[q];   // Linv_block[q][j]
+      }
+    } else if (nbelow > 0) {
+      // (b) panel: row r of X solves X Ljj^T = A(r, block), one thread per row, in place
+      if (tid < nbelow) {
+        const int r = c0 + PB + tid;
+        double x[PB];
+#pragma unroll
+        for (int m = 0; m < PB; m++) x[m] = a[r * LDP + c0 + m];
+#pragma unroll
+        for (int m = 0; m < PB; m++) {
+          const double xm = x[m] * rdbuf[m];
+          x[m] = xm;
+#pragma unroll
+          for (int q = m + 1; q < PB; q++) x[q] -= a[(c0 + q) * LDP + c0 + m] * xm;
+        }
+#pragma unroll
+        for (int m = 0; m < PB; m++) a[r * LDP + c0 + m] = x[m];
+      }
+    }
+    __syncthreads();   // (the last block column has no panel; warp 15 still finishes its inverse before the barrier)
+    if (prof_fine && tid == 0) { const long long tt = clock64(); acc_b += tt - t_a; t_a = tt; }
     if (nbelow > 0) {
-      // (b) panel: X[r][j] = sum_{m <= j} A[r][c0+m] * Linv_block[j][m]   (X Ljj^T = A)
-      for (int u = tid; u < nbelow * PB; u += POTRF_THREADS) {
-        const int r = c0 + PB + u / PB, j = u % PB;
-        const double* ar = a + r * LDP + c0;
-        const double* bj = binv + (jb * PB + j) * PB;
-        double sacc = 0.0;
+      // (c) trailing update A[r][c] -= sum_{m<16} L[r][c0+m] L[c][c0+m] for r >= c >= c0+16
+      const int Sx = nbelow / 4, ntiles = Sx * (Sx + 1) / 2, base = c0 + PB;
+      if (tid < POTRF_WORKERS)
+        for (int u = tid; u < ntiles; u += POTRF_WORKERS) {
+          int tr = (int)((sqrtf(8.0f * (float)u + 1.0f) - 1.0f) * 0.5f);
+          while ((tr + 1) * (tr + 2) / 2 <= u) tr++;
+          while (tr * (tr + 1) / 2 > u) tr--;
+          const int tc = u - tr * (tr + 1) / 2;   // tc <= tr
+          const double* P = a + (base + tr) * LDP + c0;
+          const double* Q = a + (base + tc) * LDP + c0;
+          double g[4][4];
 #pragma unroll
-        for (int m = 0; m < PB; m++)
-          if (m <= j) sacc += ar[m] * bj[m];
-        tmp[u] = sacc;
-      }
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) g[i][j] = 0.0;
+#pragma unroll 4
+          for (int m = 0; m < PB; m++) {
+            double pv[4], qv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { pv[i] = P[i * Sx * LDP + m]; qv[i] = Q[i * Sx * LDP + m]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+              for (int j = 0; j < 4; j++) g[i][j] += pv[i] * qv[j];
+          }
+          // g[i][j] = <row tr+i*Sx, row tc+j*Sx>: canonical position is (larger row index, smaller row index)
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int ri = base + tr + i * Sx, cj = base + tc + j * Sx;
+              if (j <= i) a[ri * LDP + cj] -= g[i][j];
+              else if (tr != tc) a[cj * LDP + ri] -= g[i][j];
+            }
+        }
       __syncthreads();
-      for (int u = tid; u < nbelow * PB; u += POTRF_THREADS) a[(c0 + PB + u / PB) * LDP + c0 + (u % PB)] = tmp[u];
-      __syncthreads();
-      // (c) trailing update A[r][c] -= sum_{m<16} L[r][c0+m] L[c][c0+m] for r >= c >= c0+16, 4x4 register tiles
-      const int nt4 = nbelow / 4, ntiles = nt4 * (nt4 + 1) / 2;
-      for (int u = tid; u < ntiles; u += POTRF_THREADS) {
-        int tr = (int)((sqrtf(8.0f * (float)u + 1.0f) - 1.0f) * 0.5f);
-        while ((tr + 1) * (tr + 2) / 2 <= u) tr++;
-        while (tr * (tr + 1) / 2 > u) tr--;
-        const int tc = u - tr * (tr + 1) / 2;
-        const int r0 = c0 + PB + 4 * tr, cc0 = c0 + PB + 4 * tc;
-        double c4[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++) c4[i][j] = 0.0;
-        tile4x4(a + r0 * LDP + c0, LDP, a + cc0 * LDP + c0, LDP, 0, PB, c4);
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-#pragma unroll
-          for (int j = 0; j < 4; j++)
-            if (cc0 + j <= r0 + i) a[(r0 + i) * LDP + cc0 + j] -= c4[i][j];
-      }
-      __syncthreads();
+      if (prof_fine && tid == 0) acc_c += clock64() - t_a;
     }
   }
-  for (int u = tid; u < T * T; u += POTRF_THREADS) {
-    const int r = u / T, c = u % T;
-    if (c <= r) At[(size_t)r * ld + c] = a[r * LDP + c];
+  POTRF_MARK(2);
+  if (prof_fine && tid == 0) { prof[6] = acc_a; prof[7] = acc_ab; prof[8] = acc_b; prof[9] = acc_c; }
+  for (int u = tid; u < T * T / 2; u += POTRF_THREADS) {
+    const int r = u / (T / 2), c = (u % (T / 2)) * 2;
+    if (c + 1 <= r)
+      *reinterpret_cast<double2*>(At + (size_t)r * ld + c) = make_double2(a[r * LDP + c], a[r * LDP + c + 1]);
+    else if (c <= r)
+      At[(size_t)r * ld + c] = a[r * LDP + c];
   }
   __syncthreads();
+  POTRF_MARK(3);
   // ---------------- inverse of L, in place ----------------
   // level 0: the diagonal 16x16 blocks were inverted during the factorisation
   for (int u = tid; u < (T / PB) * PB * PB; u += POTRF_THREADS) {
@@ -273,22 +347,25 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
   }
   __syncthreads();
   // levels h = 16, 32, 64: for each pair (A = inv at [p,p], C = inv at [p+h,p+h], B at [p+h,p]):
-  //   tmp = B * A  (A lower triangular),  B <- -C * tmp  (C lower triangular); 4x4 register tiles
+  //   tmp = B * A  (A lower triangular),  B <- -C * tmp  (C lower triangular).  A thread owns rows r0..r0+3 and the
+  //   interleaved columns {ct + j*h/4}: lanes run along ct → conflict-free operand loads.
   for (int h = PB; h < T; h *= 2) {
-    const int npairs = T / (2 * h), h4 = h / 4;
+    const int npairs = T / (2 * h), h4 = h / 4, ldt = h + 1;
     for (int u = tid; u < npairs * h4 * h4; u += POTRF_THREADS) {
-      const int pr = u / (h4 * h4), r0 = 4 * ((u / h4) % h4), cc0 = 4 * (u % h4);
+      const int pr = u / (h4 * h4), r0 = 4 * ((u / h4) % h4), ct = u % h4;
       const int p0 = pr * 2 * h;
       double c4[4][4];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) c4[i][j] = 0.0;
-      // (B A)[r][c] = sum_m B[r][m] A[m][c], A[m][c] = 0 for m < c
-      for (int m = cc0; m < h; m++) {
+      // (B A)[r][c] = sum_m B[r][m] A[m][c]; A[m][c] = 0 for m < c, the smallest column of the thread is ct
+      const double* Bp = a + (p0 + h + r0) * LDP + p0;
+      const double* Ap = a + p0 * LDP + p0 + ct;
+      for (int m = ct; m < h; m++) {
         double bv[4], av[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { bv[i] = a[(p0 + h + r0 + i) * LDP + p0 + m]; av[i] = a[(p0 + m) * LDP + p0 + cc0 + i]; }
+        for (int i = 0; i < 4; i++) { bv[i] = Bp[i * LDP + m]; av[i] = Ap[m * LDP + i * h4]; }
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -297,22 +374,24 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) tmp[pr * h * h + (r0 + i) * h + cc0 + j] = c4[i][j];
+        for (int j = 0; j < 4; j++) tmp[pr * h * ldt + (r0 + i) * ldt + ct + j * h4] = c4[i][j];
     }
     __syncthreads();
     for (int u = tid; u < npairs * h4 * h4; u += POTRF_THREADS) {
-      const int pr = u / (h4 * h4), r0 = 4 * ((u / h4) % h4), cc0 = 4 * (u % h4);
+      const int pr = u / (h4 * h4), r0 = 4 * ((u / h4) % h4), ct = u % h4;
       const int p0 = pr * 2 * h;
       double c4[4][4];
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) c4[i][j] = 0.0;
-      // (C tmp)[r][c] = sum_{m <= r} C[r][m] tmp[m][c]
+      // (C tmp)[r][c] = sum_{m <= r} C[r][m] tmp[m][c]   (C[r][m] = 0 above the diagonal)
+      const double* Cp = a + (p0 + h + r0) * LDP + p0 + h;
+      const double* Tp = tmp + pr * h * ldt + ct;
       for (int m = 0; m < r0 + 4; m++) {
         double cv[4], tv[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { cv[i] = a[(p0 + h + r0 + i) * LDP + p0 + h + m]; tv[i] = tmp[pr * h * h + m * h + cc0 + i]; }
+        for (int i = 0; i < 4; i++) { cv[i] = Cp[i * LDP + m]; tv[i] = Tp[m * ldt + i * h4]; }
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -321,14 +400,17 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) a[(p0 + h + r0 + i) * LDP + p0 + cc0 + j] = -c4[i][j];
+        for (int j = 0; j < 4; j++) a[(p0 + h + r0 + i) * LDP + p0 + ct + j * h4] = -c4[i][j];
     }
     __syncthreads();
   }
-  for (int u = tid; u < T * T; u += POTRF_THREADS) {
-    const int r = u / T, c = u % T;
-    linv_k[u] = (c <= r) ? a[r * LDP + c] : 0.0;
+  POTRF_MARK(4);
+  for (int u = tid; u < T * T / 2; u += POTRF_THREADS) {
+    const int r = u / (T / 2), c = (u % (T / 2)) * 2;
+    reinterpret_cast<double2*>(linv_k)[u] =
+        make_double2((c <= r) ? a[r * LDP + c] : 0.0, (c + 1 <= r) ? a[r * LDP + c + 1] : 0.0);
   }
+  POTRF_MARK(5);
 }
 
 // Triangular solves.  One launch per tile column; every CTA recomputes the tiny diagonal product (128x128 mat-vec with
@@ -472,8 +554,8 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
            const FactorStreams* fs) {
   static bool attr = false;
   if (!attr) {
-    CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    CVB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+    CVB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     CVB_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
     attr = true;
   }
@@ -489,6 +571,19 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
   // Independent column groups (the IMU chains of different agents, see TilePlan::h_col_group) run on their own
   // streams: their tile columns are pure latency chains (diagonal tile → panel → tiny update) that do not share tiles.
   const bool la = st2 != nullptr && ev != nullptr;
+  // Development trace (COVINS_B200_FACTOR_TRACE=<csv path>): per-column timeline of the first non-captured call.
+  static bool traced = false;
+  const char* trace_path = getenv("COVINS_B200_FACTOR_TRACE");
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap_status);
+  const bool tr = trace_path && !traced && cap_status == cudaStreamCaptureStatusNone;
+  std::vector<cudaEvent_t> tev;
+  if (tr) {
+    traced = true;
+    tev.resize((size_t)nt * 5 + 1);
+    for (auto& e : tev) cudaEventCreate(&e);
+    cudaEventRecord(tev[(size_t)nt * 5], st);
+  }
   int last_bulk = -1;
   bool forked = false;
   std::vector<char> used(n_gs > 0 ? n_gs : 1, 0);
@@ -514,13 +609,16 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
         }
       forked = false;
     }
-    potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, s>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag);
+    if (tr) cudaEventRecord(tev[(size_t)k * 5 + 0], s);
+    potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, s>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag, nullptr, 0);
     CVB_CHECK_LAUNCH(ctx);
+    if (tr) cudaEventRecord(tev[(size_t)k * 5 + 1], s);
     const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
     if (m > 0) {
-      trsm_kernel<<<m, GEMM_THREADS, kGemmSmem, s>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T,
+      trsm_kernel<<<2 * m, TRSM_THREADS, kTrsmSmem, s>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T,
                                                      plan.d_row_idx + plan.h_col_ptr[k]);
       CVB_CHECK_LAUNCH(ctx);
+      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 2], s);
       const bool la_k = la && grp < 0;
       const int p0 = plan.h_pair_ptr[k], np = plan.h_pair_ptr[k + 1] - p0, na = la_k ? plan.h_pair_split[k] : np;
       if (la_k) {
@@ -528,15 +626,17 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
         if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(s, ev[2 * last_bulk + 1], 0));
       }
       if (na > 0) {
-        syrk_kernel<<<na, GEMM_THREADS, kGemmSmem, s>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
+        syrk_kernel<<<4 * na, SYRK_THREADS, kSyrkSmem, s>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
         CVB_CHECK_LAUNCH(ctx);
       }
+      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 3], s);
       if (la_k && np - na > 0) {
         CVB_CUDA(ctx, cudaStreamWaitEvent(st2, ev[2 * k], 0));
-        syrk_kernel<<<np - na, GEMM_THREADS, kGemmSmem, st2>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0 + na,
-                                                               plan.d_pair_j + p0 + na);
+        syrk_kernel<<<4 * (np - na), SYRK_THREADS, kSyrkSmem, st2>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0 + na,
+                                                                     plan.d_pair_j + p0 + na);
         CVB_CHECK_LAUNCH(ctx);
         CVB_CUDA(ctx, cudaEventRecord(ev[2 * k + 1], st2));
+        if (tr) cudaEventRecord(tev[(size_t)k * 5 + 4], st2);
         last_bulk = k;
       }
     }
@@ -548,6 +648,29 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
         CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->join[g], 0));
       }
   if (la && last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[2 * last_bulk + 1], 0));   // join
+  if (tr) {
+    cudaStreamSynchronize(st);
+    FILE* f = fopen(trace_path, "w");
+    if (f) {
+      fprintf(f, "k,group,n_rows,n_pairs,n_panel_pairs,t_start_us,t_potrf_us,t_trsm_us,t_syrk_a_us,t_bulk_us\n");
+      for (int k = 0; k < nt; k++) {
+        float t[5];
+        for (int e = 0; e < 5; e++) {
+          t[e] = -1.f;
+          if (cudaEventQuery(tev[(size_t)k * 5 + e]) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, tev[(size_t)nt * 5], tev[(size_t)k * 5 + e]) == cudaSuccess) t[e] = ms * 1e3f;
+          }
+        }
+        fprintf(f, "%d,%d,%d,%d,%d,%.1f,%.1f,%.1f,%.1f,%.1f\n", k, plan.h_col_group.empty() ? -1 : plan.h_col_group[k],
+                plan.h_col_ptr[k + 1] - plan.h_col_ptr[k], plan.h_pair_ptr[k + 1] - plan.h_pair_ptr[k],
+                plan.h_pair_split[k], t[0], t[1], t[2], t[3], t[4]);
+      }
+      fclose(f);
+    }
+    for (auto& e : tev) cudaEventDestroy(e);
+    cudaGetLastError();   // queries of never-recorded events leave a sticky-looking error code behind
+  }
   return CVB_OK;
 }
 
@@ -571,6 +694,75 @@ int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* 
 }  // namespace cvb_chol
 
 // ---- test/diagnostic entry: solve A x = b for a host SPD matrix (row-major n x n) with the BA factorisation ----
+// Latency of the diagonal-tile kernel (the serial chain of the tiled factorisation): factors `reps` copies of a synthetic
+// SPD tile back to back; us_per_tile = average launch-to-launch time; phase_cycles[0..5] = clock64 marks of the last
+// launch relative to its start (loaded, factored, L stored, inverted, Linv stored); summed over the 8 block columns:
+// [6] = inside the 16x16 diagonal-block step, [7] = the same incl. the closing barrier, [8] = panel, [9] = trailing update.
+extern "C" int cvb_microbench_potrf(cvb_ctx* ctx, int reps, double* us_per_tile, int64_t* phase_cycles) {
+  if (!ctx || reps < 1 || !us_per_tile) return CVB_ERR_INVALID;
+  using namespace cvb_chol;
+  CVB_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
+  const int nt = 8;
+  std::vector<double> h((size_t)nt * T * T);
+  for (int t = 0; t < nt; t++)
+    for (int r = 0; r < T; r++)
+      for (int c = 0; c < T; c++)
+        h[((size_t)t * T + r) * T + c] = (r == c ? 4.0 + 0.01 * t : 0.0) + 1.0 / (1.0 + (r > c ? r - c : c - r));
+  double *d_a = nullptr, *d_w = nullptr, *d_inv = nullptr;
+  int* d_flag = nullptr;
+  long long* d_prof = nullptr;
+  CVB_CUDA(ctx, cudaMalloc(&d_a, h.size() * 8));
+  CVB_CUDA(ctx, cudaMalloc(&d_w, h.size() * 8));
+  CVB_CUDA(ctx, cudaMalloc(&d_inv, h.size() * 8));
+  CVB_CUDA(ctx, cudaMalloc(&d_flag, 4));
+  CVB_CUDA(ctx, cudaMalloc(&d_prof, 16 * sizeof(long long)));
+  CVB_CUDA(ctx, cudaMemcpy(d_a, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+  CVB_CUDA(ctx, cudaMemset(d_flag, 0, 4));
+  cudaStream_t st = ctx->stream;
+  cudaEvent_t e0, e1;
+  CVB_CUDA(ctx, cudaEventCreate(&e0));
+  CVB_CUDA(ctx, cudaEventCreate(&e1));
+  float ms = 0.f;
+  for (int pass = 0; pass < 2; pass++) {   // pass 0 = warm-up
+    CVB_CUDA(ctx, cudaMemcpyAsync(d_w, d_a, h.size() * 8, cudaMemcpyDeviceToDevice, st));
+    const int n = pass == 0 ? nt : reps;
+    CVB_CUDA(ctx, cudaEventRecord(e0, st));
+    for (int i = 0; i < n; i++) {
+      if (i % nt == 0 && i) CVB_CUDA(ctx, cudaMemcpyAsync(d_w, d_a, h.size() * 8, cudaMemcpyDeviceToDevice, st));
+      // each tile is its own 128 x 128 matrix (ld = T, k = 0)
+      potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, st>>>(d_w + (size_t)(i % nt) * T * T, (size_t)T, 0,
+                                                             d_inv + (size_t)(i % nt) * T * T, d_flag, nullptr, 0);
+      CVB_CHECK_LAUNCH(ctx);
+    }
+    CVB_CUDA(ctx, cudaEventRecord(e1, st));
+    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    CVB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  }
+  *us_per_tile = (double)ms * 1e3 / reps;
+  if (phase_cycles) {
+    long long hp[16], hq[16];
+    for (int fine = 0; fine < 2; fine++) {
+      for (int rep = 0; rep < 4; rep++) {   // the last (warm instruction cache) launch is reported
+        CVB_CUDA(ctx, cudaMemcpyAsync(d_w, d_a, (size_t)T * T * 8, cudaMemcpyDeviceToDevice, st));
+        CVB_CUDA(ctx, cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), st));
+        potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, st>>>(d_w, (size_t)T, 0, d_inv, d_flag, d_prof, fine);
+        CVB_CHECK_LAUNCH(ctx);
+      }
+      CVB_CUDA(ctx, cudaMemcpyAsync(fine ? hq : hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, st));
+      CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    for (int i = 6; i < 10; i++) hp[i] = hq[i];   // marks from the coarse run, in-loop sums from the fine run
+    for (int i = 0; i < 6; i++) phase_cycles[i] = (int64_t)(hp[i] - hp[0]);
+    for (int i = 6; i < 10; i++) phase_cycles[i] = (int64_t)hp[i];
+  }
+  int hflag = 0;
+  CVB_CUDA(ctx, cudaMemcpy(&hflag, d_flag, 4, cudaMemcpyDeviceToHost));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_a); cudaFree(d_w); cudaFree(d_inv); cudaFree(d_flag); cudaFree(d_prof);
+  if (hflag) return cvb_fail(ctx, CVB_ERR_NUMERIC, "microbench tile not positive definite");
+  return CVB_OK;
+}
+
 extern "C" int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, const double* b, double* x,
                                         double* factor_ms) {
   if (!ctx || !A || !b || !x || n <= 0) return CVB_ERR_INVALID;

@@ -47,3 +47,96 @@ extern "C" int cvb_microbench_popc(cvb_ctx* ctx, int iters, double* gpopc_per_s)
   *gpopc_per_s = (double)blocks * 256.0 * (double)iters * 8.0 / (ms * 1e-3) / 1e9;
   return CVB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Single-warp latency probes for the serial part of the diagonal-tile factorisation (cholesky.cu): cycles per
+// dependent operation, measured with clock64 over a chain of N operations.
+//   out[0] dependent DFMA      out[1] 8 independent DFMA chains (cycles per DFMA)   out[2] dependent rsqrt(double)
+//   out[3] dependent SHFL.IDX of a double   out[4] dependent STS.64+LDS.64 round trip (with __syncwarp)
+//   out[5] dependent DMUL      out[6] dependent FFMA (fp32, for scale)     out[7] SM clock estimate (MHz)
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void latency_kernel(double* out, double seed, int n) {
+  __shared__ double sh[32];
+  const int lane = threadIdx.x;
+  long long t0, t1;
+  double x = seed + lane * 1e-3, y = 1.0 - 1e-9;
+  t0 = clock64();
+  for (int i = 0; i < n; i++) x = fma(x, y, 1e-9);
+  t1 = clock64();
+  double r0 = (double)(t1 - t0) / n;
+  double c[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) c[k] = seed + k;
+  t0 = clock64();
+  for (int i = 0; i < n; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = fma(c[k], y, 1e-9);
+  }
+  t1 = clock64();
+  double r1 = (double)(t1 - t0) / (8.0 * n);
+#pragma unroll
+  for (int k = 0; k < 8; k++) x += c[k];
+  double z = 1.0 + x * 1e-30;
+  t0 = clock64();
+  for (int i = 0; i < n; i++) z = rsqrt(z) + 0.5;
+  t1 = clock64();
+  double r2 = (double)(t1 - t0) / n;
+  double s = z;
+  t0 = clock64();
+  for (int i = 0; i < n; i++) s = __shfl_sync(0xffffffffu, s, (lane + 1) & 31);
+  t1 = clock64();
+  double r3 = (double)(t1 - t0) / n;
+  double w = s;
+  t0 = clock64();
+  for (int i = 0; i < n; i++) {
+    sh[lane] = w;
+    __syncwarp();
+    w = sh[(lane + 1) & 31];
+    __syncwarp();
+  }
+  t1 = clock64();
+  double r4 = (double)(t1 - t0) / n;
+  double m = w + 1.0;
+  t0 = clock64();
+  for (int i = 0; i < n; i++) m = m * y;
+  t1 = clock64();
+  double r5 = (double)(t1 - t0) / n;
+  float f = (float)m, g = 0.999999f;
+  t0 = clock64();
+  for (int i = 0; i < n; i++) f = fmaf(f, g, 1e-9f);
+  t1 = clock64();
+  double r6 = (double)(t1 - t0) / n;
+  if (lane == 0) {
+    out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4; out[5] = r5; out[6] = r6;
+    out[8] = x + z + s + w + m + f;   // keep everything live
+  }
+}
+}  // namespace
+
+extern "C" int cvb_microbench_latency(cvb_ctx* ctx, double* out8) {
+  if (!ctx || !out8) return CVB_ERR_INVALID;
+  double* d = (double*)cvb_ws(ctx, WS_MISC, 256);
+  if (!d) return CVB_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  CVB_CUDA(ctx, cudaEventCreate(&e0));
+  CVB_CUDA(ctx, cudaEventCreate(&e1));
+  const int n = 4096;
+  latency_kernel<<<1, 32, 0, ctx->stream>>>(d, 1.0, n);   // warm-up
+  CVB_CHECK_LAUNCH(ctx);
+  CVB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+  latency_kernel<<<1, 32, 0, ctx->stream>>>(d, 1.0, n);
+  CVB_CHECK_LAUNCH(ctx);
+  CVB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+  double h[9];
+  CVB_CUDA(ctx, cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  CVB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  for (int i = 0; i < 7; i++) out8[i] = h[i];
+  const double cycles = n * (h[0] + 8 * h[1] + h[2] + h[3] + h[4] + h[5] + h[6]);
+  out8[7] = cycles / (ms * 1e-3) / 1e6;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return CVB_OK;
+}

@@ -165,6 +165,12 @@ CVB_API int cvb_landmark_match_batch_dev(cvb_ctx* ctx, const uint8_t* d_A, const
  * returns giga-(32-bit popc)/s in *gpopc_per_s. */
 CVB_API int cvb_microbench_popc(cvb_ctx* ctx, int iters, double* gpopc_per_s);
 
+/* Diagnostic: latency of the diagonal-tile kernel of the tiled Cholesky (K8's serial chain), see cholesky.cu.
+ * phase_cycles may be NULL, else int64[10]. */
+CVB_API int cvb_microbench_potrf(cvb_ctx* ctx, int reps, double* us_per_tile, int64_t* phase_cycles);
+/* Diagnostic: single-warp latencies (cycles per dependent DFMA, rsqrt, shuffle, ...), see microbench.cu. out8: double[8]. */
+CVB_API int cvb_microbench_latency(cvb_ctx* ctx, double* out8);
+
 /* diagnostic: solve A x = b (host SPD matrix, row-major n x n) with the BA factorisation (tiled FP64 Cholesky on
  * DMMA); *factor_ms (nullable) receives the device time of the factorisation. */
 CVB_API int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, const double* b, double* x,
