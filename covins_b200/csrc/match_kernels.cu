@@ -20,6 +20,7 @@
 // produce partial lists that are merged in split order by the same rule, so any decomposition is bit-exact.
 #include <float.h>
 #include <limits.h>
+#include <string.h>
 
 #include "cvb_internal.cuh"
 #include "tc_match.cuh"
@@ -694,6 +695,49 @@ int stage_inputs(cvb_ctx* ctx, const void* q, size_t qbytes, const void* t, size
 
 }  // namespace
 
+// Merge of per-shard k-NN lists (map-wide k-NN with the database sharded by keyframe block over G GPUs):
+// one thread per (segment, query) row merges G lists of k by (distance, global trainIdx) — the order a single
+// BFMatcher over the concatenated database produces.  Distances are compared through their int32 bit pattern, which is
+// order-preserving for the non-negative floats of the L2 path and is the value itself for Hamming.
+constexpr int kMaxMergeK = 8;
+__global__ void shard_merge_kernel(const int32_t* __restrict__ idx_all, const int32_t* __restrict__ key_all,
+                                   const int32_t* __restrict__ row_offset, int n_shards, long long n, int k,
+                                   int32_t* __restrict__ out_idx, int32_t* __restrict__ out_key, int32_t empty_key) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  int bk[kMaxMergeK], bi[kMaxMergeK];
+#pragma unroll
+  for (int c = 0; c < kMaxMergeK; c++) {
+    bk[c] = INT_MAX;
+    bi[c] = INT_MAX;
+  }
+  for (int g = 0; g < n_shards; g++) {
+    const int off = row_offset[g];
+    const size_t o = ((size_t)g * n + row) * k;
+    for (int c = 0; c < k; c++) {
+      const int li = idx_all[o + c];
+      if (li < 0) continue;
+      int ck = key_all[o + c], ci = li + off;
+#pragma unroll
+      for (int s = 0; s < kMaxMergeK; s++) {   // insertion keeping (key, idx) ascending
+        const bool lt = ck < bk[s] || (ck == bk[s] && ci < bi[s]);
+        const int tk = bk[s], ti = bi[s];
+        bk[s] = lt ? ck : tk;
+        bi[s] = lt ? ci : ti;
+        ck = lt ? tk : ck;
+        ci = lt ? ti : ci;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxMergeK; c++)
+    if (c < k) {
+      const bool have = bi[c] != INT_MAX;
+      out_idx[row * k + c] = have ? bi[c] : -1;
+      out_key[row * k + c] = have ? bk[c] : empty_key;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------
@@ -764,6 +808,26 @@ int cvb_match_hamming_batch(cvb_ctx* ctx, const uint8_t* q, int nq, const uint8_
   }
   CVB_CUDA(ctx, cudaMemcpyAsync(n_matches, d_nm, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return CVB_OK;
+}
+
+int cvb_knn_merge_shards_dev(cvb_ctx* ctx, const int32_t* d_idx_all, const void* d_dist_all, int dist_is_float,
+                             const int32_t* d_row_offset, int n_shards, int64_t n, int k, int32_t* d_idx_out,
+                             void* d_dist_out, void* stream) {
+  if (!ctx) return CVB_ERR_INVALID;
+  CVB_REQUIRE(ctx, n_shards >= 1 && n >= 0 && k >= 1 && k <= kMaxMergeK, "merge_shards: need 1 <= k <= %d, n_shards >= 1",
+              kMaxMergeK);
+  CVB_REQUIRE(ctx, d_idx_all && d_dist_all && d_row_offset && d_idx_out && d_dist_out, "merge_shards: null buffer");
+  if (n == 0) return CVB_OK;
+  int32_t empty_key = INT_MAX;   // the "no neighbour" distance of the k-NN calls: INT_MAX (Hamming) / FLT_MAX (L2)
+  if (dist_is_float) {
+    const float fmax = FLT_MAX;
+    memcpy(&empty_key, &fmax, 4);
+  }
+  shard_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cvb_stream(ctx, stream)>>>(
+      d_idx_all, (const int32_t*)d_dist_all, d_row_offset, n_shards, (long long)n, k, d_idx_out, (int32_t*)d_dist_out,
+      empty_key);
+  CVB_CHECK_LAUNCH(ctx);
   return CVB_OK;
 }
 

@@ -187,6 +187,55 @@ def match_candidates_l2(ctx: Context, q, t, seg_ptr=None, thr: float = 500.0, ra
     return mt, md, nm
 
 
+def shard_rows(n_rows_total: int, world: int, seg_ptr=None):
+    """Contiguous row ranges of the map-wide database per rank.  With seg_ptr (keyframe boundaries) the cuts fall on
+    keyframe boundaries (sharded by KF block); → int64 [world+1] row offsets."""
+    if seg_ptr is None:
+        return np.linspace(0, n_rows_total, world + 1).astype(np.int64)
+    seg = np.asarray(seg_ptr, np.int64)
+    target = np.linspace(0, n_rows_total, world + 1)
+    cut = seg[np.searchsorted(seg, target, side="left").clip(0, len(seg) - 1)]
+    cut[0], cut[-1] = 0, n_rows_total
+    return np.maximum.accumulate(cut)
+
+
+def knn_merge_shards(ctx: Context, idx_all, dist_all, row_offset, k: int):
+    """idx_all/dist_all: torch [G, n, k] (shard-local trainIdx; int32 Hamming or float32 L2 distances), row_offset
+    torch int32 [G] → merged (idx [n, k] global trainIdx, dist [n, k]), cvb_knn_merge_shards_dev."""
+    import torch
+    G, n = idx_all.shape[0], idx_all.shape[1]
+    idx_all = idx_all.contiguous(); dist_all = dist_all.contiguous()
+    out_i = torch.empty((n, k), dtype=torch.int32, device=idx_all.device)
+    out_d = torch.empty((n, k), dtype=dist_all.dtype, device=idx_all.device)
+    ctx.check(lib().cvb_knn_merge_shards_dev(ctx.handle, _ptr(idx_all), _ptr(dist_all),
+                                             1 if dist_all.dtype == torch.float32 else 0, _ptr(row_offset), G, n, k,
+                                             _ptr(out_i), _ptr(out_d), _torch_stream()))
+    return out_i, out_d
+
+
+def knn_match_sharded(ctx: Context, q, t_local, row_offset: int, k: int = 2, metric: str = "hamming", group=None):
+    """Map-wide k-NN, database sharded over the ranks of `group` (torch.distributed, NCCL): local top-k on this rank's
+    rows, ONE all-gather of the (idx, dist) lists (G*k*nq*8 B) and the shard offsets, local merge.
+    q replicated on every rank (torch u8 on the device); t_local = this rank's rows; row_offset = its first global row.
+    Every rank returns the same (idx [nq,k] global trainIdx, dist [nq,k])."""
+    import torch
+    import torch.distributed as dist
+    if metric == "hamming":
+        li, ld = knn_match_hamming(ctx, q, t_local, None, k)
+    else:
+        li, ld = knn_match_l2(ctx, q, t_local, None, k)
+    li, ld = li[0].contiguous(), ld[0].contiguous()          # one segment = the whole shard
+    world = dist.get_world_size(group)
+    idx_all = torch.empty((world,) + tuple(li.shape), dtype=li.dtype, device=li.device)
+    dist_all = torch.empty((world,) + tuple(ld.shape), dtype=ld.dtype, device=ld.device)
+    off = torch.tensor([row_offset], dtype=torch.int32, device=li.device)
+    off_all = torch.empty((world,), dtype=torch.int32, device=li.device)
+    dist.all_gather_into_tensor(idx_all, li, group=group)
+    dist.all_gather_into_tensor(dist_all, ld, group=group)
+    dist.all_gather_into_tensor(off_all, off, group=group)
+    return knn_merge_shards(ctx, idx_all, dist_all, off_all, k)
+
+
 def quantize_u8(ctx: Context, x):
     """torch f32 CUDA tensor → (u8 tensor, bad flag tensor): the exact HBM-resident SIFT layout."""
     import torch

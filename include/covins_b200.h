@@ -130,6 +130,18 @@ CVB_API int cvb_knn_l2_u8_batch_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, co
 CVB_API int cvb_match_l2_batch(cvb_ctx* ctx, const float* q, int nq, const float* t, const int32_t* seg_ptr,
                                int n_seg, int dim, float thr, float ratio, int32_t* match_train,
                                float* match_dist, int32_t* n_matches);
+/*
+ * Map-wide k-NN with the database sharded by keyframe block over G GPUs (SURVEY §8e "KNN (map-wide)"): every rank
+ * runs cvb_knn_hamming_batch_dev / cvb_knn_l2_u8_batch_dev on its shard, the per-shard lists are all-gathered
+ * (idx_all / dist_all: [n_shards][n][k], n = n_seg*nq rows; shard-local trainIdx) and this call merges them by
+ * (distance, global trainIdx = local + row_offset[shard]) — exactly the list one BFMatcher::knnMatch over the
+ * concatenated database returns (ties → lower trainIdx first).  dist_is_float: 0 = int32 Hamming, 1 = float L2.
+ * Missing neighbours: idx -1, distance INT_MAX / FLT_MAX.  1 <= k <= 8.
+ */
+CVB_API int cvb_knn_merge_shards_dev(cvb_ctx* ctx, const int32_t* d_idx_all, const void* d_dist_all, int dist_is_float,
+                                     const int32_t* d_row_offset, int n_shards, int64_t n, int k, int32_t* d_idx_out,
+                                     void* d_dist_out, void* stream);
+
 /* f32 [rows][dim] (device) → u8 [rows][dim] (device); *d_bad (int32, device) is set to 1 if any value is
  * not an integer in [0,255]. */
 CVB_API int cvb_quantize_u8_dev(cvb_ctx* ctx, const float* d_src, int64_t n, uint8_t* d_dst, int32_t* d_bad,

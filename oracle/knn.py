@@ -104,3 +104,20 @@ def landmark_match_batch(A, skipA, B, skipB, seg_ptr, thr=50.0, num_best=4, thre
                                    _p(seg_ptr, C.c_int32), ns, C.c_float(thr), num_best, _p(oA, C.c_int32),
                                    _p(oB, C.c_int32), _p(oD, C.c_float), _p(n, C.c_int32), threads)
     return oA, oB, oD, n
+
+
+def merge_shards(idx_all, dist_all, row_offset, k):
+    """CPU restatement of the map-wide sharded k-NN merge: per-shard lists [G, n, k] with shard-local
+    trainIdx → the k smallest by (distance, global trainIdx).  Missing entries have idx -1."""
+    idx_all = np.asarray(idx_all); dist_all = np.asarray(dist_all)
+    G, n, kk = idx_all.shape
+    gi = np.where(idx_all >= 0, idx_all.astype(np.int64) + np.asarray(row_offset, np.int64)[:, None, None], -1)
+    gi = gi.transpose(1, 0, 2).reshape(n, G * kk); gd = dist_all.transpose(1, 0, 2).reshape(n, G * kk)
+    big = np.iinfo(np.int64).max
+    key_i = np.where(gi >= 0, gi, big)
+    key_d = np.where(gi >= 0, gd.astype(np.float64), np.inf)
+    order = np.lexsort((key_i, key_d), axis=1)[:, :k]
+    oi = np.take_along_axis(gi, order, 1); od = np.take_along_axis(gd, order, 1)
+    empty = np.iinfo(np.int32).max if np.issubdtype(dist_all.dtype, np.integer) else np.finfo(np.float32).max
+    od = np.where(oi >= 0, od, empty).astype(dist_all.dtype)
+    return oi.astype(np.int32), od

@@ -225,3 +225,35 @@ def test_descriptor_database_matches_batch_call_and_oracle(ctx):
     nm2, *rest = db.match_hamming(desc[0], 64.0, 0.95)
     assert int(nm2.sum()) == len(rest[0]) > 3
     db.close()
+
+
+@pytest.mark.parametrize("metric", ["hamming", "l2"])
+def test_mapwide_sharded_knn_merge_equals_single_call(ctx, metric):
+    """SURVEY §8e map-wide k-NN: per-shard CUDA top-k (3 shards incl. one with fewer than k rows and an empty one) →
+    cvb_knn_merge_shards_dev == the single-call k-NN over the whole database, bit-exact, ties across shards included."""
+    import torch
+    rng = np.random.default_rng(33)
+    dim = 32 if metric == "hamming" else 128
+    base = rng.integers(0, 256, (50, dim), dtype=np.uint8)
+    t = base[rng.integers(0, 50, 5000)].copy()
+    q = base[:64].copy()
+    cuts = [0, 2, 2, 2600, 5000]                       # shard sizes 2, 0, 2598, 2400
+    k = 3
+    dev = torch.device("cuda", 0)
+    tq, tt = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+    knn = M.knn_match_hamming if metric == "hamming" else M.knn_match_l2
+    ri, rd = knn(ctx, tq, tt, None, k)
+    li_all, ld_all = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        if b > a:
+            li, ld = knn(ctx, tq, tt[a:b].contiguous(), None, k)
+            li_all.append(li[0]); ld_all.append(ld[0])
+        else:                                          # an empty shard contributes "no neighbour" lists
+            li_all.append(torch.full((len(q), k), -1, dtype=torch.int32, device=dev))
+            ld_all.append(torch.zeros((len(q), k), dtype=ri.dtype if False else rd.dtype, device=dev))
+    off = torch.tensor(cuts[:-1], dtype=torch.int32, device=dev)
+    mi, md = M.knn_merge_shards(ctx, torch.stack(li_all), torch.stack(ld_all), off, k)
+    torch.cuda.synchronize()
+    assert torch.equal(mi, ri[0]) and torch.equal(md, rd[0])
+    oi, od = ora.merge_shards(torch.stack(li_all).cpu().numpy(), torch.stack(ld_all).cpu().numpy(), cuts[:-1], k)
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(md.cpu().numpy(), od)

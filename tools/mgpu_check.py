@@ -33,6 +33,35 @@ for name, vo, iters in (("small", False, 6), ("small", True, 6), ("C1", False, 4
         ok &= good
         print(f"{name} visual_only={vo} world={world}: iterations {n}, rel err pose/sb/lm {e}, steps equal {same_steps}, "
               f"cost {r['final_cost']:.8e} vs {ref['final_cost']:.8e} -> {'OK' if good else 'MISMATCH'}", flush=True)
+# ---- map-wide k-NN, database sharded by keyframe block, one all-gather + merge ----
+from covins_b200 import matching as M
+dev = torch.device("cuda", local)
+for metric, dim, n_kf, nf, nq in (("hamming", 32, 2000, 1000, 1000), ("l2", 128, 4000, 300, 300)):
+    g = torch.Generator(device=dev).manual_seed(7)           # same database on every rank, each keeps its slice
+    t = torch.randint(0, 256, (n_kf * nf, dim), dtype=torch.uint8, device=dev, generator=g)
+    t[nf * 5:nf * 6] = t[:nf]                                 # duplicates → ties across rows
+    t[-nf:] = t[:nf]                                          # ... and across shards
+    q = t[:nq].clone()
+    seg = np.arange(n_kf + 1, dtype=np.int64) * nf
+    cuts = M.shard_rows(n_kf * nf, world, seg)
+    lo, hi = int(cuts[rank]), int(cuts[rank + 1])
+    knn = M.knn_match_hamming if metric == "hamming" else M.knn_match_l2
+    for _ in range(2):
+        mi, md = M.knn_match_sharded(ctx, q, t[lo:hi].contiguous(), lo, 2, metric)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        mi, md = M.knn_match_sharded(ctx, q, t[lo:hi], lo, 2, metric)
+    e1.record(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / 5], device=dev); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ri, rd = knn(ctx, q, t, None, 2)
+    good = bool(torch.equal(mi, ri[0]) and torch.equal(md, rd[0]))
+    flag = torch.tensor([int(good)], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        ok &= bool(flag.item())
+        print(f"map-wide sharded k-NN {metric}: {nq} queries vs {n_kf*nf} rows over {world} GPUs: {ms.item():.3f} ms per query block "
+              f"({nq*n_kf*nf/ms.item()/1e6:.0f} Gpairs/s incl. all-gather + merge) -> {'OK (bit-identical to the single-GPU k-NN)' if flag.item() else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
