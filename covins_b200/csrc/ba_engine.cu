@@ -1568,7 +1568,7 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
     } else if (E.n_solve_calls == 1) {
       cudaGraph_t g = nullptr;
       ENG_CUDA(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
-      rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st);
+      rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st, &E.fs);
       cudaError_t ce = cudaStreamEndCapture(E.st, &g);
       if (rc) return rc;
       if (ce != cudaSuccess) return cvb_fail(E.ctx, CVB_ERR_CUDA, "graph capture of the solve failed: %s", cudaGetErrorString(ce));
@@ -1576,7 +1576,7 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
       cudaGraphDestroy(g);
       ENG_CUDA(cudaGraphLaunch(E.g_solve, E.st));
     } else {
-      if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st))) return rc;
+      if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st, &E.fs))) return rc;
     }
     E.n_solve_calls++;
     if (E.L_in > 0) {

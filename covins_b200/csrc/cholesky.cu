@@ -676,18 +676,59 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
 
 // solves L L^T x = b; b is destroyed, tmp is scratch (n_pad), result in x
 int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
-          const TilePlan& plan, cudaStream_t st) {
+          const TilePlan& plan, cudaStream_t st, const FactorStreams* fs) {
   const int nt = n_pad / T;
+  // The leading tile columns that belong to independent column groups (IMU chains, TilePlan::h_col_group) touch only
+  // their own chain's rows of b / y, so the chains' substitution steps — pure launch-latency chains — run concurrently
+  // on the group streams, forward before and backward after the sequential part.
+  const int n_gs = (fs && !plan.h_col_group.empty()) ? fs->n_group : 0;
+  int n_grouped = 0;
+  while (n_gs > 0 && n_grouped < nt && plan.h_col_group[n_grouped] >= 0) n_grouped++;
+  for (int k = n_grouped; k < nt; k++)
+    if (n_gs > 0 && plan.h_col_group[k] >= 0) { n_grouped = 0; break; }   // groups must be a prefix; else run sequentially
+  std::vector<char> used(n_gs > 0 ? n_gs : 1, 0);
+  auto fork = [&]() -> int {
+    CVB_CUDA(ctx, cudaEventRecord(fs->fork, st));
+    std::fill(used.begin(), used.end(), 0);
+    return CVB_OK;
+  };
+  auto stream_of = [&](int k, cudaStream_t* s) -> int {
+    const int g = plan.h_col_group[k] % n_gs;
+    if (!used[g]) {
+      CVB_CUDA(ctx, cudaStreamWaitEvent(fs->group[g], fs->fork, 0));
+      used[g] = 1;
+    }
+    *s = fs->group[g];
+    return CVB_OK;
+  };
+  auto join = [&]() -> int {
+    for (int g = 0; g < n_gs; g++)
+      if (used[g]) {
+        CVB_CUDA(ctx, cudaEventRecord(fs->join[g], fs->group[g]));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->join[g], 0));
+      }
+    return CVB_OK;
+  };
+  int rc;
+  if (n_grouped > 0 && (rc = fork())) return rc;
   for (int k = 0; k < nt; k++) {
+    cudaStream_t s = st;
+    if (k < n_grouped && (rc = stream_of(k, &s))) return rc;
+    if (k == n_grouped && n_grouped > 0 && (rc = join())) return rc;
     const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
-    fwd_kernel<<<1 + m, SOLVE_THREADS, 0, st>>>(L, (size_t)n_pad, k, linv, b, tmp, plan.d_row_idx + plan.h_col_ptr[k]);
+    fwd_kernel<<<1 + m, SOLVE_THREADS, 0, s>>>(L, (size_t)n_pad, k, linv, b, tmp, plan.d_row_idx + plan.h_col_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
+  if (n_grouped == nt && n_grouped > 0 && (rc = join())) return rc;
   for (int k = nt - 1; k >= 0; k--) {
+    cudaStream_t s = st;
+    if (k == n_grouped - 1 && (rc = fork())) return rc;
+    if (k < n_grouped && (rc = stream_of(k, &s))) return rc;
     const int m = plan.h_rowc_ptr[k + 1] - plan.h_rowc_ptr[k];
-    bwd_kernel<<<1 + m, SOLVE_THREADS, 0, st>>>(L, (size_t)n_pad, k, linv, tmp, x, plan.d_rowc_idx + plan.h_rowc_ptr[k]);
+    bwd_kernel<<<1 + m, SOLVE_THREADS, 0, s>>>(L, (size_t)n_pad, k, linv, tmp, x, plan.d_rowc_idx + plan.h_rowc_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
+  if (n_grouped > 0 && (rc = join())) return rc;
   return CVB_OK;
 }
 

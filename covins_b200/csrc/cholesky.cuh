@@ -36,6 +36,6 @@ struct FactorStreams {
 int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
            const FactorStreams* fs);
 int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
-          const TilePlan& plan, cudaStream_t st);
+          const TilePlan& plan, cudaStream_t st, const FactorStreams* fs = nullptr);
 
 }  // namespace cvb_chol
