@@ -20,7 +20,11 @@
 // produce partial lists that are merged in split order by the same rule, so any decomposition is bit-exact.
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "cvb_internal.cuh"
 #include "tc_match.cuh"
@@ -629,72 +633,6 @@ int check_segs(cvb_ctx* ctx, const int32_t* h_seg_ptr, int n_seg, int* max_len, 
   return CVB_OK;
 }
 
-// Common implementation of knn / fused-match for both metrics (device pointers).
-template <class M, int QPT_BIG>
-int knn_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, const int32_t* d_seg_ptr,
-            const int32_t* h_seg_ptr, int n_seg, int k, int32_t* d_idx, void* d_dist, bool filter, float thr,
-            float ratio, int32_t* d_match_train, float* d_match_dist, int32_t* d_n_matches, cudaStream_t st) {
-  CVB_REQUIRE(ctx, ctx != nullptr, "null ctx");
-  CVB_REQUIRE(ctx, nq >= 0 && k >= 1 && k <= 4, "bad nq/k");
-  int max_len = 0;
-  int64_t total = 0;
-  int rc = check_segs(ctx, h_seg_ptr, n_seg, &max_len, &total);
-  if (rc) return rc;
-  CVB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_t) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_q) & 15) == 0,
-              "descriptor arrays must be 16-byte aligned");
-  if (filter) {
-    CVB_REQUIRE(ctx, k == 2, "fused filter needs k == 2");
-    CVB_CUDA(ctx, cudaMemsetAsync(d_n_matches, 0, sizeof(int32_t) * n_seg, st));
-  }
-  if (nq == 0) return CVB_OK;
-  if (cvb_tc::profitable(ctx, nq, n_seg, (long)total, max_len)) {   // tensor-core formulation (tc_match.cu), same results
-    cvb_tc::TcParams tp{};
-    tp.q = d_q; tp.nq = nq; tp.t = d_t; tp.seg_ptr = d_seg_ptr; tp.n_seg = n_seg;
-    tp.out_idx = d_idx; tp.out_dist = d_dist; tp.filter = filter ? 1 : 0; tp.thr = thr; tp.ratio = ratio;
-    tp.match_train = d_match_train; tp.match_dist = d_match_dist; tp.n_matches = d_n_matches;
-    return cvb_tc::launch(ctx, tp, M::kIsL2 ? 1 : 0, k, st);
-  }
-  const Plan pl = make_plan<M>(nq, n_seg, max_len, ctx->sm_count, QPT_BIG, true);
-  ScanParams sp{};
-  sp.q = d_q; sp.nq = nq; sp.t = d_t; sp.seg_ptr = d_seg_ptr; sp.n_seg = n_seg;
-  sp.splits = pl.splits; sp.chunk = pl.chunk;
-  sp.filter = filter ? 1 : 0; sp.thr = thr; sp.ratio = ratio;
-  sp.match_train = d_match_train; sp.match_dist = d_match_dist; sp.n_matches = d_n_matches;
-  if (pl.splits == 1) {
-    sp.out_idx = d_idx; sp.out_dist = d_dist;
-    return dispatch_scan<M, QPT_BIG, MODE_BF>(ctx, sp, pl, k, st);
-  }
-  const size_t pn = (size_t)n_seg * pl.splits * nq * k;
-  int32_t* part_i = (int32_t*)cvb_ws(ctx, WS_PART_I, pn * sizeof(int32_t));
-  int32_t* part_d = (int32_t*)cvb_ws(ctx, WS_PART_D, pn * sizeof(int32_t));
-  if (!part_i || !part_d) return CVB_ERR_CUDA;
-  sp.out_idx = part_i; sp.out_dist = part_d;
-  rc = dispatch_scan<M, QPT_BIG, MODE_BF>(ctx, sp, pl, k, st);
-  if (rc) return rc;
-  switch (k) {
-    case 1: return launch_merge<M, 1>(ctx, sp, pl, d_idx, d_dist, st);
-    case 2: return launch_merge<M, 2>(ctx, sp, pl, d_idx, d_dist, st);
-    case 3: return launch_merge<M, 3>(ctx, sp, pl, d_idx, d_dist, st);
-    default: return launch_merge<M, 4>(ctx, sp, pl, d_idx, d_dist, st);
-  }
-}
-
-// Host-buffer staging helper: copies q, t, seg_ptr to device workspaces.
-int stage_inputs(cvb_ctx* ctx, const void* q, size_t qbytes, const void* t, size_t tbytes, const int32_t* seg_ptr,
-                 int n_seg, void** d_q, void** d_t, int32_t** d_seg) {
-  *d_q = cvb_ws(ctx, WS_Q, qbytes);
-  *d_t = cvb_ws(ctx, WS_T, tbytes);
-  *d_seg = (int32_t*)cvb_ws(ctx, WS_SEG, sizeof(int32_t) * (n_seg + 1));
-  if (!*d_q || !*d_t || !*d_seg) return CVB_ERR_CUDA;
-  if (qbytes) CVB_CUDA(ctx, cudaMemcpyAsync(*d_q, q, qbytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (tbytes) CVB_CUDA(ctx, cudaMemcpyAsync(*d_t, t, tbytes, cudaMemcpyHostToDevice, ctx->stream));
-  CVB_CUDA(ctx, cudaMemcpyAsync(*d_seg, seg_ptr, sizeof(int32_t) * (n_seg + 1), cudaMemcpyHostToDevice,
-                                ctx->stream));
-  return CVB_OK;
-}
-
-}  // namespace
-
 // Merge of per-shard k-NN lists (map-wide k-NN with the database sharded by keyframe block over G GPUs):
 // one thread per (segment, query) row merges G lists of k by (distance, global trainIdx) — the order a single
 // BFMatcher over the concatenated database produces.  Distances are compared through their int32 bit pattern, which is
@@ -737,6 +675,111 @@ __global__ void shard_merge_kernel(const int32_t* __restrict__ idx_all, const in
       out_key[row * k + c] = have ? bk[c] : empty_key;
     }
 }
+
+// Common implementation of knn / fused-match for both metrics (device pointers).
+template <class M, int QPT_BIG>
+int knn_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, const int32_t* d_seg_ptr,
+            const int32_t* h_seg_ptr, int n_seg, int k, int32_t* d_idx, void* d_dist, bool filter, float thr,
+            float ratio, int32_t* d_match_train, float* d_match_dist, int32_t* d_n_matches, cudaStream_t st) {
+  CVB_REQUIRE(ctx, ctx != nullptr, "null ctx");
+  CVB_REQUIRE(ctx, nq >= 0 && k >= 1 && k <= 4, "bad nq/k");
+  int max_len = 0;
+  int64_t total = 0;
+  int rc = check_segs(ctx, h_seg_ptr, n_seg, &max_len, &total);
+  if (rc) return rc;
+  CVB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_t) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_q) & 15) == 0,
+              "descriptor arrays must be 16-byte aligned");
+  if (filter) {
+    CVB_REQUIRE(ctx, k == 2, "fused filter needs k == 2");
+    CVB_CUDA(ctx, cudaMemsetAsync(d_n_matches, 0, sizeof(int32_t) * n_seg, st));
+  }
+  if (nq == 0) return CVB_OK;
+  if (cvb_tc::profitable(ctx, nq, n_seg, (long)total, max_len)) {   // tensor-core formulation (tc_match.cu), same results
+    cvb_tc::TcParams tp{};
+    tp.q = d_q; tp.nq = nq; tp.t = d_t; tp.seg_ptr = d_seg_ptr; tp.n_seg = n_seg;
+    tp.out_idx = d_idx; tp.out_dist = d_dist; tp.filter = filter ? 1 : 0; tp.thr = thr; tp.ratio = ratio;
+    tp.match_train = d_match_train; tp.match_dist = d_match_dist; tp.n_matches = d_n_matches;
+    return cvb_tc::launch(ctx, tp, M::kIsL2 ? 1 : 0, k, st);
+  }
+  {
+    // One very long segment (map-wide k-NN): too few segments to spread over the SMs as they are → cut it into uniform
+    // chunks, run the tensor-core kernel on the chunks and merge the chunk lists exactly (the same (distance, index)
+    // merge that combines GPU shards).
+    const char* e = getenv("COVINS_B200_MATCH_KERNEL");
+    const int nqb = (nq + 127) / 128;
+    const int parts = ctx->sm_count / nqb > 0 ? ctx->sm_count / nqb : 1;
+    if (!filter && n_seg == 1 && !(e && !strcmp(e, "popc")) && (long)nq * total >= (1L << 26) &&
+        total >= (int64_t)parts * 4 * 1024) {
+      int n_ps = parts * 4;
+      const int64_t chunk = ((total + n_ps - 1) / n_ps + 127) / 128 * 128;
+      n_ps = (int)((total + chunk - 1) / chunk);
+      std::vector<int32_t> h_ps((size_t)n_ps + 1), h_off((size_t)n_ps);
+      for (int c = 0; c <= n_ps; c++) h_ps[c] = (int32_t)std::min<int64_t>((int64_t)c * chunk, total);
+      for (int c = 0; c < n_ps; c++) h_off[c] = (int32_t)((int64_t)c * chunk);
+      int32_t* d_ps = (int32_t*)cvb_ws(ctx, WS_TMP0, sizeof(int32_t) * (n_ps + 1));
+      int32_t* d_off = (int32_t*)cvb_ws(ctx, WS_TMP1, sizeof(int32_t) * n_ps);
+      const size_t pn = (size_t)n_ps * nq * k;
+      int32_t* part_i = (int32_t*)cvb_ws(ctx, WS_PART_I, pn * sizeof(int32_t));
+      int32_t* part_d = (int32_t*)cvb_ws(ctx, WS_PART_D, pn * sizeof(int32_t));
+      if (!d_ps || !d_off || !part_i || !part_d) return CVB_ERR_CUDA;
+      CVB_CUDA(ctx, cudaMemcpyAsync(d_ps, h_ps.data(), sizeof(int32_t) * (n_ps + 1), cudaMemcpyHostToDevice, st));
+      CVB_CUDA(ctx, cudaMemcpyAsync(d_off, h_off.data(), sizeof(int32_t) * n_ps, cudaMemcpyHostToDevice, st));
+      CVB_CUDA(ctx, cudaStreamSynchronize(st));   // the host vectors go out of scope
+      cvb_tc::TcParams tp{};
+      tp.q = d_q; tp.nq = nq; tp.t = d_t; tp.seg_ptr = d_ps; tp.n_seg = n_ps;
+      tp.out_idx = part_i; tp.out_dist = part_d; tp.filter = 0;
+      if ((rc = cvb_tc::launch(ctx, tp, M::kIsL2 ? 1 : 0, k, st))) return rc;
+      int32_t empty_key = INT_MAX;
+      if (M::kIsL2) {
+        const float fmax = FLT_MAX;
+        memcpy(&empty_key, &fmax, 4);
+      }
+      shard_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(part_i, part_d, d_off, n_ps, (long long)nq, k, d_idx,
+                                                                      (int32_t*)d_dist, empty_key);
+      CVB_CHECK_LAUNCH(ctx);
+      return CVB_OK;
+    }
+  }
+  const Plan pl = make_plan<M>(nq, n_seg, max_len, ctx->sm_count, QPT_BIG, true);
+  ScanParams sp{};
+  sp.q = d_q; sp.nq = nq; sp.t = d_t; sp.seg_ptr = d_seg_ptr; sp.n_seg = n_seg;
+  sp.splits = pl.splits; sp.chunk = pl.chunk;
+  sp.filter = filter ? 1 : 0; sp.thr = thr; sp.ratio = ratio;
+  sp.match_train = d_match_train; sp.match_dist = d_match_dist; sp.n_matches = d_n_matches;
+  if (pl.splits == 1) {
+    sp.out_idx = d_idx; sp.out_dist = d_dist;
+    return dispatch_scan<M, QPT_BIG, MODE_BF>(ctx, sp, pl, k, st);
+  }
+  const size_t pn = (size_t)n_seg * pl.splits * nq * k;
+  int32_t* part_i = (int32_t*)cvb_ws(ctx, WS_PART_I, pn * sizeof(int32_t));
+  int32_t* part_d = (int32_t*)cvb_ws(ctx, WS_PART_D, pn * sizeof(int32_t));
+  if (!part_i || !part_d) return CVB_ERR_CUDA;
+  sp.out_idx = part_i; sp.out_dist = part_d;
+  rc = dispatch_scan<M, QPT_BIG, MODE_BF>(ctx, sp, pl, k, st);
+  if (rc) return rc;
+  switch (k) {
+    case 1: return launch_merge<M, 1>(ctx, sp, pl, d_idx, d_dist, st);
+    case 2: return launch_merge<M, 2>(ctx, sp, pl, d_idx, d_dist, st);
+    case 3: return launch_merge<M, 3>(ctx, sp, pl, d_idx, d_dist, st);
+    default: return launch_merge<M, 4>(ctx, sp, pl, d_idx, d_dist, st);
+  }
+}
+
+// Host-buffer staging helper: copies q, t, seg_ptr to device workspaces.
+int stage_inputs(cvb_ctx* ctx, const void* q, size_t qbytes, const void* t, size_t tbytes, const int32_t* seg_ptr,
+                 int n_seg, void** d_q, void** d_t, int32_t** d_seg) {
+  *d_q = cvb_ws(ctx, WS_Q, qbytes);
+  *d_t = cvb_ws(ctx, WS_T, tbytes);
+  *d_seg = (int32_t*)cvb_ws(ctx, WS_SEG, sizeof(int32_t) * (n_seg + 1));
+  if (!*d_q || !*d_t || !*d_seg) return CVB_ERR_CUDA;
+  if (qbytes) CVB_CUDA(ctx, cudaMemcpyAsync(*d_q, q, qbytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (tbytes) CVB_CUDA(ctx, cudaMemcpyAsync(*d_t, t, tbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CVB_CUDA(ctx, cudaMemcpyAsync(*d_seg, seg_ptr, sizeof(int32_t) * (n_seg + 1), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  return CVB_OK;
+}
+
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // C-ABI

@@ -111,3 +111,29 @@ def test_tc_equals_popc_kernel_at_full_size(ctx, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(i0, i1) and torch.equal(d0, d1)
     assert all(torch.equal(a, b) for a, b in zip(m0, m1))
+
+
+@pytest.mark.parametrize("metric,k", [("hamming", 2), ("hamming", 4), ("l2", 2), ("l2", 3)])
+def test_tc_single_long_segment_chunked_equals_scalar(ctx, monkeypatch, metric, k):
+    """Map-wide k-NN (one segment of 200k rows): the segment is cut into chunks for the tensor-core kernel and the chunk
+    lists are merged by (distance, index); must be bit-identical to the scalar split/merge path, duplicates included."""
+    import torch
+    rng = np.random.default_rng(77)
+    dim = 32 if metric == "hamming" else 128
+    base = rng.integers(0, 256, (3000, dim), dtype=np.uint8)
+    t = base[rng.integers(0, 3000, 200_003)].copy()          # many exact duplicates → ties across chunk boundaries
+    noise = rng.random(t.shape) < 0.01
+    t[noise] ^= rng.integers(1, 256, int(noise.sum()), dtype=np.uint8)
+    q = base[:700].copy()
+    dev = torch.device("cuda", 0)
+    tq, tt = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+    knn = M.knn_match_hamming if metric == "hamming" else M.knn_match_l2
+    monkeypatch.delenv("COVINS_B200_MATCH_KERNEL", raising=False)
+    i1, d1 = knn(ctx, tq, tt, None, k)
+    monkeypatch.setenv("COVINS_B200_MATCH_KERNEL", "popc")
+    i0, d0 = knn(ctx, tq, tt, None, k)
+    torch.cuda.synchronize()
+    assert torch.equal(i1, i0) and torch.equal(d1, d0)
+    if metric == "hamming":
+        ri, rd = ora.knn_hamming(q[:64], t, k)
+        assert np.array_equal(i1[0, :64].cpu().numpy(), ri) and np.array_equal(d1[0, :64].cpu().numpy(), rd)
