@@ -170,7 +170,7 @@ constexpr int PB = 16;
 constexpr int POTRF_THREADS = 512;
 constexpr int POTRF_WORKERS = POTRF_THREADS - 32;   // warp 15 inverts the diagonal blocks
 constexpr int TMP_DOUBLES = 64 * 65;
-constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)TMP_DOUBLES + (size_t)(T / PB) * PB * PB) * sizeof(double);
+constexpr size_t kPotrfSmem = ((size_t)T * LDP + (size_t)TMP_DOUBLES + (size_t)(T / PB) * PB * PB + 5 * PB) * sizeof(double);
 
 #define POTRF_MARK(i)                                     \
   do {                                                    \
@@ -184,9 +184,8 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
   double* a = smem_d;                     // [T][LDP]
   double* tmp = smem_d + T * LDP;         // scratch of the inverse phase
   double* binv = tmp + TMP_DOUBLES;       // [8][16][16] inverses of the diagonal 16x16 blocks of L
-  __shared__ __align__(16) double colbuf[2][PB];
-  __shared__ double pivbuf[2];
-  __shared__ double rdbuf[PB];            // reciprocal diagonal of the current diagonal block
+  double* colbuf = binv + (T / PB) * PB * PB;   // [2][2*PB] pivot-column exchange (second half: dummy slots)
+  double* rdbuf = colbuf + 4 * PB;              // [PB] reciprocal diagonal of the current diagonal block
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* At = S + (size_t)k * T * ld + (size_t)k * T;
   POTRF_MARK(0);
@@ -213,7 +212,8 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
     const int c0 = jb * PB, nbelow = T - c0 - PB;
     if (prof_fine && tid == 0) t_a = clock64();
     if (warp == 0) {
-      // (a) the 16x16 diagonal block, treated as a full symmetric matrix (the upper half is mirrored in on load)
+      // (a) the 16x16 diagonal block.  Branch-free pivot loop: every lane stores one value per step (lanes of the other
+      // column half into a dummy slot), readers mask by row index; a non-positive pivot only sets a flag bit.
       const int r = lane >> 1, hf = lane & 1;
       double v[8];
 #pragma unroll
@@ -221,29 +221,35 @@ __global__ void __launch_bounds__(POTRF_THREADS, 1) potrf_inv_kernel(double* __r
         const int cc = hf * 8 + c;
         v[c] = (cc <= r) ? a[(c0 + r) * LDP + c0 + cc] : a[(c0 + cc) * LDP + c0 + r];
       }
+      int bad = 0;
 #pragma unroll
       for (int j = 0; j < PB; j++) {
         const int jh = j >> 3, jc = j & 7;
-        if (hf == jh) {
-          colbuf[j & 1][r] = (r > j) ? v[jc] : 0.0;    // unscaled column j below the pivot; zeros at and above it
-          if (r == j) pivbuf[j & 1] = v[jc];
-        }
+        double* cbuf = colbuf + (j & 1) * 2 * PB;
+        cbuf[(hf == jh) ? r : PB + r] = v[jc];          // column j (unscaled, incl. the pivot at row j); dummy half
         __syncwarp();
-        double piv = pivbuf[j & 1];
-        const double own = colbuf[j & 1][r];
-        const double2* cb = reinterpret_cast<const double2*>(&colbuf[j & 1][hf * 8]);
-        const double2 l01 = cb[0], l23 = cb[1], l45 = cb[2], l67 = cb[3];
-        if (!(piv > 0.0)) {
-          if (lane == 0) atomicOr(flag, 1);
-          piv = 1.0;
-        }
-        const double t = own * (1.0 / piv);             // the chain: reciprocal → DMUL → DFMA
+        const double pv = cbuf[j];
+        const double own_raw = cbuf[r];
+        const double2* cb = reinterpret_cast<const double2*>(cbuf + hf * 8);
+        double2 l01 = cb[0], l23 = cb[1], l45 = cb[2], l67 = cb[3];
+        bad |= !(pv > 0.0);
+        const double piv = (pv > 0.0) ? pv : 1.0;
+        const double rinv = rsqrt(piv);                 // the chain: LDS → rsqrt → 2 DMUL → DFMA → STS
+        const double own = (r > j) ? own_raw : 0.0;
+        const double t = (own * rinv) * rinv;
+        // rows of the column at or above the pivot must not contribute: zero them (off the chain, parallel to rsqrt)
+        const int cbase = hf * 8;
+        l01.x = (cbase + 0 > j) ? l01.x : 0.0; l01.y = (cbase + 1 > j) ? l01.y : 0.0;
+        l23.x = (cbase + 2 > j) ? l23.x : 0.0; l23.y = (cbase + 3 > j) ? l23.y : 0.0;
+        l45.x = (cbase + 4 > j) ? l45.x : 0.0; l45.y = (cbase + 5 > j) ? l45.y : 0.0;
+        l67.x = (cbase + 6 > j) ? l67.x : 0.0; l67.y = (cbase + 7 > j) ? l67.y : 0.0;
         v[0] -= t * l01.x; v[1] -= t * l01.y; v[2] -= t * l23.x; v[3] -= t * l23.y;
         v[4] -= t * l45.x; v[5] -= t * l45.y; v[6] -= t * l67.x; v[7] -= t * l67.y;
-        const double rinv = rsqrt(piv);                 // off the chain
-        if (hf == jh) v[jc] = (r > j) ? own * rinv : ((r == j) ? piv * rinv : 0.0);   // column j of L
+        const double lval = (r > j) ? own * rinv : ((r == j) ? piv * rinv : 0.0);   // column j of L
+        v[jc] = (hf == jh) ? lval : v[jc];
         if (lane == 0) rdbuf[j] = rinv;
       }
+      if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flag, 1);
 #pragma unroll
       for (int c = 0; c < 8; c++) a[(c0 + r) * LDP + c0 + hf * 8 + c] = (hf * 8 + c <= r) ? v[c] : 0.0;
       if (prof_fine && tid == 0) acc_a += clock64() - t_a;
