@@ -241,6 +241,74 @@ def global_bundle_adjustment(ctx: Context, p: dict, iterations_limit=10, visual_
     return out
 
 
+def _quat_to_rot(q):
+    """[qx,qy,qz,qw] (Hamilton, Eigen coefficient order, keyframe_base.cpp:490-499) → R, vectorised."""
+    q = np.asarray(q, np.float64)
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.empty((len(q), 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - z * w); R[:, 0, 2] = 2 * (x * z + y * w)
+    R[:, 1, 0] = 2 * (x * y + z * w); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - x * w)
+    R[:, 2, 0] = 2 * (x * z - y * w); R[:, 2, 1] = 2 * (y * z + x * w); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def _rot_to_quat(R):
+    t = lambda v: np.sqrt(np.maximum(0.0, v)) / 2
+    w = t(1 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2])
+    x = np.copysign(t(1 + R[:, 0, 0] - R[:, 1, 1] - R[:, 2, 2]), R[:, 2, 1] - R[:, 1, 2])
+    y = np.copysign(t(1 - R[:, 0, 0] + R[:, 1, 1] - R[:, 2, 2]), R[:, 0, 2] - R[:, 2, 0])
+    z = np.copysign(t(1 - R[:, 0, 0] - R[:, 1, 1] + R[:, 2, 2]), R[:, 1, 0] - R[:, 0, 1])
+    q = np.stack([x, y, z, w], 1)
+    return q / np.linalg.norm(q, axis=1, keepdims=True)
+
+
+def pgo_edges(p: dict, vio_pose, wt=(10.0, 1.0, 10.0, 2.0, 3.0), covins_mode=True, use_robust=True, use_nbr=True):
+    """Edge list of Optimization::PoseGraphOptimization (optimization_be.cpp:886-1021), the host-side problem
+    construction (the C++ shim does the same on the reference containers): loop edges first (sqrt_info = the keyframe
+    weights diag(wt_kf_r, wt_kf_t)*wt_kf_n1 in COVINS mode :896-898, else chol(cov^-1)^T :922-923; Cauchy when
+    use_robust), then one successor edge per keyframe with a successor of the same agent (:947-972), then up to five
+    predecessor edges per keyframe with weights /1, /n23, /n23, /n45, /n45 (:976-1021), measured on the VIO poses and
+    de-duplicated on the ordered (kf, other) pair.  Defaults config_backend.yaml:126-130."""
+    wt_r, wt_t, n1, n23, n45 = wt
+    S1 = np.diag([wt_r] * 3 + [wt_t] * 3) * n1
+    vio_pose = np.asarray(vio_pose, np.float64)
+    Rv = _quat_to_rot(vio_pose[:, :4]); tv = vio_pose[:, 4:]
+    K = int(p["K"])
+    agent, kid = np.asarray(p["agent_of"]), np.asarray(p["kf_id"])
+    nl = len(p["loop_i"])
+    I = [np.asarray(p["loop_i"], np.int64)]; J = [np.asarray(p["loop_j"], np.int64)]
+    kind = [np.full(nl, -1)]                                   # -1 loop, 1..5 = which neighbour
+    idx = np.arange(K)
+    succ = idx[:-1][agent[1:] == agent[:-1]] if K > 1 else idx[:0]
+    I.append(succ); J.append(succ + 1); kind.append(np.full(len(succ), 1))
+    if use_nbr:
+        ii = np.repeat(idx, 5); kk = np.tile(np.arange(1, 6), K)
+        ok = kid[ii] - kk > 0
+        ii, kk = ii[ok], kk[ok]
+        I.append(ii); J.append(ii - kk); kind.append(kk)
+    I = np.concatenate(I); J = np.concatenate(J); kind = np.concatenate(kind)
+    # de-duplicate non-loop edges on the ordered pair, first occurrence wins (std::set semantics of the reference)
+    key = I * (K + 1) + J
+    keep = np.ones(len(I), bool)
+    nz = np.flatnonzero(kind > 0)
+    _, first = np.unique(key[nz], return_index=True)
+    mask = np.zeros(len(nz), bool); mask[first] = True
+    keep[nz] = mask
+    I, J, kind = I[keep], J[keep], kind[keep]
+    Rrel = np.einsum("nji,njk->nik", Rv[I], Rv[J])
+    Q = _rot_to_quat(Rrel); T = np.einsum("nji,nj->ni", Rv[I], tv[J] - tv[I])
+    SI = np.empty((len(I), 6, 6))
+    SI[:] = S1
+    SI[(kind == 2) | (kind == 3)] = S1 / n23
+    SI[(kind == 4) | (kind == 5)] = S1 / n45
+    loops = kind < 0
+    if nl:
+        Q[:nl] = np.asarray(p["loop_q"], np.float64); T[:nl] = np.asarray(p["loop_t"], np.float64)
+        if not covins_mode:
+            SI[:nl] = np.stack([np.linalg.cholesky(np.linalg.inv(c)).T for c in np.asarray(p["loop_cov"])])
+    return dict(i=I.astype(np.int32), j=J.astype(np.int32), q=Q, t=T, sqrt_info=SI, robust=loops & bool(use_robust))
+
+
 def pose_graph_optimization(ctx: Context, p: dict, edges: dict, iterations=10, robust_th=0.5):
     """Optimization::PoseGraphOptimization solve: poses only, `edges` = loop + successor + neighbour edges built as in
     optimization_be.cpp:886-1021; pgo_iteration_limit 10, robust_loss_th 0.5 (config_backend.yaml:121,125)."""

