@@ -20,12 +20,15 @@
 // per-keyframe and per-pair gathers read whole records), per landmark Hll/Hll^-1/b (15 doubles), S dense
 // row-major (n_c_pad^2 doubles, lower triangle), state double-buffered for accept/reject.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
 #include <numeric>
 #include <string>
 #include <vector>
+
+#include <cub/cub.cuh>
 
 #include "ba_math.cuh"
 #include "cholesky.cuh"
@@ -53,6 +56,10 @@ __device__ __forceinline__ int cam_col(const int* __restrict__ off_pose, const i
 constexpr int RED_BLOCKS = 512;   // fixed grid for reducing kernels → fixed summation order
 constexpr int RED_SLOTS = 8;
 
+// Device arrays come from the stream-ordered allocator on the engine's stream: the pool (release threshold raised in
+// cvb_ctx_create) keeps freed blocks, so building a second problem re-uses the first one's memory instead of paying
+// cudaMalloc/cudaFree (which cost ~100 ms of a 180 ms set-up at C3, the 7.4 GB S buffer alone several ms each way).
+static thread_local cudaStream_t t_alloc_stream = nullptr;
 template <typename T>
 struct DevArr {
   T* p = nullptr;
@@ -60,10 +67,10 @@ struct DevArr {
   int alloc(size_t count) {
     n = count;
     if (count == 0) count = 1;
-    return cudaMalloc(&p, count * sizeof(T)) == cudaSuccess ? 0 : 1;
+    return cudaMallocAsync(&p, count * sizeof(T), t_alloc_stream) == cudaSuccess ? 0 : 1;
   }
   void free_() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, t_alloc_stream);
     p = nullptr;
   }
 };
@@ -134,6 +141,14 @@ struct Engine {
   double phase_ms[5] = {0, 0, 0, 0, 0};
   double chol_flops = 0.0;
   ~Engine() {
+    const bool trace = getenv("COVINS_B200_SETUP_TRACE") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!trace) return;
+      const auto now = std::chrono::steady_clock::now();
+      fprintf(stderr, "[destroy] %-26s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+      t_prev = now;
+    };
     for (int i = 0; i < 2; i++) { pose[i].free_(); sb[i].free_(); lm[i].free_(); }
     pose_const.free_(); off_pose.free_(); off_sb.free_(); xt_i.free_(); xt_j.free_(); zt_i.free_(); zt_j.free_(); xbuf.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
     obs_kf.free_(); obs_lm.free_(); lm_ptr.free_(); kf_ptr.free_(); kf_obs.free_(); obs_uv.free_(); obs_sigma.free_();
@@ -146,14 +161,18 @@ struct Engine {
     scale.free_(); colsq.free_(); diag.free_(); gvec.free_(); grad.free_(); sgrad.free_(); gn.free_(); step.free_();
     xsol.free_(); yb.free_(); gs.free_(); tmp.free_(); S.free_(); linv.free_(); flag.free_(); partials.free_();
     scalars.free_();
+    lap("device arrays");
     if (h_scalars) cudaFreeHost(h_scalars);
+    lap("pinned scalars");
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : la_ev) if (e) cudaEventDestroy(e);
     if (fs.bulk) cudaStreamDestroy(fs.bulk);
     for (int g = 0; g < fs.n_group; g++) { if (fs.group[g]) cudaStreamDestroy(fs.group[g]); if (fs.join[g]) cudaEventDestroy(fs.join[g]); }
     if (fs.fork) cudaEventDestroy(fs.fork);
+    lap("events, streams");
     if (g_factor) cudaGraphExecDestroy(g_factor);
     if (g_solve) cudaGraphExecDestroy(g_solve);
+    lap("graphs");
   }
 };
 
@@ -993,8 +1012,113 @@ int read_scalars(Engine& E, int nslots) {
   return CVB_OK;
 }
 
+// ---- Schur (block → observation-pair) lists, built on the device -----------------------------------------------
+// For every S block (hi keyframe, lo keyframe) the Schur kernel needs the list of observation pairs (a, b) of the
+// landmarks seen by both, in landmark order (fixed summation order → bit-reproducible).  3.6 M pairs at C3: generated by
+// one thread per landmark, ordered by two stable LSD radix sorts (cub) over the keyframe indices, run-length encoded.
+// (The host version of the same — two counting-sort passes — cost 120 ms of the 180 ms problem set-up.)
+__global__ void gen_pairs_kernel(int L_in, const int* __restrict__ lm_ptr, const long long* __restrict__ pair_ptr,
+                                 const int* __restrict__ obs_kf, unsigned long long* __restrict__ keys,
+                                 unsigned long long* __restrict__ vals) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L_in) return;
+  long long o = pair_ptr[l];
+  const int o0 = lm_ptr[l], o1 = lm_ptr[l + 1];
+  for (int a = o0; a < o1; a++) {
+    const unsigned long long hi = (unsigned long long)(unsigned)obs_kf[a] << 32;
+    for (int b = o0; b <= a; b++, o++) {
+      keys[o] = hi | (unsigned)obs_kf[b];
+      vals[o] = ((unsigned long long)(unsigned)a << 32) | (unsigned)b;
+    }
+  }
+}
+__global__ void pair_heads_kernel(long long np, const unsigned long long* __restrict__ keys, int* __restrict__ head) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+__global__ void pair_scatter_kernel(long long np, const unsigned long long* __restrict__ keys,
+                                    const unsigned long long* __restrict__ vals, const int* __restrict__ head,
+                                    const int* __restrict__ blk /*exclusive scan of head*/, int* __restrict__ sb_hi,
+                                    int* __restrict__ sb_lo, int* __restrict__ sb_ptr, int* __restrict__ sp_a,
+                                    int* __restrict__ sp_b) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= np) return;
+  const unsigned long long v = vals[i];
+  sp_a[i] = (int)(v >> 32);
+  sp_b[i] = (int)(v & 0xffffffffu);
+  if (head[i]) {
+    const int bidx = blk[i];
+    sb_hi[bidx] = (int)(keys[i] >> 32);
+    sb_lo[bidx] = (int)(keys[i] & 0xffffffffu);
+    sb_ptr[bidx] = (int)i;
+  }
+}
+
+int build_schur_lists(Engine& E, const std::vector<int>& h_lm_ptr, int K) {
+  std::vector<long long> h_pair_ptr((size_t)E.L_in + 1, 0);
+  for (int l = 0; l < E.L_in; l++) {
+    const long long n = h_lm_ptr[l + 1] - h_lm_ptr[l];
+    h_pair_ptr[l + 1] = h_pair_ptr[l] + n * (n + 1) / 2;
+  }
+  const long long np = h_pair_ptr[E.L_in];
+  if (np >= (1LL << 31)) return cvb_fail(E.ctx, CVB_ERR_UNSUPPORTED, "more than 2^31 Schur observation pairs");
+  int rc;
+  if ((rc = zalloc(E, E.sp_a, (size_t)np)) || (rc = zalloc(E, E.sp_b, (size_t)np))) return rc;
+  E.n_sb = 0;
+  if (np == 0) {
+    if ((rc = zalloc(E, E.sb_hi, 0)) || (rc = zalloc(E, E.sb_lo, 0)) || (rc = zalloc(E, E.sb_ptr, 1))) return rc;
+    return CVB_OK;
+  }
+  DevArr<long long> d_pair_ptr;
+  DevArr<unsigned long long> k0, k1, v0, v1;
+  DevArr<int> head, blk;
+  DevArr<unsigned char> tmp;
+  if ((rc = upload(E, d_pair_ptr, h_pair_ptr))) return rc;
+  if (k0.alloc((size_t)np) || k1.alloc((size_t)np) || v0.alloc((size_t)np) || v1.alloc((size_t)np) || head.alloc((size_t)np + 1) ||
+      blk.alloc((size_t)np + 1))
+    return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (Schur pair scratch, %lld pairs)", np);
+  gen_pairs_kernel<<<grid1((size_t)E.L_in), 256, 0, E.st>>>(E.L_in, E.lm_ptr.p, d_pair_ptr.p, E.obs_kf.p, k0.p, v0.p);
+  ENG_LAUNCH();
+  int bits = 1;
+  while ((1 << bits) < K) bits++;
+  size_t t1 = 0, t2 = 0, t3 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, t1, k0.p, k1.p, v0.p, v1.p, (int)np, 0, bits, E.st);
+  cub::DeviceRadixSort::SortPairs(nullptr, t2, k1.p, k0.p, v1.p, v0.p, (int)np, 32, 32 + bits, E.st);
+  cub::DeviceScan::ExclusiveSum(nullptr, t3, head.p, blk.p, (int)np + 1, E.st);
+  size_t tb = std::max(t1, std::max(t2, t3));
+  if (tmp.alloc(tb ? tb : 1)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (sort scratch)");
+  ENG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.p, k1.p, v0.p, v1.p, (int)np, 0, bits, E.st));        // by lo keyframe
+  ENG_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1.p, k0.p, v1.p, v0.p, (int)np, 32, 32 + bits, E.st));  // by hi (stable)
+  pair_heads_kernel<<<grid1((size_t)np), 256, 0, E.st>>>(np, k0.p, head.p);
+  ENG_LAUNCH();
+  ENG_CUDA(cudaMemsetAsync(head.p + np, 0, sizeof(int), E.st));
+  ENG_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, head.p, blk.p, (int)np + 1, E.st));
+  int n_sb = 0;
+  ENG_CUDA(cudaMemcpyAsync(&n_sb, blk.p + np, sizeof(int), cudaMemcpyDeviceToHost, E.st));
+  ENG_CUDA(cudaStreamSynchronize(E.st));
+  E.n_sb = n_sb;
+  if ((rc = zalloc(E, E.sb_hi, (size_t)n_sb)) || (rc = zalloc(E, E.sb_lo, (size_t)n_sb)) || (rc = zalloc(E, E.sb_ptr, (size_t)n_sb + 1)))
+    return rc;
+  pair_scatter_kernel<<<grid1((size_t)np), 256, 0, E.st>>>(np, k0.p, v0.p, head.p, blk.p, E.sb_hi.p, E.sb_lo.p, E.sb_ptr.p, E.sp_a.p,
+                                                          E.sp_b.p);
+  ENG_LAUNCH();
+  const int np_i = (int)np;
+  ENG_CUDA(cudaMemcpyAsync(E.sb_ptr.p + n_sb, &np_i, sizeof(int), cudaMemcpyHostToDevice, E.st));
+  ENG_CUDA(cudaStreamSynchronize(E.st));   // scratch arrays are freed on return
+  d_pair_ptr.free_(); k0.free_(); k1.free_(); v0.free_(); v1.free_(); head.free_(); blk.free_(); tmp.free_();
+  return CVB_OK;
+}
+
 int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   cvb_ctx* ctx = E.ctx;
+  const bool trace = getenv("COVINS_B200_SETUP_TRACE") != nullptr;   // development aid: host-side phase times to stderr
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[setup] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+    t_prev = now;
+  };
   E.visual_only = o->visual_only ? 1 : 0;
   E.per = E.visual_only ? 6 : 15;
   E.K = p->K;
@@ -1094,6 +1218,7 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   E.n_c_pad = ((n_total + TT - 1) / TT) * TT;
   E.n_vec = E.n_c_pad + 3 * E.L_in;
   auto col_of = [&](int kf, int c) { return c < 6 ? E.h_off_pose[kf] + c : E.h_off_sb[kf] + (c - 6); };
+  lap("landmarks / observations");
   // ---- tile-level structure of S (every rank needs the structure of the WHOLE problem: S is all-reduced) ----
   const int nt = E.n_c_pad / TT;
   std::vector<uint8_t> tmask((size_t)nt * nt, 0);
@@ -1141,6 +1266,7 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   E.plan.h_col_group.assign(nt, -1);
   for (size_t g = 0; g < sb_ranges.size(); g++)
     for (int t = sb_ranges[g].first / TT; t <= (sb_ranges[g].second - 1) / TT; t++) E.plan.h_col_group[t] = (int)g;
+  lap("tile structure + plan");
   // ---- by-keyframe CSR ----
   std::vector<int> h_kf_ptr(K + 1, 0), h_kf_obs(E.n_obs);
   for (int ob = 0; ob < E.n_obs; ob++) h_kf_ptr[h_obs_kf[ob] + 1]++;
@@ -1149,55 +1275,9 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     std::vector<int> fill(h_kf_ptr.begin(), h_kf_ptr.end() - 1);
     for (int ob = 0; ob < E.n_obs; ob++) h_kf_obs[fill[h_obs_kf[ob]]++] = ob;
   }
-  // ---- Schur (block → pair) lists ----
-  std::vector<uint64_t> keys;
-  std::vector<int> pa, pb;
-  {
-    size_t np = 0;
-    for (int l = 0; l < E.L_in; l++) {
-      const size_t n = h_lm_ptr[l + 1] - h_lm_ptr[l];
-      np += n * (n + 1) / 2;
-    }
-    keys.reserve(np); pa.reserve(np); pb.reserve(np);
-    for (int l = 0; l < E.L_in; l++)
-      for (int a = h_lm_ptr[l]; a < h_lm_ptr[l + 1]; a++)
-        for (int b = h_lm_ptr[l]; b <= a; b++) {
-          keys.push_back(((uint64_t)h_obs_kf[a] << 32) | (uint32_t)h_obs_kf[b]);
-          pa.push_back(a);
-          pb.push_back(b);
-        }
-  }
-  // order the pairs by (hi keyframe, lo keyframe), stable w.r.t. the landmark order in which they were generated:
-  // two counting-sort passes (LSD radix over the two keyframe indices) — O(n), where std::stable_sort took ~1 s at C3
-  std::vector<uint32_t> order(keys.size()), tmp_order(keys.size());
-  {
-    std::vector<uint32_t> cnt((size_t)K + 1);
-    auto pass = [&](const std::vector<uint32_t>* in, std::vector<uint32_t>& out, int shift) {
-      std::fill(cnt.begin(), cnt.end(), 0u);
-      const size_t n = keys.size();
-      for (size_t i = 0; i < n; i++) cnt[(size_t)((keys[in ? (*in)[i] : i] >> shift) & 0xffffffffu) + 1]++;
-      for (int b = 0; b < K; b++) cnt[b + 1] += cnt[b];
-      for (size_t i = 0; i < n; i++) {
-        const uint32_t src = in ? (*in)[i] : (uint32_t)i;
-        out[cnt[(size_t)((keys[src] >> shift) & 0xffffffffu)]++] = src;
-      }
-    };
-    pass(nullptr, tmp_order, 0);      // by lo keyframe
-    pass(&tmp_order, order, 32);      // by hi keyframe (stable)
-  }
-  std::vector<int> h_sb_hi, h_sb_lo, h_sb_ptr, h_sp_a(keys.size()), h_sp_b(keys.size());
-  for (size_t i = 0; i < order.size(); i++) {
-    const uint64_t k = keys[order[i]];
-    if (i == 0 || k != keys[order[i - 1]]) {
-      h_sb_hi.push_back((int)(k >> 32));
-      h_sb_lo.push_back((int)(k & 0xffffffffu));
-      h_sb_ptr.push_back((int)i);
-    }
-    h_sp_a[i] = pa[order[i]];
-    h_sp_b[i] = pb[order[i]];
-  }
-  h_sb_ptr.push_back((int)order.size());
-  E.n_sb = (int)h_sb_hi.size();
+  lap("by-keyframe CSR");
+  // ---- Schur (block → pair) lists: built on the device after the observation arrays are uploaded (build_schur_lists) ----
+  lap("Schur pair lists");
   // ---- factors of this rank (round-robin) and their gather lists ----
   std::vector<int> h_imu_i, h_imu_j, sel_imu;
   if (!E.visual_only)
@@ -1245,6 +1325,7 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   h_fb_ptr.push_back((int)terms.size());
   E.n_fb = (int)h_fb_hi.size();
 
+  lap("factor lists");
   // ---- uploads ----
   int rc;
   E.h_const.assign(p->pose_const, p->pose_const + K);
@@ -1274,9 +1355,8 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   if ((rc = zalloc(E, E.Hll, (size_t)6 * E.L_in)) || (rc = zalloc(E, E.HllInv, (size_t)6 * E.L_in)) ||
       (rc = zalloc(E, E.bl, (size_t)3 * E.L_in)))
     return rc;
-  if ((rc = upload(E, E.sb_hi, h_sb_hi)) || (rc = upload(E, E.sb_lo, h_sb_lo)) || (rc = upload(E, E.sb_ptr, h_sb_ptr)) ||
-      (rc = upload(E, E.sp_a, h_sp_a)) || (rc = upload(E, E.sp_b, h_sp_b)))
-    return rc;
+  if ((rc = build_schur_lists(E, h_lm_ptr, K))) return rc;
+  lap("Schur pair lists (device)");
   if ((rc = upload(E, E.fb_hi, h_fb_hi)) || (rc = upload(E, E.fb_lo, h_fb_lo)) || (rc = upload(E, E.fb_ptr, h_fb_ptr)) ||
       (rc = upload(E, E.ft_type, h_ft_type)) || (rc = upload(E, E.ft_fac, h_ft_fac)) || (rc = upload(E, E.ft_rhi, h_ft_rhi)) ||
       (rc = upload(E, E.ft_rlo, h_ft_rlo)))
@@ -1326,6 +1406,7 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     ENG_CUDA(cudaStreamSynchronize(E.st));
     d_ptr.free_(); d_dt.free_(); d_acc.free_(); d_gyr.free_(); d_a0.free_(); d_g0.free_(); d_noise.free_();
   }
+  lap("uploads");
   // ---- vectors, S ----
   std::vector<double> h_scale(E.n_vec, 0.0);
   for (int k = 0; k < K; k++) {
@@ -1348,7 +1429,8 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   DevArr<double>* vecs[] = {&E.colsq, &E.diag, &E.gvec, &E.grad, &E.sgrad, &E.gn, &E.step, &E.xsol, &E.yb, &E.gs, &E.tmp};
   for (auto* v : vecs)
     if ((rc = zalloc(E, *v, (size_t)E.n_vec))) return rc;
-  if ((rc = zalloc(E, E.S, (size_t)E.n_c_pad * E.n_c_pad))) return rc;
+  // S is not cleared here: every iteration clears exactly the tiles it uses (zero_tiles_kernel), nothing else is read
+  if (E.S.alloc((size_t)E.n_c_pad * E.n_c_pad)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (reduced camera system, %zu bytes)", (size_t)E.n_c_pad * E.n_c_pad * 8);
   if ((rc = zalloc(E, E.linv, (size_t)E.n_c_pad * cvb_chol::T))) return rc;
   if ((rc = zalloc(E, E.partials, (size_t)RED_SLOTS * RED_BLOCKS)) || (rc = zalloc(E, E.scalars, RED_SLOTS))) return rc;
   ENG_CUDA(cudaMallocHost(&E.h_scalars, RED_SLOTS * sizeof(double)));
@@ -1368,6 +1450,7 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     ENG_CUDA(cudaEventCreateWithFlags(&E.fs.fork, cudaEventDisableTiming));
   }
   ENG_CUDA(cudaStreamSynchronize(E.st));
+  lap("vectors, S, streams (sync)");
   return CVB_OK;
 }
 
@@ -1819,6 +1902,7 @@ int cvb_ba_create(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o
   cvb_ba* h = new cvb_ba();
   h->E.ctx = ctx;
   h->E.st = ctx->stream;
+  t_alloc_stream = ctx->stream;
   h->prob_copy = *p;
   int rc = engine_setup(h->E, p, o);
   if (!rc) rc = engine_begin(h->E);
@@ -1908,6 +1992,7 @@ int cvb_ba_timing(cvb_ba* h, double out[6], int reset) {
 int cvb_ba_destroy(cvb_ba* h) {
   if (h) {
     cudaStreamSynchronize(h->E.st);
+    t_alloc_stream = h->E.st;
     delete h;
   }
   return CVB_OK;

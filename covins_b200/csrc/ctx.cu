@@ -79,6 +79,13 @@ int cvb_ctx_create(int device, cvb_ctx** out) {
     delete c;
     return CVB_ERR_CUDA;
   }
+  {   // keep memory freed by the stream-ordered allocator in the pool (problem set-up re-uses it)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   *out = c;
   return CVB_OK;
 }
