@@ -296,10 +296,14 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         s2 = O.BaSolver(ctx, prob, visual_only=False, rank=rank, world=world, allreduce=O.torch_allreduce() if world > 1 else None)
+        t1 = time.perf_counter()
         done = s2.iterate(e2e_iters)
+        t2 = time.perf_counter()
         r2 = s2.result()
         ctx.sync()
         e2e_runs.append((max_over_ranks(time.perf_counter() - t0), done))
+        if os.environ.get("COVINS_BENCH_VERBOSE") and rank == 0:
+            print(f"[e2e] create {1e3*(t1-t0):.1f} ms, iterate {1e3*(t2-t1):.1f} ms, result {1e3*(time.perf_counter()-t2):.1f} ms", file=sys.stderr)
         s2.close()
     dt_e2e, done = sorted(e2e_runs)[1]
     h2d_gba = sum(np.asarray(v).nbytes for k, v in prob.items() if isinstance(v, np.ndarray) and not k.startswith("gt_"))

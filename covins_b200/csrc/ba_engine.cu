@@ -1226,14 +1226,21 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     for (int ta = a0 / TT; ta <= (a0 + alen - 1) / TT; ta++)
       for (int tb = b0 / TT; tb <= (b0 + blen - 1) / TT; tb++) tmask[(size_t)std::max(ta, tb) * nt + std::min(ta, tb)] = 1;
   };
-  for (int l = 0; l < p->L; l++) {
-    if (lm_compact[l] < 0) continue;
-    for (int a = p->lm_obs_ptr[l]; a < p->lm_obs_ptr[l + 1]; a++) {
-      if (p->obs_skip && p->obs_skip[a]) continue;
-      for (int b = p->lm_obs_ptr[l]; b <= a; b++) {
-        if (p->obs_skip && p->obs_skip[b]) continue;
-        mark(E.h_off_pose[p->obs_kf[a]], 6, E.h_off_pose[p->obs_kf[b]], 6);
+  {
+    // a landmark couples the pose blocks of all its observers pairwise: mark the pairs of the DISTINCT tiles they touch
+    // (a landmark's ~8 observers fall into a handful of tiles, so this is several times cheaper than walking the pairs)
+    std::vector<int> ts;
+    for (int l = 0; l < p->L; l++) {
+      if (lm_compact[l] < 0) continue;
+      ts.clear();
+      for (int a = p->lm_obs_ptr[l]; a < p->lm_obs_ptr[l + 1]; a++) {
+        if (p->obs_skip && p->obs_skip[a]) continue;
+        const int o0 = E.h_off_pose[p->obs_kf[a]];
+        for (int t = o0 / TT; t <= (o0 + 5) / TT; t++)
+          if (std::find(ts.begin(), ts.end(), t) == ts.end()) ts.push_back(t);
       }
+      for (size_t x = 0; x < ts.size(); x++)
+        for (size_t y = 0; y <= x; y++) tmask[(size_t)std::max(ts[x], ts[y]) * nt + std::min(ts[x], ts[y])] = 1;
     }
   }
   if (!E.visual_only)
