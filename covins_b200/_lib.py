@@ -63,6 +63,7 @@ SIGNATURES = {
     "cvb_landmark_match_batch_dev": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_float,
                                                C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "cvb_microbench_popc": (C.c_int, [c_vp, C.c_int, c_f64p]),
+    "cvb_microbench_minmax": (C.c_int, [c_vp, c_f64p]),
     "cvb_microbench_latency": (C.c_int, [c_vp, c_f64p]),
     "cvb_microbench_potrf": (C.c_int, [c_vp, C.c_int, c_f64p, c_vp]),
     "cvb_dense_cholesky_solve": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_f64p]),

@@ -140,3 +140,64 @@ extern "C" int cvb_microbench_latency(cvb_ctx* ctx, double* out8) {
   cudaEventDestroy(e1);
   return CVB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Issue rate of the integer min/max forms the matching epilogue can use (per SM per clock, all SMs busy):
+//   out[0] 32-bit signed min/max (VIMNMX.S32)   out[1] packed 2 x u16 min/max (VIMNMX.U16x2), counted per instruction
+// ------------------------------------------------------------------------------------------------
+namespace {
+template <int MODE>
+__global__ void __launch_bounds__(256) minmax_kernel(unsigned* out, unsigned seed, int iters) {
+  unsigned w[8], x = seed * (threadIdx.x + 1) + blockIdx.x;
+#pragma unroll
+  for (int c = 0; c < 8; c++) w[c] = 0xffffffffu - c * seed;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      if (MODE == 0) {
+        const int lo = min((int)w[c], (int)x);
+        x = (unsigned)max((int)w[c], (int)x);
+        w[c] = (unsigned)lo;
+      } else {
+        const unsigned lo = __vminu2(w[c], x);
+        x = __vmaxu2(w[c], x);
+        w[c] = lo;
+      }
+    }
+    x = x * 1664525u + 1013904223u;
+  }
+  unsigned r = x;
+#pragma unroll
+  for (int c = 0; c < 8; c++) r ^= w[c];
+  if (r == 0x12345678u) out[0] = r;
+}
+}  // namespace
+
+extern "C" int cvb_microbench_minmax(cvb_ctx* ctx, double* out2) {
+  if (!ctx || !out2) return CVB_ERR_INVALID;
+  unsigned* d = (unsigned*)cvb_ws(ctx, WS_MISC, 256);
+  if (!d) return CVB_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  CVB_CUDA(ctx, cudaEventCreate(&e0));
+  CVB_CUDA(ctx, cudaEventCreate(&e1));
+  const int iters = 4096, blocks = ctx->sm_count * 8;
+  int clk_khz = 0;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, ctx->device);
+  for (int mode = 0; mode < 2; mode++) {
+    for (int rep = 0; rep < 2; rep++) {
+      CVB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+      if (mode == 0) minmax_kernel<0><<<blocks, 256, 0, ctx->stream>>>(d, 12345u, iters);
+      else minmax_kernel<1><<<blocks, 256, 0, ctx->stream>>>(d, 12345u, iters);
+      CVB_CHECK_LAUNCH(ctx);
+      CVB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+      CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    float ms = 0.f;
+    CVB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    const double lane_ops = (double)blocks * 256 * iters * 16;   // 2 instructions x 8 chains per iteration
+    out2[mode] = lane_ops / (ms * 1e-3) / ((double)clk_khz * 1e3) / ctx->sm_count;   // lane-instructions / clk / SM
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return CVB_OK;
+}

@@ -116,6 +116,22 @@ struct TcHamming {
     }
     return pc;
   }
+  // query side: the same permutation with 0/1 bytes, so that accumulator = 128 * popc(a & b) = (2 popc(a & b)) << 6,
+  // which is what the packed 16-bit keys of the epilogue subtract (done once per CTA: plain shifts are fine here)
+  static __device__ __forceinline__ int store_half_q(const uint4 (&v)[kLoads], int half, uint8_t* dst_row0) {
+    const uint32_t w[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+    int pc = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      pc += __popc(w[i]);
+      uint4 lo, hi;
+      lo.x = w[i] & 0x01010101u; lo.y = (w[i] >> 1) & 0x01010101u; lo.z = (w[i] >> 2) & 0x01010101u; lo.w = (w[i] >> 3) & 0x01010101u;
+      hi.x = (w[i] >> 4) & 0x01010101u; hi.y = (w[i] >> 5) & 0x01010101u; hi.z = (w[i] >> 6) & 0x01010101u; hi.w = (w[i] >> 7) & 0x01010101u;
+      *reinterpret_cast<uint4*>(dst_row0 + (8 * half + 2 * i) * 128) = lo;
+      *reinterpret_cast<uint4*>(dst_row0 + (8 * half + 2 * i + 1) * 128) = hi;
+    }
+    return pc;
+  }
 };
 struct TcL2 {
   static constexpr int kRowBytes = 128;
@@ -135,6 +151,9 @@ struct TcL2 {
       *reinterpret_cast<uint4*>(dst_row0 + (4 * half + c) * 128) = v[c];
     }
     return (int)n2;
+  }
+  static __device__ __forceinline__ int store_half_q(const uint4 (&v)[kLoads], int half, uint8_t* dst_row0) {
+    return store_half(v, half, dst_row0);
   }
 };
 
@@ -235,7 +254,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
     if (q < p.nq) {
       uint4 v[M::kLoads];
       M::load_half(p.q + (size_t)q * M::kRowBytes, half, v);
-      nrm = M::store_half(v, half, dst);
+      nrm = M::store_half_q(v, half, dst);
     } else {
       for (int c = 0; c < KB / 32; c++) *reinterpret_cast<uint4*>(dst + (half * (KB / 32) + c) * 128) = make_uint4(0, 0, 0, 0);
     }
@@ -297,15 +316,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
         uint8_t* dst = sB + (size_t)s * TN * KB + row_offset<KB>(prow);
         const bool rv = it.r0 + prow < it.len;
         int part = 0;
-        if (rv) {
+        if (rv && !(p.dbg & 2)) {
           part = M::store_half(cur, half, dst);
         } else {
           for (int c = 0; c < KB / 32; c++) *reinterpret_cast<uint4*>(dst + (half * (KB / 32) + c) * 128) = make_uint4(0, 0, 0, 0);
         }
         part += __shfl_xor_sync(0xffffffffu, part, 8);   // the two halves of a row sit 8 lanes apart
         // Hamming: packed column term (popc(row) << 22 | segment-local index), L2: |row|^2; tail rows never enter a list
-        const int nrm = M::kIsL2 ? (rv ? part : kInf) : (rv ? ((part << kIdxBits) | (it.r0 + prow)) : INT_MAX);
-        if (half == 0) sNorm[(n % NORM_RING) * TN + prow] = nrm;
+        if (M::kIsL2) {
+          if (half == 0) sNorm[(n % NORM_RING) * TN + prow] = rv ? part : kInf;
+        } else if (half == 0) {
+          // Hamming: 16-bit column term ((popc(row) + 256) << 6 | column within its 32-column group); 0xFFFF = no row
+          reinterpret_cast<uint16_t*>(sNorm)[(n % NORM_RING) * TN + prow] =
+              rv ? (uint16_t)(((part + 256) << 6) | (prow & 31)) : (uint16_t)0xFFFFu;
+        }
         fence_proxy_async();
         mbar_arrive(&full[s]);
         it.advance();
@@ -357,29 +381,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
         const int s = n % STAGES;
         cvb_mbar_wait(&tfull[s], (n / STAGES) & 1);
         tc_fence_after();
-        const int4* nrm4 = reinterpret_cast<const int4*>(sNorm + (n % NORM_RING) * TN + grp * 32);
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)s * TN + grp * 32;
         uint32_t acc[32];
         tc_ld32(taddr, acc);
-        if (valid) {
+        if (valid && !(p.dbg & 1)) {
+          if (!M::kIsL2) {
+            // Two columns per instruction: 16-bit keys ((popc(t) - 2 popc(q & t) + 256) << 6 | column) packed pairwise
+            // (even column low, odd column high), k-lists kept per half with packed 16-bit min/max (VIMNMX.U16x2 issues
+            // at the 32-bit rate), merged into the 32-bit (distance, index) lists once per tile — and only if the tile
+            // holds a candidate that beats the current k-th entry (later tiles have larger indices, so "beats" is a
+            // strict distance comparison).
+            const uint4* nrm4 = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(sNorm) + (n % NORM_RING) * TN + grp * 32);
+            unsigned pk[K];
 #pragma unroll
-          for (int i4 = 0; i4 < 8; i4++) {
-            const int4 nn = nrm4[i4];
-            const int nv[4] = {nn.x, nn.y, nn.z, nn.w};
+            for (int c = 0; c < K; c++) pk[c] = 0xFFFFFFFFu;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const int i = 4 * i4 + j;
-              if (!M::kIsL2) {
-                // packed key in the "t domain" (without the per-query constant): numeric order == (distance, index)
-                // order, so the k smallest keys ARE OpenCV's k-NN list.  Branch-free min/max insertion network.
-                int x = (int)((unsigned)nv[j] - acc[i] * 512u);   // (popc(t) - 2 popc(q & t)) << 22 | idx (wraps mod 2^32)
+            for (int i4 = 0; i4 < 4; i4++) {
+              const uint4 nn = nrm4[i4];
+              const unsigned nv[4] = {nn.x, nn.y, nn.z, nn.w};
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const int i = 8 * i4 + 2 * j;   // columns i (low half) and i + 1 (high half)
+                unsigned x = nv[j] + acc[i] * 0xFFFFFFFFu + acc[i + 1] * 0xFFFF0000u;
 #pragma unroll
                 for (int c = 0; c < K; c++) {
-                  const int lo = min(wk[c], x);
-                  x = max(wk[c], x);
-                  wk[c] = lo;
+                  const unsigned lo = __vminu2(pk[c], x);
+                  x = __vmaxu2(pk[c], x);
+                  pk[c] = lo;
                 }
-              } else {
+              }
+            }
+            const unsigned best16 = min(pk[0] & 0xFFFFu, pk[0] >> 16);
+            const int worst_v = wk[K - 1] == INT_MAX ? 1024 : (wk[K - 1] >> kIdxBits) + 256;   // arithmetic shift: t-domain value
+            if ((int)(best16 >> 6) < worst_v) {
+#pragma unroll
+              for (int c = 0; c < K; c++)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                  const unsigned k16 = h ? (pk[c] >> 16) : (pk[c] & 0xFFFFu);
+                  int x = k16 == 0xFFFFu ? INT_MAX
+                                         : (int)((((unsigned)(k16 >> 6) - 256u) << kIdxBits) + (unsigned)(r0 + grp * 32 + (int)(k16 & 63u)));
+#pragma unroll
+                  for (int cc = 0; cc < K; cc++) {
+                    const int lo = min(wk[cc], x);
+                    x = max(wk[cc], x);
+                    wk[cc] = lo;
+                  }
+                }
+            }
+          } else {
+            const int4* nrm4 = reinterpret_cast<const int4*>(sNorm + (n % NORM_RING) * TN + grp * 32);
+#pragma unroll
+            for (int i4 = 0; i4 < 8; i4++) {
+              const int4 nn = nrm4[i4];
+              const int nv[4] = {nn.x, nn.y, nn.z, nn.w};
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const int i = 4 * i4 + j;
                 const int d = qn + nv[j] - 2 * (int)acc[i];
                 if (d < wd2[K - 1]) {
                   const int key = __float_as_int(__fsqrt_rn((float)d));
@@ -503,6 +561,10 @@ int launch(cvb_ctx* ctx, TcParams p, int metric, int k, cudaStream_t st) {
   if (parts < 1) parts = 1;
   if (parts > p.n_seg) parts = p.n_seg;
   p.parts = parts;
+  {
+    const char* d = getenv("COVINS_B200_TC_DEBUG");
+    p.dbg = d ? atoi(d) : 0;
+  }
 #define TC_CASE(MM, KK) return launch_tc<MM, KK>(ctx, p, st)
   if (metric == 0) {
     switch (k) { case 1: TC_CASE(TcHamming, 1); case 2: TC_CASE(TcHamming, 2); case 3: TC_CASE(TcHamming, 3); default: TC_CASE(TcHamming, 4); }

@@ -21,6 +21,7 @@ struct TcParams {
   int32_t* match_train;
   float* match_dist;
   int32_t* n_matches;
+  int dbg;   // development switches (COVINS_B200_TC_DEBUG): 1 = epilogue skips the selection, 2 = producers skip the expansion
 };
 
 // metric 0 = Hamming (32-byte rows), 1 = L2 on u8 (128-byte rows); OpenCV k-NN rule (the DenseMatcher list rule is

@@ -177,6 +177,8 @@ CVB_API int cvb_landmark_match_batch_dev(cvb_ctx* ctx, const uint8_t* d_A, const
  * returns giga-(32-bit popc)/s in *gpopc_per_s. */
 CVB_API int cvb_microbench_popc(cvb_ctx* ctx, int iters, double* gpopc_per_s);
 
+/* Diagnostic: issue rate (lane-instructions per clock per SM) of 32-bit and packed 2x16-bit integer min/max. out2: double[2]. */
+CVB_API int cvb_microbench_minmax(cvb_ctx* ctx, double* out2);
 /* Diagnostic: latency of the diagonal-tile kernel of the tiled Cholesky (K8's serial chain), see cholesky.cu.
  * phase_cycles may be NULL, else int64[10]. */
 CVB_API int cvb_microbench_potrf(cvb_ctx* ctx, int reps, double* us_per_tile, int64_t* phase_cycles);

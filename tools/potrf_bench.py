@@ -17,3 +17,6 @@ ctx.check(lib().cvb_microbench_latency(ctx.handle, lat.ctypes.data_as(C.POINTER(
 for n, v in zip(["dep DFMA", "8-way indep DFMA (per op)", "dep rsqrt(double)+add", "dep SHFL double", "STS+LDS round trip",
                  "dep DMUL", "dep FFMA", "SM clock MHz (est)"], lat):
     print(f"  {n:28s} {v:9.1f}")
+mm = np.zeros(2)
+ctx.check(lib().cvb_microbench_minmax(ctx.handle, mm.ctypes.data_as(C.POINTER(C.c_double))))
+print(f"  integer min/max issue rate (lane-instr/clk/SM): 32-bit {mm[0]:.1f}, packed u16x2 {mm[1]:.1f}")
