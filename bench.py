@@ -388,18 +388,22 @@ def run_ours(args):
         db.append(h_maps_np[c % 2] if c < 2 else maps[c].cpu().numpy(), np.full(N_KF, N_FEAT, np.int32))
         dbs.append(db)
     h_queries = [np.ascontiguousarray(h_maps_np[0][k * N_FEAT:(k + 1) * N_FEAT]) for k in (123, 777, 1500, 42)]
-    db_steps = max(args.steps, 10)
+    db_steps = max(args.steps, 30)
     d2h_db = 0
     for i in range(3):
         dbs[i % N_COPIES].match_hamming(h_queries[i % 4], THR, RATIO)
     barrier()
+    step_s = []
     t0 = time.perf_counter()
     for i in range(db_steps):
-        out = dbs[i % N_COPIES].match_hamming(h_queries[i % 4], THR, RATIO)
+        ts = time.perf_counter()
+        out = dbs[i % N_COPIES].match_hamming(h_queries[i % 4], THR, RATIO)   # returns after the D2H of the matches
+        step_s.append(time.perf_counter() - ts)
         d2h_db += out[0].nbytes + 4 + sum(o.nbytes for o in out[1:])
     barrier()
-    dt_db = max_over_ranks(time.perf_counter() - t0)
-    e2e_db_gp = pairs * world * db_steps / dt_db / 1e9
+    dt_db_mean = max_over_ranks(time.perf_counter() - t0) / db_steps
+    dt_db = max_over_ranks(float(np.median(step_s)))      # per-request median: robust against host scheduling noise
+    e2e_db_gp = pairs * world / dt_db / 1e9
     for db in dbs:
         db.close()
     alg_bytes = 32 * N_KF * N_FEAT + 32 * N_FEAT + 8 * N_KF * N_FEAT + 4 * N_KF   # 32 Nt + 32 Nq + outputs
@@ -446,7 +450,8 @@ def run_ours(args):
                    "l2_policy": f"{N_COPIES} map copies (256 MB > 126 MB L2) rotated per step",
                    "parallelism": f"map sharded by keyframe x{world}, no data-path collective"},
         "e2e": {"value": e2e_db_gp, "unit": "Gpairs/s", "h2d_bytes_per_step": int(h_queries[0].nbytes),
-                "d2h_bytes_per_step": int(d2h_db // db_steps), "steps": db_steps, "ms_per_step": dt_db / db_steps * 1e3,
+                "d2h_bytes_per_step": int(d2h_db // db_steps), "steps": db_steps, "ms_per_step": dt_db * 1e3,
+                "mean_ms_per_step": dt_db_mean * 1e3, "timing": "median over the requests of the wall time of one complete call (each call returns after its D2H)",
                 "api": "cvb_db_match_hamming: host query in, per-keyframe match counts + compacted accepted matches out; the "
                        "map's descriptors were appended once with cvb_db_append (outside the timed region) and stay in HBM; "
                        f"{N_COPIES} databases (256 MB > L2) rotated per step",
