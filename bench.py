@@ -441,6 +441,26 @@ def run_ours(args):
         sift = {"metric": "match_l2_gpairs_per_sec", "value": n_kf5 * nf5 * nf5 / (ms_l2 * 1e-3) / 1e9, "unit": "Gpairs/s",
                 "ms_per_step": ms_l2, "config": "C5 shard: 300 SIFT queries vs 10000 KF x 300 rows x 128-d u8 (384 MB), k=2, exact brute force"}
         del ts
+    # Landmark::ComputeDescriptor batched over the C3 map's landmarks: 100k landmarks x 8 observers
+    lmdesc = None
+    if rank == 0:
+        n_lm7, per7 = 100_000, 8
+        c7 = torch.randint(0, 256, (n_lm7 * per7, 32), dtype=torch.uint8, device=dev, generator=g)
+        p7 = torch.arange(0, n_lm7 * per7 + 1, per7, dtype=torch.int32, device=dev)
+        for _ in range(3):
+            M.landmark_descriptors(ctx, c7, p7)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(10):
+            M.landmark_descriptors(ctx, c7, p7)
+        e1.record(); torch.cuda.synchronize()
+        ms7 = e0.elapsed_time(e1) / 10
+        b7 = n_lm7 * per7 * 32 + n_lm7 * 36 + (n_lm7 + 1) * 4
+        lmdesc = {"metric": "landmark_descriptors_per_sec", "value": n_lm7 / (ms7 * 1e-3), "unit": "landmarks/s", "ms_per_step": ms7,
+                  "config": "Landmark::ComputeDescriptor for 100000 landmarks x 8 observers (25.6 MB of descriptors), one launch",
+                  "roofline": {"bound": "hbm", "achieved": b7 / (ms7 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": b7 / (ms7 * 1e-3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": b7,
+                               "note": "32 B per observation read once + 36 B per landmark written; includes the clone of the old descriptors"}}
+        del c7
     match = {
         "metric": "match_gpairs_per_sec", "value": gp, "unit": "Gpairs/s", "ms_per_step": ms_step, "steps": m_steps,
         "scaling": "weak", "dtype": "u8",
@@ -472,6 +492,7 @@ def run_ours(args):
                                             "int_pipe_frac": (8 * pairs / (ms_popc * 1e-3) / 1e9) / popc_peak if popc_peak else None,
                                             "peak_gpopc_s": popc_peak, "note": "previous formulation: 94 % of the POPC-pipe roofline"}},
         "sift_l2": sift,
+        "landmark_descriptor": lmdesc,
     }
 
     line = {

@@ -782,6 +782,68 @@ int stage_inputs(cvb_ctx* ctx, const void* q, size_t qbytes, const void* t, size
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
+// Landmark::ComputeDescriptor (src/covins_backend/landmark_be.cpp:49-92), batched: one warp per landmark.  For every
+// candidate row i the lanes hold the Hamming distances d(i, j) (j = lane, lane + 32, …; d(i,i) = 0 as in the reference's
+// matrix), the median = the (int)(0.5 (n-1))-th smallest is found by a 9-step bisection over the value range [0,256]
+// with ballot counts (no sort), and the first row with the strictly smallest median wins (:86-89).  HBM-bound in the
+// batch (32 B per observation, read once into L1/registers); n <= 32*kLmCap candidates keep their distances in
+// registers, longer lists recompute them inside the bisection.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLmCap = 8;
+__device__ __forceinline__ int ham256(const uint4& a0, const uint4& a1, const uint8_t* __restrict__ b) {
+  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(b)), b1 = __ldg(reinterpret_cast<const uint4*>(b) + 1);
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) +
+         __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+__global__ void __launch_bounds__(128) lm_descriptor_kernel(const uint8_t* __restrict__ cand, const int32_t* __restrict__ lm_ptr,
+                                                            int n_lm, int32_t* __restrict__ best_idx,
+                                                            uint8_t* __restrict__ out_desc) {
+  const int l = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (l >= n_lm) return;
+  const int o0 = lm_ptr[l], n = lm_ptr[l + 1] - o0;
+  if (n <= 0) {
+    if (lane == 0) best_idx[l] = -1;
+    return;
+  }
+  const uint8_t* D = cand + (size_t)o0 * 32;
+  const int kth = (int)(0.5 * (n - 1));          // index into the sorted row, as the reference computes it
+  const bool in_regs = n <= 32 * kLmCap;
+  int best_med = INT_MAX, best = -1;
+  for (int i = 0; i < n; i++) {
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(D + (size_t)i * 32));
+    const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(D + (size_t)i * 32) + 1);
+    int d[kLmCap];
+    if (in_regs) {
+#pragma unroll
+      for (int c = 0; c < kLmCap; c++) {
+        const int j = lane + 32 * c;
+        d[c] = j < n ? ham256(a0, a1, D + (size_t)j * 32) : INT_MAX;   // j == i gives 0, the matrix diagonal
+      }
+    }
+    // smallest v with #{j : d(i,j) <= v} >= kth + 1
+    int lo = 0, hi = 256;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      int cnt = 0;
+      if (in_regs) {
+#pragma unroll
+        for (int c = 0; c < kLmCap; c++) cnt += __popc(__ballot_sync(0xffffffffu, d[c] <= mid));
+      } else {
+        for (int j0 = 0; j0 < n; j0 += 32) {
+          const int j = j0 + lane;
+          const bool le = j < n && ham256(a0, a1, D + (size_t)j * 32) <= mid;
+          cnt += __popc(__ballot_sync(0xffffffffu, le));
+        }
+      }
+      if (cnt >= kth + 1) hi = mid; else lo = mid + 1;
+    }
+    if (lo < best_med) { best_med = lo; best = i; }
+  }
+  if (lane == 0) best_idx[l] = best;
+  if (lane < 8) reinterpret_cast<uint32_t*>(out_desc + (size_t)l * 32)[lane] = __ldg(reinterpret_cast<const uint32_t*>(D + (size_t)best * 32) + lane);
+}
+
+// ------------------------------------------------------------------------------------------------
 // C-ABI
 // ------------------------------------------------------------------------------------------------
 extern "C" {
@@ -871,6 +933,43 @@ int cvb_knn_merge_shards_dev(cvb_ctx* ctx, const int32_t* d_idx_all, const void*
       d_idx_all, (const int32_t*)d_dist_all, d_row_offset, n_shards, (long long)n, k, d_idx_out, (int32_t*)d_dist_out,
       empty_key);
   CVB_CHECK_LAUNCH(ctx);
+  return CVB_OK;
+}
+
+int cvb_landmark_descriptor_batch_dev(cvb_ctx* ctx, const uint8_t* d_cand, const int32_t* d_lm_ptr, int n_lm,
+                                      int32_t* d_best_idx, uint8_t* d_out_desc, void* stream) {
+  if (!ctx) return CVB_ERR_INVALID;
+  CVB_REQUIRE(ctx, n_lm >= 0 && (n_lm == 0 || (d_cand && d_lm_ptr && d_best_idx && d_out_desc)), "landmark_descriptor: bad arguments");
+  CVB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_cand) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out_desc) & 3) == 0,
+              "landmark_descriptor: misaligned buffers");
+  if (n_lm == 0) return CVB_OK;
+  lm_descriptor_kernel<<<(unsigned)(((size_t)n_lm * 32 + 127) / 128), 128, 0, cvb_stream(ctx, stream)>>>(d_cand, d_lm_ptr, n_lm,
+                                                                                                       d_best_idx, d_out_desc);
+  CVB_CHECK_LAUNCH(ctx);
+  return CVB_OK;
+}
+
+int cvb_landmark_descriptor_batch(cvb_ctx* ctx, const uint8_t* cand, const int32_t* lm_ptr, int n_lm, int32_t* best_idx,
+                                  uint8_t* out_desc) {
+  if (!ctx) return CVB_ERR_INVALID;
+  CVB_REQUIRE(ctx, n_lm >= 0 && (n_lm == 0 || (lm_ptr && best_idx && out_desc)), "landmark_descriptor: bad arguments");
+  if (n_lm == 0) return CVB_OK;
+  const size_t rows = (size_t)lm_ptr[n_lm];
+  CVB_REQUIRE(ctx, lm_ptr[0] == 0 && (rows == 0 || cand), "landmark_descriptor: bad lm_ptr / null candidates");
+  uint8_t* d_c = (uint8_t*)cvb_ws(ctx, WS_T, rows * 32);
+  int32_t* d_p = (int32_t*)cvb_ws(ctx, WS_SEG, sizeof(int32_t) * ((size_t)n_lm + 1));
+  int32_t* d_b = (int32_t*)cvb_ws(ctx, WS_OUT0, sizeof(int32_t) * (size_t)n_lm);
+  uint8_t* d_o = (uint8_t*)cvb_ws(ctx, WS_OUT1, (size_t)n_lm * 32);
+  if (!d_c || !d_p || !d_b || !d_o) return CVB_ERR_CUDA;
+  if (rows) CVB_CUDA(ctx, cudaMemcpyAsync(d_c, cand, rows * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CVB_CUDA(ctx, cudaMemcpyAsync(d_p, lm_ptr, sizeof(int32_t) * ((size_t)n_lm + 1), cudaMemcpyHostToDevice, ctx->stream));
+  // landmarks without candidates keep their descriptor (the reference returns early): pass the caller's bytes through
+  CVB_CUDA(ctx, cudaMemcpyAsync(d_o, out_desc, (size_t)n_lm * 32, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = cvb_landmark_descriptor_batch_dev(ctx, d_c, d_p, n_lm, d_b, d_o, nullptr);
+  if (rc) return rc;
+  CVB_CUDA(ctx, cudaMemcpyAsync(best_idx, d_b, sizeof(int32_t) * (size_t)n_lm, cudaMemcpyDeviceToHost, ctx->stream));
+  CVB_CUDA(ctx, cudaMemcpyAsync(out_desc, d_o, (size_t)n_lm * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return CVB_OK;
 }
 

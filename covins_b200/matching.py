@@ -281,6 +281,26 @@ def landmark_match(ctx: Context, A, skipA, B, skipB, seg_ptr=None, thr: float = 
     return out
 
 
+def landmark_descriptors(ctx: Context, cand, lm_ptr, old_desc=None):
+    """Landmark::ComputeDescriptor for a batch of landmarks (landmark_be.cpp:49-92): cand u8 [rows, 32] = descriptor rows
+    of the valid observers of every landmark, concatenated; lm_ptr i32 [n_lm+1].  → (best_idx [n_lm] i32 (-1 = landmark
+    without observers), desc [n_lm, 32] u8; rows of landmarks without observers keep old_desc (zeros if not given))."""
+    if _is_torch(cand):
+        import torch
+        n = lm_ptr.shape[0] - 1
+        best = torch.empty((n,), dtype=torch.int32, device=cand.device)
+        out = old_desc.clone() if old_desc is not None else torch.zeros((n, 32), dtype=torch.uint8, device=cand.device)
+        ctx.check(lib().cvb_landmark_descriptor_batch_dev(ctx.handle, _ptr(cand), _ptr(lm_ptr), n, _ptr(best), _ptr(out),
+                                                          _torch_stream()))
+        return best, out
+    cand = _np(cand, np.uint8).reshape(-1, 32); lm_ptr = np.ascontiguousarray(lm_ptr, np.int32)
+    n = len(lm_ptr) - 1
+    best = np.empty(n, np.int32)
+    out = np.ascontiguousarray(old_desc, np.uint8).copy() if old_desc is not None else np.zeros((n, 32), np.uint8)
+    ctx.check(lib().cvb_landmark_descriptor_batch(ctx.handle, _ptr(cand), _ptr(lm_ptr), n, _ptr(best), _ptr(out)))
+    return best, out
+
+
 def microbench_popc(ctx: Context, iters: int = 20000) -> float:
     v = C.c_double()
     ctx.check(lib().cvb_microbench_popc(ctx.handle, iters, C.byref(v)))

@@ -142,6 +142,20 @@ CVB_API int cvb_knn_merge_shards_dev(cvb_ctx* ctx, const int32_t* d_idx_all, con
                                      const int32_t* d_row_offset, int n_shards, int64_t n, int k, int32_t* d_idx_out,
                                      void* d_dist_out, void* stream);
 
+/*
+ * Landmark::ComputeDescriptor (src/covins_backend/landmark_be.cpp:49-92), batched over landmarks (SURVEY §8a M7;
+ * called for every landmark of a new keyframe, communicator_be.cpp:190-198, and after map maintenance).
+ * cand: the 32-byte descriptor rows of the valid observing keyframes of every landmark (kf->descriptors_.row(feat_idx),
+ * :57-64), concatenated in the landmark's observation order; lm_ptr[n_lm+1] row offsets.  Per landmark the row with the
+ * least median Hamming distance to all rows (zero diagonal included; median = sorted[(int)(0.5 (n-1))]; first row
+ * wins ties, :80-90): best_idx[l] = landmark-local row or -1 if the landmark has no candidate, out_desc[l] = its 32
+ * bytes (left as passed in when -1: the reference returns early and keeps the old descriptor, :53-55,65-67).
+ */
+CVB_API int cvb_landmark_descriptor_batch(cvb_ctx* ctx, const uint8_t* cand, const int32_t* lm_ptr, int n_lm,
+                                          int32_t* best_idx, uint8_t* out_desc);
+CVB_API int cvb_landmark_descriptor_batch_dev(cvb_ctx* ctx, const uint8_t* d_cand, const int32_t* d_lm_ptr, int n_lm,
+                                              int32_t* d_best_idx, uint8_t* d_out_desc, void* stream);
+
 /* f32 [rows][dim] (device) → u8 [rows][dim] (device); *d_bad (int32, device) is set to 1 if any value is
  * not an integer in [0,255]. */
 CVB_API int cvb_quantize_u8_dev(cvb_ctx* ctx, const float* d_src, int64_t n, uint8_t* d_dst, int32_t* d_bad,

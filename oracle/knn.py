@@ -121,3 +121,12 @@ def merge_shards(idx_all, dist_all, row_offset, k):
     empty = np.iinfo(np.int32).max if np.issubdtype(dist_all.dtype, np.integer) else np.finfo(np.float32).max
     od = np.where(oi >= 0, od, empty).astype(dist_all.dtype)
     return oi.astype(np.int32), od
+
+
+def landmark_descriptor(cand, lm_ptr):
+    """Landmark::ComputeDescriptor batched (landmark_be.cpp:49-92) → (best_idx [n_lm] i32, desc [n_lm, 32] u8)."""
+    cand = np.ascontiguousarray(cand, np.uint8).reshape(-1, 32); lm_ptr = np.ascontiguousarray(lm_ptr, np.int32)
+    n = len(lm_ptr) - 1
+    best = np.full(n, -1, np.int32); out = np.zeros((n, 32), np.uint8)
+    lib().ora_landmark_descriptor(_p(cand, C.c_uint8), _p(lm_ptr, C.c_int32), n, _p(best, C.c_int32), _p(out, C.c_uint8))
+    return best, out

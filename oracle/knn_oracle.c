@@ -31,6 +31,8 @@
  *                        (all three are float: include/covins/covins_base/config_backend.hpp:119-120).
  *   ora_hamming256       FeatureMatcher::DescriptorDistanceHamming, src/covins_backend/feature_matcher_be.cpp:49-64
  *                        (8 x u32 SWAR popcount, hard-coded 256 bit).
+ *   ora_landmark_descriptor  Landmark::ComputeDescriptor, src/covins_backend/landmark_be.cpp:49-92 (representative
+ *                        descriptor = the observation with the least median Hamming distance to all observations).
  *   ora_landmark_match   estd2::DenseMatcher::match<LandmarkMatchingAlgorithm> as used at
  *                        src/covins_backend/placerec_be.cpp:85-90:
  *                          distance()            include/covins/matcher/LandmarkMatchingAlgorithm.h:103-114
@@ -317,5 +319,51 @@ ORA_API void ora_landmark_match_batch(const uint8_t *A, const uint8_t *skipA, in
     int off = seg_ptr[s], nB = seg_ptr[s + 1] - seg_ptr[s];
     n_out[s] = ora_landmark_match(A, skipA, nA, B + (size_t)off * 32, skipB ? skipB + off : NULL, nB, thr,
                                   numBest, outA + off, outB + off, outD + off, NULL, NULL);
+  }
+}
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Landmark::ComputeDescriptor (src/covins_backend/landmark_be.cpp:49-92), batched over landmarks.
+ * cand: the descriptor rows (32 B) of the valid observing keyframes of every landmark, concatenated in
+ * the landmark's observation order (:57-64; canonical order = keyframe idpair order);
+ * lm_ptr[n_lm+1] row offsets.  Per landmark: the full num_desc x num_desc Hamming matrix with a zero
+ * diagonal (:70-78), per row the sorted distances and median = sorted[(int)(0.5 * (num_desc - 1))]
+ * (:84-85), the FIRST row with the strictly smallest median wins (:86-89).  best_idx[l] = that row
+ * (landmark-local) or -1 for a landmark without candidates (the reference returns early and keeps the
+ * old descriptor, :53-55,65-67); out_desc[l] = its 32 bytes (untouched when -1).
+ * ------------------------------------------------------------------------------------------------ */
+static int cmp_double(const void *a, const void *b) {
+  double x = *(const double *)a, y = *(const double *)b;
+  return (x > y) - (x < y);
+}
+ORA_API void ora_landmark_descriptor(const uint8_t *cand, const int32_t *lm_ptr, int n_lm, int32_t *best_idx,
+                                     uint8_t *out_desc) {
+  for (int l = 0; l < n_lm; l++) {
+    const int n = lm_ptr[l + 1] - lm_ptr[l];
+    best_idx[l] = -1;
+    if (n <= 0) continue;
+    const uint8_t *D = cand + (size_t)lm_ptr[l] * 32;
+    double *dist = (double *)malloc(sizeof(double) * (size_t)n * n);
+    double *row = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+      dist[(size_t)i * n + i] = 0;
+      for (int j = i + 1; j < n; j++) {
+        int d = 0;
+        for (int b = 0; b < 32; b++) d += __builtin_popcount((unsigned)(D[(size_t)i * 32 + b] ^ D[(size_t)j * 32 + b]));
+        dist[(size_t)i * n + j] = dist[(size_t)j * n + i] = (double)d;
+      }
+    }
+    double best_median = (double)INT_MAX;
+    int best = -1;
+    for (int i = 0; i < n; i++) {
+      memcpy(row, dist + (size_t)i * n, sizeof(double) * (size_t)n);
+      qsort(row, (size_t)n, sizeof(double), cmp_double);
+      const double median = row[(int)(0.5 * (n - 1))];
+      if (median < best_median) { best_median = median; best = i; }
+    }
+    best_idx[l] = best;
+    memcpy(out_desc + (size_t)l * 32, D + (size_t)best * 32, 32);
+    free(dist); free(row);
   }
 }

@@ -257,3 +257,23 @@ def test_mapwide_sharded_knn_merge_equals_single_call(ctx, metric):
     assert torch.equal(mi, ri[0]) and torch.equal(md, rd[0])
     oi, od = ora.merge_shards(torch.stack(li_all).cpu().numpy(), torch.stack(ld_all).cpu().numpy(), cuts[:-1], k)
     assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(md.cpu().numpy(), od)
+
+
+def test_landmark_descriptor_batch_vs_oracle(ctx):
+    """K-M7 Landmark::ComputeDescriptor batched (landmark_be.cpp:49-92): bit-exact vs the oracle for landmark sizes
+    0..300 (register path, > 256-observer recompute path), host and device entry points, old descriptors kept for
+    landmarks without observers."""
+    import torch
+    from test_oracle_knn import _lm_desc_case
+    rng = np.random.default_rng(9)
+    sizes = [0, 1, 2, 3, 8, 31, 32, 33, 64, 100, 0, 256, 257, 300] + list(rng.integers(2, 20, 400))
+    cand, lm_ptr = _lm_desc_case(12, sizes)
+    old = rng.integers(0, 256, (len(sizes), 32), dtype=np.uint8)
+    rb, rd = ora.landmark_descriptor(cand, lm_ptr)
+    rd[rb < 0] = old[rb < 0]
+    b, d = M.landmark_descriptors(ctx, cand, lm_ptr, old)
+    assert np.array_equal(b, rb) and np.array_equal(d, rd)
+    dev = torch.device("cuda", 0)
+    tb, td = M.landmark_descriptors(ctx, torch.from_numpy(cand).to(dev), torch.from_numpy(lm_ptr).to(dev), torch.from_numpy(old).to(dev))
+    torch.cuda.synchronize()
+    assert np.array_equal(tb.cpu().numpy(), rb) and np.array_equal(td.cpu().numpy(), rd)

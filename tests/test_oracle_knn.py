@@ -114,3 +114,37 @@ def test_landmark_match_oracle_vs_python_restatement(seed):
     # invariants: one-to-one, no skipped keypoint is ever matched, every distance < 50
     assert len(set(oa.tolist())) == len(oa) and len(set(ob.tolist())) == len(ob)
     assert not skipA[oa].any() and not skipB[ob].any() and (od < 50).all()
+
+
+def _lm_desc_case(seed, sizes):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (7, 32), dtype=np.uint8)
+    rows = []
+    for n in sizes:
+        d = base[rng.integers(0, 7, n)].copy()
+        flip = rng.random(d.shape) < 0.08
+        d[flip] ^= rng.integers(1, 256, int(flip.sum()), dtype=np.uint8)
+        rows.append(d)
+    lm_ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    return (np.concatenate(rows) if sum(sizes) else np.zeros((0, 32), np.uint8)), lm_ptr
+
+
+def test_landmark_descriptor_oracle_vs_independent_restatement():
+    """Landmark::ComputeDescriptor (landmark_be.cpp:49-92): C oracle vs a plain numpy restatement (full distance matrix,
+    per-row sort, median index (int)(0.5 (n-1)), first strict minimum), incl. empty / single / duplicated observers."""
+    sizes = [0, 1, 2, 3, 8, 8, 33, 5, 0, 64, 2]
+    cand, lm_ptr = _lm_desc_case(3, sizes)
+    cand[lm_ptr[4]:lm_ptr[4] + 8] = cand[lm_ptr[4]]            # all observers identical → row 0 wins
+    best, desc = ora.landmark_descriptor(cand, lm_ptr)
+    bits = np.unpackbits(cand, axis=1).astype(np.int32)
+    for l, n in enumerate(sizes):
+        if n == 0:
+            assert best[l] == -1
+            continue
+        B = bits[lm_ptr[l]:lm_ptr[l + 1]]
+        D = (B[:, None, :] != B[None, :, :]).sum(-1).astype(np.float64)
+        med = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
+        ref = int(np.argmin(med))                              # argmin returns the first minimum
+        assert best[l] == ref, (l, n)
+        assert np.array_equal(desc[l], cand[lm_ptr[l] + ref])
+    assert best[4] == 0
