@@ -808,6 +808,7 @@ __global__ void __launch_bounds__(128) lm_descriptor_kernel(const uint8_t* __res
   const uint8_t* D = cand + (size_t)o0 * 32;
   const int kth = (int)(0.5 * (n - 1));          // index into the sorted row, as the reference computes it
   const bool in_regs = n <= 32 * kLmCap;
+  const int nc = (n + 31) >> 5;                  // 32-wide chunks of candidates actually present (warp-uniform)
   int best_med = INT_MAX, best = -1;
   for (int i = 0; i < n; i++) {
     const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(D + (size_t)i * 32));
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(128) lm_descriptor_kernel(const uint8_t* __res
 #pragma unroll
       for (int c = 0; c < kLmCap; c++) {
         const int j = lane + 32 * c;
-        d[c] = j < n ? ham256(a0, a1, D + (size_t)j * 32) : INT_MAX;   // j == i gives 0, the matrix diagonal
+        d[c] = (c < nc && j < n) ? ham256(a0, a1, D + (size_t)j * 32) : INT_MAX;   // j == i gives 0, the matrix diagonal
       }
     }
     // smallest v with #{j : d(i,j) <= v} >= kth + 1
@@ -827,7 +828,8 @@ __global__ void __launch_bounds__(128) lm_descriptor_kernel(const uint8_t* __res
       int cnt = 0;
       if (in_regs) {
 #pragma unroll
-        for (int c = 0; c < kLmCap; c++) cnt += __popc(__ballot_sync(0xffffffffu, d[c] <= mid));
+        for (int c = 0; c < kLmCap; c++)
+          if (c < nc) cnt += __popc(__ballot_sync(0xffffffffu, d[c] <= mid));
       } else {
         for (int j0 = 0; j0 < n; j0 += 32) {
           const int j = j0 + lane;
