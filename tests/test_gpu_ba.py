@@ -165,3 +165,21 @@ def test_pgo_c2_size_properties(ctx):
     costs = np.asarray(a["cost"])
     assert a["final_cost"] <= a["initial_cost"] and np.all(np.diff(costs) <= 1e-9 * costs[0])
     assert np.all(np.isfinite(a["pose"])) and np.allclose(np.linalg.norm(a["pose"][:, :4], axis=1), 1.0, atol=1e-12)
+
+
+def test_gba_from_serialized_map_equals_flat_problem(ctx, tmp_path):
+    """"Results on the same serialized map": write the synthetic map in the COVINS on-disk format (mapio),
+    read it back and solve — the states must agree with solving the in-memory flat problem (landmarks with < 2
+    observations are not stored by the format and do not take part in either solve)."""
+    from covins_b200 import mapio
+    p = synth_map.make_config("small")
+    d = str(tmp_path / "map")
+    mapio.write_map(d, p)
+    q = mapio.read_map(d)
+    a = O.solve(ctx, p, 5, visual_only=False)
+    b = O.solve(ctx, q, 5, visual_only=False)
+    keep = np.diff(p["lm_obs_ptr"]) >= 2
+    assert a["steps"] == b["steps"]
+    assert _rel(b["pose"][:, 4:], a["pose"][:, 4:]) < 1e-8 and _rel(b["speedbias"], a["speedbias"]) < 1e-8
+    inc = a["lm_owner"][keep] >= 0
+    assert _rel(b["lm"][inc], a["lm"][keep][inc]) < 1e-7
