@@ -8,7 +8,8 @@ synthetic map (config C3: 2000 KF / 100k LM / 800k obs; 1000 ORB features per KF
 of the hot path: one outer trust-region iteration of the visual-inertial global BA (linearise → Schur → Cholesky →
 dogleg → candidate cost) and one query keyframe matched against every keyframe of the rank's map shard (2 Gpairs,
 fused k-NN + ratio filter).  The two legs are timed separately; the JSON line carries the GBA rate as `value`
-and the matching rate under `match` (each with its own e2e / roofline / cpu_baseline).
+and the matching rate under `match` (each with its own e2e / roofline / cpu_baseline); `pgo` carries the pose-graph
+optimisation rate on the same map, `match.sift_l2` / `match.landmark_descriptor` the SIFT and ComputeDescriptor kernels.
 """
 from __future__ import annotations
 
