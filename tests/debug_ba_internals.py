@@ -1,6 +1,6 @@
 """Development aid (run under gpurun): compare the CUDA engine's first-iteration internals with the oracle's."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # checker-side development aid: lives under tests/ because it uses the oracle
 import numpy as np, scipy.sparse as sp, math
 import covins_b200
 from covins_b200 import optimization as O, synth_map
