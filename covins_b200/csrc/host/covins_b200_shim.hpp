@@ -614,4 +614,65 @@ inline std::vector<Matches> LandmarkMatchCandidates(Context& ctx, const uint8_t*
   return out;
 }
 
+// Resident-map descriptor database (cvb_db_*): the ORB descriptors of the map's keyframes live in HBM; the candidate
+// loop of PlaceRecognitionG::ComputeSE3 (placerec_gen_be.cpp:60-135) becomes one call per query keyframe.  The database
+// index of a keyframe is its insertion order; keep it next to the keyframe (e.g. std::map<idpair, int>).
+class DescriptorDatabase {
+ public:
+  explicit DescriptorDatabase(Context& ctx) : ctx_(ctx) { ctx_.check(cvb_db_create(ctx_.get(), 32, &db_), "cvb_db_create"); }
+  ~DescriptorDatabase() { if (db_) cvb_db_destroy(ctx_.get(), db_); }
+  DescriptorDatabase(const DescriptorDatabase&) = delete;
+  DescriptorDatabase& operator=(const DescriptorDatabase&) = delete;
+  // descriptors: kf->descriptors_add_ (CV_8U, continuous, rows x 32; keyframe_be.cpp:103,137) → returns the database index
+  int AddKeyframe(const uint8_t* descriptors, int rows) {
+    const int32_t r = rows;
+    ctx_.check(cvb_db_append(ctx_.get(), db_, descriptors, &r, 1), "cvb_db_append");
+    return n_kf_++;
+  }
+  int size() const { return n_kf_; }
+  // knnMatch(k=2) + distance/ratio filter of the query keyframe against EVERY keyframe of the database:
+  // result[db index] == the reference's img_matches for that candidate (accepted queries ascending, :102-114)
+  std::vector<Matches> MatchAll(const uint8_t* query, int n_query, const OptParams& P) {
+    std::vector<int32_t> nm(n_kf_ > 0 ? n_kf_ : 1);
+    if (cap_ == 0) cap_ = 4096;
+    for (;;) {
+      m_kf_.resize(cap_); m_q_.resize(cap_); m_t_.resize(cap_); m_d_.resize(cap_);
+      int32_t total = 0;
+      ctx_.check(cvb_db_match_hamming(ctx_.get(), db_, query, n_query, P.img_match_thres, P.ratio_thres, nm.data(), m_kf_.data(),
+                                      m_q_.data(), m_t_.data(), m_d_.data(), cap_, &total),
+                 "cvb_db_match_hamming");
+      if (total <= cap_) {
+        std::vector<Matches> out(n_kf_);
+        for (int i = 0; i < total; i++) out[m_kf_[i]].push_back(Match{(size_t)m_q_[i], (size_t)m_t_[i], m_d_[i]});
+        return out;
+      }
+      cap_ = total + total / 4 + 16;
+    }
+  }
+
+ private:
+  Context& ctx_;
+  cvb_db* db_ = nullptr;
+  int n_kf_ = 0, cap_ = 0;
+  std::vector<int32_t> m_kf_, m_q_, m_t_;
+  std::vector<float> m_d_;
+};
+
+// Landmark::ComputeDescriptor (landmark_be.cpp:49-92) for a batch of landmarks: cand[l] = the descriptor rows
+// (kf->descriptors_.row(feat_idx), 32 bytes each) of the landmark's valid observers in observation order.
+// Returns per landmark the index of the chosen observer (-1: no observer, descriptor unchanged) and writes the chosen
+// descriptor to out_desc[l] (32 bytes each; pass the current descriptors in, as the reference keeps them on early return).
+inline std::vector<int> ComputeLandmarkDescriptors(Context& ctx, const std::vector<std::vector<const uint8_t*>>& cand,
+                                                   uint8_t* out_desc) {
+  const int n_lm = (int)cand.size();
+  std::vector<int32_t> ptr(n_lm + 1, 0);
+  for (int l = 0; l < n_lm; l++) ptr[l + 1] = ptr[l] + (int32_t)cand[l].size();
+  std::vector<uint8_t> rows((size_t)ptr[n_lm] * 32 + 32);
+  for (int l = 0; l < n_lm; l++)
+    for (size_t j = 0; j < cand[l].size(); j++) std::copy(cand[l][j], cand[l][j] + 32, rows.begin() + ((size_t)ptr[l] + j) * 32);
+  std::vector<int32_t> best(n_lm > 0 ? n_lm : 1);
+  ctx.check(cvb_landmark_descriptor_batch(ctx.get(), rows.data(), ptr.data(), n_lm, best.data(), out_desc), "cvb_landmark_descriptor_batch");
+  return std::vector<int>(best.begin(), best.begin() + n_lm);
+}
+
 }  // namespace covins_b200

@@ -53,6 +53,26 @@ int main(int argc, char** argv) {
       for (auto& m : all[s]) { out.push_back((int32_t)m.idxA); out.push_back((int32_t)m.idxB); out.push_back((int32_t)m.distance); }
     }
     wr(dir, "match_out", out);
+    // resident-map database: append the candidates one by one, match the same query against all of them
+    covins_b200::DescriptorDatabase db(ctx);
+    for (int s = 0; s < n_seg; s++)
+      if (db.AddKeyframe(desc[s], rows[s]) != s) return 3;
+    auto all_db = db.MatchAll(q.data(), nq, P);
+    std::vector<int32_t> out_db;
+    for (int s = 0; s < n_seg; s++) {
+      out_db.push_back((int32_t)all_db[s].size());
+      for (auto& m : all_db[s]) { out_db.push_back((int32_t)m.idxA); out_db.push_back((int32_t)m.idxB); out_db.push_back((int32_t)m.distance); }
+    }
+    wr(dir, "match_db_out", out_db);
+    // Landmark::ComputeDescriptor batched: every candidate segment plays the observers of one landmark (first 9 rows)
+    std::vector<std::vector<const uint8_t*>> cand(n_seg);
+    for (int s = 0; s < n_seg; s++)
+      for (int j = 0; j < std::min(rows[s], 9); j++) cand[s].push_back(desc[s] + (size_t)j * 32);
+    std::vector<uint8_t> od((size_t)n_seg * 32, 0xAB);
+    auto best = covins_b200::ComputeLandmarkDescriptors(ctx, cand, od.data());
+    std::vector<int32_t> out_lm(best.begin(), best.end());
+    for (auto b : od) out_lm.push_back((int32_t)b);
+    wr(dir, "lmdesc_out", out_lm);
     return 0;
   }
   // ---- build the mock map from the flat arrays ----

@@ -107,3 +107,22 @@ def test_shim_match_candidates_equals_oracle(tmp_path):
         q = np.flatnonzero(mt[s] >= 0)
         got = out[pos:pos + 3 * n].reshape(-1, 3); pos += 3 * n
         assert np.array_equal(got[:, 0], q) and np.array_equal(got[:, 1], mt[s][q]) and np.array_equal(got[:, 2], md[s][q].astype(np.int32))
+    # the resident-map database (covins_b200::DescriptorDatabase) gives the same img_matches per candidate
+    out_db = np.fromfile(tmp_path / "match_db_out.bin", dtype=np.int32)
+    pos = 0
+    for s in range(len(lens)):
+        n = out_db[pos]; pos += 1
+        q = np.flatnonzero(mt[s] >= 0)
+        assert n == cnt[s]
+        got = out_db[pos:pos + 3 * n].reshape(-1, 3); pos += 3 * n
+        assert np.array_equal(got[:, 0], q) and np.array_equal(got[:, 1], mt[s][q]) and np.array_equal(got[:, 2], md[s][q].astype(np.int32))
+    assert pos == len(out_db)
+    # covins_b200::ComputeLandmarkDescriptors: the first (up to) 9 rows of every candidate as one landmark's observers
+    out_lm = np.fromfile(tmp_path / "lmdesc_out.bin", dtype=np.int32)
+    sizes = [min(l, 9) for l in lens]
+    cand = np.concatenate([t[seg[i]:seg[i] + n] for i, n in enumerate(sizes)])
+    rb, rd = ora.landmark_descriptor(cand, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32))
+    assert np.array_equal(out_lm[:len(lens)], rb)
+    got_d = out_lm[len(lens):].astype(np.uint8).reshape(len(lens), 32)
+    for i in range(len(lens)):
+        assert np.array_equal(got_d[i], rd[i] if rb[i] >= 0 else np.full(32, 0xAB, np.uint8))
