@@ -59,3 +59,16 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(covins_b200.CvbError):
         covins_b200.Context(0)
+
+
+def test_shard_rows_cuts_on_keyframe_boundaries():
+    """host logic of the map-wide sharded k-NN: contiguous, exhaustive, keyframe-aligned row ranges"""
+    import numpy as np
+    from covins_b200 import matching as M
+    seg = np.array([0, 10, 10, 250, 600, 1000, 1001, 4000], np.int64)
+    for world in (1, 2, 3, 8, 16):
+        cuts = M.shard_rows(4000, world, seg)
+        assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == 4000
+        assert np.all(np.diff(cuts) >= 0) and set(cuts.tolist()) <= set(seg.tolist())
+    cuts = M.shard_rows(10, 4)                       # without keyframe boundaries: even split
+    assert cuts.tolist() == [0, 2, 5, 7, 10]
