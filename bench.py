@@ -482,7 +482,8 @@ def run_ours(args):
                                       "api": "cvb_match_hamming_batch: the whole 64 MB map re-uploaded from host memory on "
                                              "every call and the dense [n_kf][nq] result matrices downloaded (PCIe-bound)"}},
         "gpu_launches": int(match_launches),
-        "roofline": {"bound": "tensor", "achieved": tops, "peak": i8_peak, "unit": "TOP/s", "frac": tops / i8_peak, "traffic": None,
+        "roofline": {"bound": "tensor", "achieved": tops, "peak": i8_peak, "unit": "TOP/s", "frac": tops / i8_peak, "traffic": 67.5e6,
+                     "traffic_note": "bytes per launch from profiles/r01_ncu_summary.md §2 (ncu --set full of this launch: dram read 64.1 MB + write 3.4 MB; algorithmic 80 MB incl. 16 MB of results still in L2 at capture end)",
                      "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate); no measured int8 figure exists",
                      "kernel": "cvb_tc::tc_scan_kernel<TcHamming,2> (tcgen05.mma kind::i8, TMEM accumulators, fused top-2 + ratio filter)",
                      "note": "ncu: tensor pipe ~30 % active, ALU pipe ~60 %: the per-pair integer min/max selection in the epilogue "
@@ -517,7 +518,8 @@ def run_ours(args):
         "device_ms_per_step": dev_ms / args.steps,
         "final_cost": res["final_cost"], "initial_cost": res["initial_cost"],
         "roofline": {"bound": "tensor", "achieved": chol_tflops, "peak": dgemm_peak, "unit": "TFLOP/s",
-                     "frac": chol_tflops / dgemm_peak if dgemm_peak else None, "traffic": None,
+                     "frac": chol_tflops / dgemm_peak if dgemm_peak else None, "traffic": 1.073e9,
+                     "traffic_note": "bytes of ONE syrk_kernel launch (bulk update of the first pose tile column at C3, 4278 tile pairs) from profiles/r01_ncu_summary.md §3: dram read 570 MB + write 503 MB = each C tile read and written once (algorithmic 4278 x 256 KB = 1.12 GB); operands served by L2",
                      "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (FP64; MEASURED_PEAKS.json holds no FP64 figure)",
                      "kernel": "cvb_chol::syrk_kernel (FP64 DMMA m8n8k4, 64x64x128 per CTA, 3 CTAs/SM) inside the tile-sparse Cholesky of the reduced camera system; achieved = executed tile-GEMM flops / factorisation time (includes the latency-bound diagonal-tile chain)",
                      "flops_per_factorisation_dense_equivalent": (15.0 * prob["K"]) ** 3 / 3.0},
