@@ -9,15 +9,18 @@ A saved map (`Map::SaveToFile`, covins_backend/src/covins_backend/map_be.cpp:835
     <dir>/mapdata.txt                     MsgMap: the loop constraints (map_be.hpp:126-136)
 
 and is read back by `Map::LoadFromFile` (map_be.cpp:508-700), which lists the two directories (any file name, any
-order) and rebuilds the containers.  The encoding restated here is cereal's portable-less BinaryOutputArchive
-(cereal is not in this image — it is an external dependency of covins_comm): arithmetic values raw little-endian;
+order) and rebuilds the containers.  The encoding restated here is cereal's BinaryOutputArchive (vendored header-only
+at covins_comm/thirdparty/cereal: archives/binary.hpp, types/vector.hpp, types/utility.hpp,
+types/concepts/pair_associative_container.hpp): arithmetic values raw little-endian;
 `bool` one byte; enums as their `int`; `std::pair` = first, second; `std::vector` / `std::map` / = a uint64 size tag,
 then the elements (vectors of arithmetic types as one raw block; map items as key, value in key order);
 Eigen matrices by the reference's own `save` (msg_keyframe.hpp:211-234): int32 rows, int32 cols, raw column-major
 data; `cv::Mat` by msg_keyframe.hpp:237-285: int rows, cols, type, bool continuous, raw rows.
 
-PARITY UNPINNED: the reference ships no saved map and cereal is absent, so the byte layout is pinned only by the
-in-tree serialisation code cited above and by round-trip tests (tests/test_mapio.py).
+PARITY PINNED by reference-written bytes: tests/golden/covins_map_ref/ is written by the vendored cereal + the
+reference's own message headers and `save` templates (oracle/ref/cereal_fixture_gen.cpp, built by oracle/ref/Makefile);
+tests/test_mapio_cereal.py checks that this module decodes those files to the values that went in and re-encodes them
+byte for byte.  (The reference ships no saved map; the fixture is a small synthetic one.)
 
 `write_map(dir, problem)` turns a flat problem (covins_b200.synth_map) into such a directory; `read_map(dir)` turns a
 directory into the flat problem that `optimization.BaSolver / global_bundle_adjustment / pgo_edges` and the matching
@@ -262,10 +265,13 @@ def _qt(T):
     return np.concatenate([_rot_to_quat(np.asarray(T)[None, :3, :3])[0], np.asarray(T)[:3, 3]])
 
 
-def write_map(path: str, p: dict, descriptors=None, map_id: int = 0):
+def write_map(path: str, p: dict, descriptors=None, map_id: int = 0, descriptors_add=None, keypoints_add=None):
     """Flat problem → COVINS map directory.  Every observation of a keyframe becomes one of its keypoints (feature index =
     its position among the keyframe's observations in landmark order); `descriptors` (optional, [n_obs, 32] u8) are the
-    ORB rows of those features.  Octave is recovered from sigma = 2 (octave + 1) (optimization_be.cpp:183-184)."""
+    ORB rows of those features.  Octave is recovered from sigma = 2 (octave + 1) (optimization_be.cpp:183-184).
+    `descriptors_add` (optional, list of K arrays [n_k, 32] u8 or [n_k, 128] f32): the ADDITIONAL feature set of every
+    keyframe (descriptors_add_, keyframe_be.hpp:111) — the set the place-recognition k-NN runs on
+    (placerec_gen_be.cpp:82-100); `keypoints_add` (optional, list of K arrays [n_k, 2] f32) their distorted keypoints."""
     os.makedirs(os.path.join(path, "keyframes"), exist_ok=True)
     os.makedirs(os.path.join(path, "mappoints"), exist_ok=True)
     K, L = int(p["K"]), int(p["L"])
@@ -299,14 +305,17 @@ def write_map(path: str, p: dict, descriptors=None, map_id: int = 0):
             pre.update(dt=np.asarray(p["imu_dt"])[a:b], lin_acc_x=acc[:, 0], lin_acc_y=acc[:, 1], lin_acc_z=acc[:, 2],
                        ang_vel_x=gyr[:, 0], ang_vel_y=gyr[:, 1], ang_vel_z=gyr[:, 2], acc=acc[0], gyr=gyr[0])
             acc0, gyr0 = p["imu_acc0"][f], p["imu_gyr0"][f]
+        d_add = None if descriptors_add is None else np.asarray(descriptors_add[k])
+        n_add = 0 if d_add is None else len(d_add)
+        kp_add = np.zeros((n_add, 2), np.float32) if keypoints_add is None else np.asarray(keypoints_add[k], np.float32).reshape(n_add, 2)
         same_prev = k > 0 and agent[k - 1] == agent[k]
         same_next = k + 1 < K and agent[k + 1] == agent[k]
         T_ws = _T(p["pose"][k][:4], p["pose"][k][4:])
         kf = dict(timestamp=float(kid[k]) * 0.25, id=ids[k], calibration=calib, img_dim_x_min=0, img_dim_y_min=0, img_dim_x_max=752,
                   img_dim_y_max=480, keypoints_distorted=uv, keypoints_undistorted=uv, keypoints_aors=aors,
                   descriptors=None if descriptors is None else np.asarray(descriptors, np.uint8)[sel],
-                  keypoints_distorted_add=np.zeros((0, 2), np.float32), keypoints_undistorted_add=np.zeros((0, 2), np.float32),
-                  keypoints_aors_add=np.zeros((0, 4), np.float32), descriptors_add=None,
+                  keypoints_distorted_add=kp_add, keypoints_undistorted_add=kp_add,
+                  keypoints_aors_add=np.zeros((len(kp_add), 4), np.float32), descriptors_add=d_add,
                   T_s_c=T_sc, T_w_s=T_ws, T_w_s_vio=T_ws, velocity=p["speedbias"][k][0:3], bias_gyro=p["speedbias"][k][6:9],
                   bias_accel=p["speedbias"][k][3:6], lin_acc=np.zeros(3), ang_vel=np.zeros(3), lin_acc_init=acc0, ang_vel_init=gyr0,
                   preintegration=pre, landmarks={int(feat_of_obs[o]): (int(obs_lm[o]), 0) for o in sel},
@@ -330,8 +339,11 @@ def write_map(path: str, p: dict, descriptors=None, map_id: int = 0):
 
 
 def read_map(path: str) -> dict:
-    """COVINS map directory → flat problem (+ `descriptors` [n_obs, 32] of the observed features and `kf_descriptors`, the
-    per-keyframe descriptor matrices for the matching calls).  Canonical orders as in synth_map: keyframes by
+    """COVINS map directory → flat problem (+ `descriptors` [n_obs, 32] of the observed features, `kf_descriptors` — the
+    per-keyframe `descriptors` matrices that DenseMatcher / ComputeDescriptor read (keyframe_base.cpp:258-260,
+    landmark_be.cpp:57-64) — and `kf_descriptors_add`, the per-keyframe `descriptors_add` matrices that the
+    place-recognition k-NN (cvb_match_hamming_batch / cvb_db_*) must be fed with, as placerec_gen_be.cpp:82-100 does).
+    Canonical orders as in synth_map: keyframes by
     (client_id, kf_id), landmarks by (client_id, id), a landmark's observations by keyframe index."""
     def _load(sub, dec):
         d = os.path.join(path, sub)
@@ -394,5 +406,6 @@ def read_map(path: str) -> dict:
              loop_t=np.array([_qt(T)[4:] for T in md["transforms12"]]).reshape(nl, 3),
              loop_cov=np.array(md["cov"]).reshape(nl, 6, 6),
              descriptors=np.array(desc, np.uint8).reshape(-1, 32) if desc else np.zeros((0, 32), np.uint8),
-             kf_descriptors=[k["descriptors"] for k in kfs], lm_ids=[l["id"] for l in lms])
+             kf_descriptors=[k["descriptors"] for k in kfs], kf_descriptors_add=[k["descriptors_add"] for k in kfs],
+             kf_keypoints_add=[k["keypoints_distorted_add"] for k in kfs], lm_ids=[l["id"] for l in lms])
     return p

@@ -91,3 +91,19 @@ def test_reread_map_gives_the_same_cost_in_the_oracle(tmp_path):
     c1 = bo.Problem(q, visual_only=False, loop_loss=1.0)
     f0 = c0.evaluate(c0.pose, c0.sb, c0.lm)[0]; f1 = c1.evaluate(c1.pose, c1.sb, c1.lm)[0]
     assert np.isclose(float(f0), float(f1), rtol=1e-9)
+
+
+def test_descriptors_add_roundtrip(tmp_path):
+    """descriptors_add_ is the feature set the place-recognition k-NN runs on (placerec_gen_be.cpp:82-100): write_map
+    stores it per keyframe, read_map returns it as kf_descriptors_add next to kf_descriptors (the DenseMatcher set)."""
+    p = synth_map.make_config("tiny")
+    rng = np.random.default_rng(2)
+    desc = rng.integers(0, 256, (len(p["obs_kf"]), 32), dtype=np.uint8)
+    add = [rng.integers(0, 256, (5 + k % 3, 32), dtype=np.uint8) for k in range(p["K"])]
+    kp = [rng.random((len(a), 2)).astype(np.float32) for a in add]
+    d = str(tmp_path / "map")
+    mapio.write_map(d, p, descriptors=desc, descriptors_add=add, keypoints_add=kp)
+    q = mapio.read_map(d)
+    assert all(np.array_equal(a, b) for a, b in zip(q["kf_descriptors_add"], add))
+    assert all(np.array_equal(a, b) for a, b in zip(q["kf_keypoints_add"], kp))
+    assert sum(len(m) for m in q["kf_descriptors"]) == len(p["obs_kf"])
