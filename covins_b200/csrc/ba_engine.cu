@@ -59,18 +59,22 @@ constexpr int RED_SLOTS = 8;
 // Device arrays come from the stream-ordered allocator on the engine's stream: the pool (release threshold raised in
 // cvb_ctx_create) keeps freed blocks, so building a second problem re-uses the first one's memory instead of paying
 // cudaMalloc/cudaFree (which cost ~100 ms of a 180 ms set-up at C3, the 7.4 GB S buffer alone several ms each way).
+// t_alloc_stream is (re)set by BaEnter at EVERY cvb_ba_* entry point (a handle may be driven from any host thread, and
+// several handles may exist); an array is freed on the stream it was allocated on.
 static thread_local cudaStream_t t_alloc_stream = nullptr;
 template <typename T>
 struct DevArr {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t st = nullptr;
   int alloc(size_t count) {
     n = count;
     if (count == 0) count = 1;
-    return cudaMallocAsync(&p, count * sizeof(T), t_alloc_stream) == cudaSuccess ? 0 : 1;
+    st = t_alloc_stream;
+    return cudaMallocAsync(&p, count * sizeof(T), st) == cudaSuccess ? 0 : 1;
   }
   void free_() {
-    if (p) cudaFreeAsync(p, t_alloc_stream);
+    if (p) cudaFreeAsync(p, st);
     p = nullptr;
   }
 };
@@ -89,6 +93,7 @@ struct Engine {
   std::vector<uint8_t> h_const;
   // device state (double buffered)
   DevArr<double> pose[2], sb[2], lm[2];
+  DevArr<double> pose0, sb0, lm0;   // the state the problem was created with (cvb_ba_restart returns to it)
   DevArr<uint8_t> pose_const;
   DevArr<int> off_pose, off_sb, xt_i, xt_j;   // xt_*: tile list of the multi-GPU exchange
   DevArr<int> zt_i, zt_j;                     // tiles of L's structure (incl. fill): the only part of S that is ever read
@@ -120,7 +125,7 @@ struct Engine {
   DevArr<double> scale, colsq, diag, gvec, grad, sgrad, gn, step, xsol, yb, gs, tmp;
   DevArr<double> S, linv;
   DevArr<int> flag;
-  DevArr<double> partials, scalars;
+  DevArr<double> partials, scalars, rankmax;
   double* h_scalars = nullptr;   // pinned
   int cur = 0;
   // trust-region state (Ceres DoglegStrategy / TrustRegionMinimizer)
@@ -150,6 +155,7 @@ struct Engine {
       t_prev = now;
     };
     for (int i = 0; i < 2; i++) { pose[i].free_(); sb[i].free_(); lm[i].free_(); }
+    pose0.free_(); sb0.free_(); lm0.free_();
     pose_const.free_(); off_pose.free_(); off_sb.free_(); xt_i.free_(); xt_j.free_(); zt_i.free_(); zt_j.free_(); xbuf.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
     obs_kf.free_(); obs_lm.free_(); lm_ptr.free_(); kf_ptr.free_(); kf_obs.free_(); obs_uv.free_(); obs_sigma.free_();
     lin.free_(); wy.free_(); Hll.free_(); HllInv.free_(); bl.free_();
@@ -160,7 +166,7 @@ struct Engine {
     sb_hi.free_(); sb_lo.free_(); sb_ptr.free_(); sp_a.free_(); sp_b.free_();
     scale.free_(); colsq.free_(); diag.free_(); gvec.free_(); grad.free_(); sgrad.free_(); gn.free_(); step.free_();
     xsol.free_(); yb.free_(); gs.free_(); tmp.free_(); S.free_(); linv.free_(); flag.free_(); partials.free_();
-    scalars.free_();
+    scalars.free_(); rankmax.free_();
     lap("device arrays");
     if (h_scalars) cudaFreeHost(h_scalars);
     lap("pinned scalars");
@@ -959,9 +965,18 @@ __global__ void max_abs_grad_kernel(int n_vec, const double* __restrict__ g, con
   }
   if (threadIdx.x == 0) partials[slot * RED_BLOCKS + blockIdx.x] = sm[0];
 }
-__global__ void max_final_kernel(const double* __restrict__ partials, double* __restrict__ scalars, int slot) {
+// the rank's maximum goes to rankmax[rank] of a zeroed world-sized vector: a SUM all-reduce of that vector hands every
+// rank all the local maxima (the injected collective is sum-only)
+__global__ void max_final_kernel(const double* __restrict__ partials, double* __restrict__ scalars, int slot,
+                                 double* __restrict__ rankmax, int rank, int world) {
   double m = 0.0;
   for (int i = 0; i < RED_BLOCKS; i++) m = fmax(m, partials[slot * RED_BLOCKS + i]);
+  scalars[slot] = m;
+  for (int r = 0; r < world; r++) rankmax[r] = (r == rank) ? m : 0.0;
+}
+__global__ void max_ranks_kernel(const double* __restrict__ rankmax, int world, double* __restrict__ scalars, int slot) {
+  double m = 0.0;
+  for (int r = 0; r < world; r++) m = fmax(m, rankmax[r]);
   scalars[slot] = m;
 }
 
@@ -1129,6 +1144,17 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   CVB_REQUIRE(ctx, p->K > 0, "problem has no keyframes");
   CVB_REQUIRE(ctx, E.rank >= 0 && E.rank < E.world, "bad rank/world");
   const int K = p->K;
+  CVB_REQUIRE(ctx, p->n_imu >= 0 && p->n_edge >= 0 && p->L >= 0, "negative problem size");
+  if (!E.visual_only)
+    for (int f = 0; f < p->n_imu; f++)
+      CVB_REQUIRE(ctx, p->imu_i[f] >= 0 && p->imu_i[f] < K && p->imu_j[f] >= 0 && p->imu_j[f] < K && p->imu_i[f] != p->imu_j[f],
+                  "bad IMU factor indices");
+  for (int e = 0; e < p->n_edge; e++)
+    CVB_REQUIRE(ctx, p->edge_i[e] >= 0 && p->edge_i[e] < K && p->edge_j[e] >= 0 && p->edge_j[e] < K && p->edge_i[e] != p->edge_j[e],
+                "bad edge indices");
+  for (int l = 0; l < p->L; l++)
+    for (int ob = p->lm_obs_ptr[l]; ob < p->lm_obs_ptr[l + 1]; ob++)
+      CVB_REQUIRE(ctx, p->obs_kf[ob] >= 0 && p->obs_kf[ob] < K, "obs_kf out of range");
   // ---- landmarks with >= 2 usable observations (opt.cpp:158-171, 438-453), observations of this rank's landmarks ----
   std::vector<int> lm_compact(p->L > 0 ? p->L : 0, -1);
   E.lm_of_compact.clear();
@@ -1344,6 +1370,7 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   if ((rc = zalloc(E, E.sb[1], (size_t)9 * K))) return rc;
   if ((rc = upload(E, E.lm[0], h_lm))) return rc;
   if ((rc = zalloc(E, E.lm[1], (size_t)3 * E.L_in))) return rc;
+  if ((rc = upload(E, E.pose0, p->pose, (size_t)7 * K)) || (rc = upload(E, E.sb0, h_sb)) || (rc = upload(E, E.lm0, h_lm))) return rc;
   if ((rc = upload(E, E.pose_const, p->pose_const, (size_t)K))) return rc;
   std::vector<double> ex((size_t)7 * K), in((size_t)4 * K), di((size_t)4 * K);
   for (int k = 0; k < K; k++) {
@@ -1439,7 +1466,9 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   // S is not cleared here: every iteration clears exactly the tiles it uses (zero_tiles_kernel), nothing else is read
   if (E.S.alloc((size_t)E.n_c_pad * E.n_c_pad)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (reduced camera system, %zu bytes)", (size_t)E.n_c_pad * E.n_c_pad * 8);
   if ((rc = zalloc(E, E.linv, (size_t)E.n_c_pad * cvb_chol::T))) return rc;
-  if ((rc = zalloc(E, E.partials, (size_t)RED_SLOTS * RED_BLOCKS)) || (rc = zalloc(E, E.scalars, RED_SLOTS))) return rc;
+  if ((rc = zalloc(E, E.partials, (size_t)RED_SLOTS * RED_BLOCKS)) || (rc = zalloc(E, E.scalars, RED_SLOTS)) ||
+      (rc = zalloc(E, E.rankmax, (size_t)E.world)))
+    return rc;
   ENG_CUDA(cudaMallocHost(&E.h_scalars, RED_SLOTS * sizeof(double)));
   for (auto& e : E.ev) ENG_CUDA(cudaEventCreate(&e));
   {
@@ -1646,8 +1675,11 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
   // gradient tolerance (max-norm of the unscaled gradient)
   max_abs_grad_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_vec, E.gvec.p, E.scale.p, E.partials.p, 7);
   ENG_LAUNCH();
-  max_final_kernel<<<1, 1, 0, E.st>>>(E.partials.p, E.scalars.p, 7);
+  max_final_kernel<<<1, 1, 0, E.st>>>(E.partials.p, E.scalars.p, 7, E.rankmax.p, E.rank, E.world);
   ENG_LAUNCH();
+  if (E.world > 1) {
+    if ((rc = ar(E, E.rankmax.p, (size_t)E.world))) return rc;
+  }
   // Cauchy point: alpha = |grad|^2 / |J (grad / diag)|^2
   jv_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.lin.p, E.sgrad.p, E.off_pose.p, E.n_c_pad,
                                               E.partials.p, 3);
@@ -1703,6 +1735,10 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
     reduce_final<<<1, 256, 0, E.st>>>(E.partials.p, E.scalars.p, 7, 0);
     ENG_LAUNCH();
     if ((rc = ar(E, E.scalars.p, 7))) return rc;
+    if (E.world > 1) {   // slot 7 (max-norm of the gradient) = max over the ranks' maxima
+      max_ranks_kernel<<<1, 1, 0, E.st>>>(E.rankmax.p, E.world, E.scalars.p, 7);
+      ENG_LAUNCH();
+    }
     tick(E, 4);
     ENG_CUDA(cudaMemcpyAsync(E.h_scalars, E.scalars.p, RED_SLOTS * sizeof(double), cudaMemcpyDeviceToHost, E.st));
     ENG_CUDA(cudaStreamSynchronize(E.st));
@@ -1721,7 +1757,7 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
   E.gn2 = E.h_scalars[0]; E.gg = E.h_scalars[1]; E.g_gn = E.h_scalars[2];
   const double JgJg = E.h_scalars[3] + E.h_scalars[5];
   E.alpha = E.gg / JgJg;
-  if (E.h_scalars[7] <= 1e-10 && E.world == 1) *grad_converged = true;
+  if (E.h_scalars[7] <= 1e-10) *grad_converged = true;
   return CVB_OK;
 }
 
@@ -1899,6 +1935,14 @@ struct cvb_ba {
   cvb_ba_problem prob_copy;
 };
 
+// every cvb_ba_* entry: make the ctx's device current and bind the stream-ordered allocator to the engine's stream
+struct BaEnter {
+  cvb_device_guard guard;
+  explicit BaEnter(cvb_ba* h) : guard(h ? h->E.ctx : nullptr) {
+    if (h) t_alloc_stream = h->E.st;
+  }
+};
+
 extern "C" {
 
 void cvb_ba_free(cvb_ctx*) {}
@@ -1909,7 +1953,7 @@ int cvb_ba_create(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o
   cvb_ba* h = new cvb_ba();
   h->E.ctx = ctx;
   h->E.st = ctx->stream;
-  t_alloc_stream = ctx->stream;
+  BaEnter enter(h);
   h->prob_copy = *p;
   int rc = engine_setup(h->E, p, o);
   if (!rc) rc = engine_begin(h->E);
@@ -1931,13 +1975,22 @@ int cvb_ba_set_allreduce(cvb_ba* h, cvb_allreduce_fn fn, void* user) {
   return CVB_OK;
 }
 
+// Back to the state the problem was created with (the preintegrations were propagated at those biases), then iteration 0
+// again: a restarted solve repeats the original one bit for bit.
 int cvb_ba_restart(cvb_ba* h) {
   if (!h) return CVB_ERR_INVALID;
-  return engine_begin(h->E);
+  BaEnter enter(h);
+  Engine& E = h->E;
+  E.cur = 0;
+  ENG_CUDA(cudaMemcpyAsync(E.pose[0].p, E.pose0.p, sizeof(double) * 7 * E.K, cudaMemcpyDeviceToDevice, E.st));
+  ENG_CUDA(cudaMemcpyAsync(E.sb[0].p, E.sb0.p, sizeof(double) * 9 * E.K, cudaMemcpyDeviceToDevice, E.st));
+  if (E.L_in) ENG_CUDA(cudaMemcpyAsync(E.lm[0].p, E.lm0.p, sizeof(double) * 3 * E.L_in, cudaMemcpyDeviceToDevice, E.st));
+  return engine_begin(E);
 }
 
 int cvb_ba_iterate(cvb_ba* h, int max_iterations, int* iterations_done) {
   if (!h) return CVB_ERR_INVALID;
+  BaEnter enter(h);
   Engine& E = h->E;
   int n = 0;
   bool done = E.termination != TERM_NO_CONVERGENCE;
@@ -1952,11 +2005,13 @@ int cvb_ba_iterate(cvb_ba* h, int max_iterations, int* iterations_done) {
 
 int cvb_ba_result_get(cvb_ba* h, const cvb_ba_problem* p, cvb_ba_result* r) {
   if (!h || !p || !r) return CVB_ERR_INVALID;
+  BaEnter enter(h);
   return engine_download(h->E, p, r);
 }
 
 int cvb_ba_reproj_norms(cvb_ba* h, double* norms, int n_obs) {
   if (!h || !norms) return CVB_ERR_INVALID;
+  BaEnter enter(h);
   return engine_corrected_norms(h->E, norms, n_obs);
 }
 
@@ -1964,6 +2019,7 @@ int cvb_ba_reproj_norms(cvb_ba* h, double* norms, int n_obs) {
 // which: 0 scale, 1 colsq, 2 diag, 3 gradient g, 4 grad/diag, 5 gn, 6 step, 7 x (linear solve), 8 reduced rhs
 int cvb_ba_debug_vector(cvb_ba* h, int which, double* out, int64_t cap, int64_t* n_cam, int64_t* n_total) {
   if (!h) return CVB_ERR_INVALID;
+  BaEnter enter(h);
   Engine& E = h->E;
   const DevArr<double>* v[] = {&E.scale, &E.colsq, &E.diag, &E.gvec, &E.grad, &E.gn, &E.step, &E.xsol, &E.gs};
   if (which < 0 || which > 8) return CVB_ERR_INVALID;
@@ -1998,8 +2054,8 @@ int cvb_ba_timing(cvb_ba* h, double out[6], int reset) {
 
 int cvb_ba_destroy(cvb_ba* h) {
   if (h) {
+    BaEnter enter(h);
     cudaStreamSynchronize(h->E.st);
-    t_alloc_stream = h->E.st;
     delete h;
   }
   return CVB_OK;
@@ -2021,6 +2077,7 @@ int cvb_ba_solve(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o,
 // state (the reference re-reads the map at :325,454-457; round 1 only removes observations) with Cauchy(1) on loops.
 int cvb_gba(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_gba_options* g, cvb_ba_result* r, uint8_t* obs_removed) {
   if (!ctx || !p || !g || !r) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   std::vector<uint8_t> skip(p->n_obs > 0 ? p->n_obs : 1, 0), rb0(p->n_edge > 0 ? p->n_edge : 1, 0), rb1(p->n_edge > 0 ? p->n_edge : 1, 1);
   if (p->obs_skip) std::memcpy(skip.data(), p->obs_skip, (size_t)p->n_obs);
   cvb_ba_options o{};

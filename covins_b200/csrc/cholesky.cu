@@ -747,6 +747,7 @@ int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* 
 // [6] = inside the 16x16 diagonal-block step, [7] = the same incl. the closing barrier, [8] = panel, [9] = trailing update.
 extern "C" int cvb_microbench_potrf(cvb_ctx* ctx, int reps, double* us_per_tile, int64_t* phase_cycles) {
   if (!ctx || reps < 1 || !us_per_tile) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   using namespace cvb_chol;
   CVB_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
   const int nt = 8;
@@ -813,6 +814,7 @@ extern "C" int cvb_microbench_potrf(cvb_ctx* ctx, int reps, double* us_per_tile,
 extern "C" int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, const double* b, double* x,
                                         double* factor_ms) {
   if (!ctx || !A || !b || !x || n <= 0) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   using namespace cvb_chol;
   const int np = ((n + T - 1) / T) * T;
   cudaStream_t st = ctx->stream;

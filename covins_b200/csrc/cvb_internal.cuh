@@ -21,7 +21,7 @@ struct cvb_ctx {
   int64_t launches = 0;
   std::string err;
   // grow-only device workspaces (named slots so independent stages never alias)
-  cvb_buf ws[16];
+  cvb_buf ws[24];
   // pinned host staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
@@ -29,7 +29,7 @@ struct cvb_ctx {
 };
 
 enum { WS_Q = 0, WS_T, WS_SEG, WS_OUT0, WS_OUT1, WS_OUT2, WS_PART_I, WS_PART_D, WS_LIST_I, WS_LIST_D, WS_SKIPA,
-       WS_SKIPB, WS_TMP0, WS_TMP1, WS_FLAG, WS_MISC };
+       WS_SKIPB, WS_TMP0, WS_TMP1, WS_FLAG, WS_MISC, WS_CHUNK_PS, WS_CHUNK_OFF, WS_GS0, WS_GS1, WS_GS2, WS_GS3, WS_GS4, WS_GS5 };
 
 int cvb_fail(cvb_ctx* ctx, int code, const char* fmt, ...);
 void* cvb_ws(cvb_ctx* ctx, int slot, size_t bytes);          // returns nullptr on failure (ctx->err set)
@@ -58,6 +58,22 @@ void* cvb_pinned(cvb_ctx* ctx, size_t bytes);
   } while (0)
 
 static inline cudaStream_t cvb_stream(cvb_ctx* ctx, void* s) { return s ? (cudaStream_t)s : ctx->stream; }
+
+// Scoped device guard: every extern "C" entry point makes the ctx's device current for the calling thread (a new host
+// thread defaults to device 0; two ctxs on different GPUs may be driven from one thread) and restores the previous one.
+struct cvb_device_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit cvb_device_guard(const cvb_ctx* c) {
+    if (c && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~cvb_device_guard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  cvb_device_guard(const cvb_device_guard&) = delete;
+  cvb_device_guard& operator=(const cvb_device_guard&) = delete;
+};
+#define CVB_GUARD(ctx) cvb_device_guard cvb_guard_((ctx))
 
 // ---------------------------------------------------------------------------------------------
 // Device helpers: mbarrier + 1-D bulk TMA (cp.async.bulk → SASS UBLKCP), used to stage descriptor

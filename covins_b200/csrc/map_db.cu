@@ -112,6 +112,7 @@ extern "C" {
 
 int cvb_db_create(cvb_ctx* ctx, int desc_bytes, cvb_db** out) {
   if (!ctx || !out) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   *out = nullptr;
   if (desc_bytes != 32)
     return cvb_fail(ctx, CVB_ERR_UNSUPPORTED, "descriptor database: only 32-byte ORB descriptors, got %d", desc_bytes);
@@ -134,6 +135,7 @@ int cvb_db_destroy(cvb_ctx* ctx, cvb_db* db) {
 
 int cvb_db_reserve(cvb_ctx* ctx, cvb_db* db, int64_t rows) {
   if (!ctx || !db || rows < 0) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   if ((size_t)rows <= db->cap_rows) return CVB_OK;
   uint8_t* p = nullptr;
   CVB_CUDA(ctx, cudaMalloc(&p, (size_t)rows * db->desc_bytes));
@@ -148,6 +150,7 @@ int cvb_db_reserve(cvb_ctx* ctx, cvb_db* db, int64_t rows) {
 
 int cvb_db_append(cvb_ctx* ctx, cvb_db* db, const uint8_t* rows, const int32_t* rows_per_kf, int n_kf) {
   if (!ctx || !db) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   CVB_REQUIRE(ctx, n_kf >= 0 && (n_kf == 0 || rows_per_kf), "cvb_db_append: bad arguments");
   int64_t add = 0;
   for (int i = 0; i < n_kf; ++i) {
@@ -182,6 +185,7 @@ int cvb_db_match_hamming(cvb_ctx* ctx, cvb_db* db, const uint8_t* q, int nq, flo
                          int32_t* n_matches, int32_t* m_kf, int32_t* m_query, int32_t* m_train, float* m_dist,
                          int cap, int32_t* n_total) {
   if (!ctx || !db) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   const int n_seg = (int)db->seg_ptr.size() - 1;
   CVB_REQUIRE(ctx, nq >= 0 && cap >= 0 && n_total && (nq == 0 || q), "cvb_db_match_hamming: bad arguments");
   CVB_REQUIRE(ctx, cap == 0 || (m_kf && m_query && m_train && m_dist), "cvb_db_match_hamming: null outputs");

@@ -711,13 +711,18 @@ int knn_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, const 
     if (!filter && n_seg == 1 && !(e && !strcmp(e, "popc")) && (long)nq * total >= (1L << 26) &&
         total >= (int64_t)parts * 4 * 1024) {
       int n_ps = parts * 4;
-      const int64_t chunk = ((total + n_ps - 1) / n_ps + 127) / 128 * 128;
+      int64_t chunk = ((total + n_ps - 1) / n_ps + 127) / 128 * 128;
+      // the tensor-core kernel packs (distance, local index) keys: a chunk must stay below its index range (cvb_tc::profitable
+      // enforces the same bound on ordinary segments)
+      const int64_t max_chunk = ((int64_t)1 << cvb_tc::kIdxBits) - 128;
+      if (chunk > max_chunk) chunk = max_chunk;
       n_ps = (int)((total + chunk - 1) / chunk);
       std::vector<int32_t> h_ps((size_t)n_ps + 1), h_off((size_t)n_ps);
       for (int c = 0; c <= n_ps; c++) h_ps[c] = (int32_t)std::min<int64_t>((int64_t)c * chunk, total);
       for (int c = 0; c < n_ps; c++) h_off[c] = (int32_t)((int64_t)c * chunk);
-      int32_t* d_ps = (int32_t*)cvb_ws(ctx, WS_TMP0, sizeof(int32_t) * (n_ps + 1));
-      int32_t* d_off = (int32_t*)cvb_ws(ctx, WS_TMP1, sizeof(int32_t) * n_ps);
+      // own slots: WS_TMP0/WS_TMP1 hold the quantised descriptors of the host L2 path (l2_host) at this point
+      int32_t* d_ps = (int32_t*)cvb_ws(ctx, WS_CHUNK_PS, sizeof(int32_t) * (n_ps + 1));
+      int32_t* d_off = (int32_t*)cvb_ws(ctx, WS_CHUNK_OFF, sizeof(int32_t) * n_ps);
       const size_t pn = (size_t)n_ps * nq * k;
       int32_t* part_i = (int32_t*)cvb_ws(ctx, WS_PART_I, pn * sizeof(int32_t));
       int32_t* part_d = (int32_t*)cvb_ws(ctx, WS_PART_D, pn * sizeof(int32_t));
@@ -763,6 +768,16 @@ int knn_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, const 
     case 3: return launch_merge<M, 3>(ctx, sp, pl, d_idx, d_dist, st);
     default: return launch_merge<M, 4>(ctx, sp, pl, d_idx, d_dist, st);
   }
+}
+
+// Host wrappers validate the host seg_ptr BEFORE sizing any buffer with seg_ptr[n_seg].
+int host_rows(cvb_ctx* ctx, const int32_t* seg_ptr, int n_seg, size_t* rows) {
+  int max_len = 0;
+  int64_t total = 0;
+  int rc = check_segs(ctx, seg_ptr, n_seg, &max_len, &total);
+  if (rc) return rc;
+  *rows = (size_t)total;
+  return CVB_OK;
 }
 
 // Host-buffer staging helper: copies q, t, seg_ptr to device workspaces.
@@ -854,6 +869,7 @@ int cvb_knn_hamming_batch_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const ui
                               const int32_t* d_seg_ptr, const int32_t* h_seg_ptr, int n_seg, int k,
                               int32_t* d_idx, int32_t* d_dist, void* stream) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   return knn_dev<HammingMetric, 4>(ctx, d_q, nq, d_t, d_seg_ptr, h_seg_ptr, n_seg, k, d_idx, d_dist, false, 0.f,
                                    0.f, nullptr, nullptr, nullptr, cvb_stream(ctx, stream));
 }
@@ -863,6 +879,7 @@ int cvb_match_hamming_batch_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const 
                                 float ratio, int32_t* d_match_train, float* d_match_dist, int32_t* d_n_matches,
                                 void* stream) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   return knn_dev<HammingMetric, 4>(ctx, d_q, nq, d_t, d_seg_ptr, h_seg_ptr, n_seg, 2, nullptr, nullptr, true, thr,
                                    ratio, d_match_train, d_match_dist, d_n_matches, cvb_stream(ctx, stream));
 }
@@ -870,11 +887,14 @@ int cvb_match_hamming_batch_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const 
 int cvb_knn_hamming_batch(cvb_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, const int32_t* seg_ptr,
                           int n_seg, int k, int32_t* idx, int32_t* dist) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   CVB_REQUIRE(ctx, seg_ptr && n_seg >= 1 && nq >= 0, "bad arguments");
-  const size_t rows = (size_t)seg_ptr[n_seg];
+  size_t rows = 0;
+  int rc = host_rows(ctx, seg_ptr, n_seg, &rows);
+  if (rc) return rc;
   void *d_q, *d_t;
   int32_t* d_seg;
-  int rc = stage_inputs(ctx, q, (size_t)nq * 32, t, rows * 32, seg_ptr, n_seg, &d_q, &d_t, &d_seg);
+  rc = stage_inputs(ctx, q, (size_t)nq * 32, t, rows * 32, seg_ptr, n_seg, &d_q, &d_t, &d_seg);
   if (rc) return rc;
   const size_t on = (size_t)n_seg * nq * k;
   int32_t* d_idx = (int32_t*)cvb_ws(ctx, WS_OUT0, on * 4);
@@ -895,11 +915,14 @@ int cvb_match_hamming_batch(cvb_ctx* ctx, const uint8_t* q, int nq, const uint8_
                             int n_seg, float thr, float ratio, int32_t* match_train, float* match_dist,
                             int32_t* n_matches) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   CVB_REQUIRE(ctx, seg_ptr && n_seg >= 1 && nq >= 0, "bad arguments");
-  const size_t rows = (size_t)seg_ptr[n_seg];
+  size_t rows = 0;
+  int rc = host_rows(ctx, seg_ptr, n_seg, &rows);
+  if (rc) return rc;
   void *d_q, *d_t;
   int32_t* d_seg;
-  int rc = stage_inputs(ctx, q, (size_t)nq * 32, t, rows * 32, seg_ptr, n_seg, &d_q, &d_t, &d_seg);
+  rc = stage_inputs(ctx, q, (size_t)nq * 32, t, rows * 32, seg_ptr, n_seg, &d_q, &d_t, &d_seg);
   if (rc) return rc;
   const size_t on = (size_t)n_seg * nq;
   int32_t* d_mt = (int32_t*)cvb_ws(ctx, WS_OUT0, on * 4);
@@ -922,6 +945,7 @@ int cvb_knn_merge_shards_dev(cvb_ctx* ctx, const int32_t* d_idx_all, const void*
                              const int32_t* d_row_offset, int n_shards, int64_t n, int k, int32_t* d_idx_out,
                              void* d_dist_out, void* stream) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   CVB_REQUIRE(ctx, n_shards >= 1 && n >= 0 && k >= 1 && k <= kMaxMergeK, "merge_shards: need 1 <= k <= %d, n_shards >= 1",
               kMaxMergeK);
   CVB_REQUIRE(ctx, d_idx_all && d_dist_all && d_row_offset && d_idx_out && d_dist_out, "merge_shards: null buffer");
@@ -941,6 +965,7 @@ int cvb_knn_merge_shards_dev(cvb_ctx* ctx, const int32_t* d_idx_all, const void*
 int cvb_landmark_descriptor_batch_dev(cvb_ctx* ctx, const uint8_t* d_cand, const int32_t* d_lm_ptr, int n_lm,
                                       int32_t* d_best_idx, uint8_t* d_out_desc, void* stream) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   CVB_REQUIRE(ctx, n_lm >= 0 && (n_lm == 0 || (d_cand && d_lm_ptr && d_best_idx && d_out_desc)), "landmark_descriptor: bad arguments");
   CVB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_cand) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out_desc) & 3) == 0,
               "landmark_descriptor: misaligned buffers");
@@ -954,6 +979,7 @@ int cvb_landmark_descriptor_batch_dev(cvb_ctx* ctx, const uint8_t* d_cand, const
 int cvb_landmark_descriptor_batch(cvb_ctx* ctx, const uint8_t* cand, const int32_t* lm_ptr, int n_lm, int32_t* best_idx,
                                   uint8_t* out_desc) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   CVB_REQUIRE(ctx, n_lm >= 0 && (n_lm == 0 || (lm_ptr && best_idx && out_desc)), "landmark_descriptor: bad arguments");
   if (n_lm == 0) return CVB_OK;
   const size_t rows = (size_t)lm_ptr[n_lm];
@@ -977,6 +1003,7 @@ int cvb_landmark_descriptor_batch(cvb_ctx* ctx, const uint8_t* cand, const int32
 
 int cvb_quantize_u8_dev(cvb_ctx* ctx, const float* d_src, int64_t n, uint8_t* d_dst, int32_t* d_bad, void* stream) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   cudaStream_t st = cvb_stream(ctx, stream);
   CVB_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_dst) & 3) == 0,
               "quantize: misaligned buffers");
@@ -992,6 +1019,7 @@ int cvb_knn_l2_u8_batch_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint
                             const int32_t* h_seg_ptr, int n_seg, int dim, int k, int32_t* d_idx, float* d_dist,
                             void* stream) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   if (dim != 128) return cvb_fail(ctx, CVB_ERR_UNSUPPORTED, "L2 k-NN is implemented for dim == 128 (SIFT), got %d", dim);
   return knn_dev<L2Metric, 2>(ctx, d_q, nq, d_t, d_seg_ptr, h_seg_ptr, n_seg, k, d_idx, d_dist, false, 0.f, 0.f,
                               nullptr, nullptr, nullptr, cvb_stream(ctx, stream));
@@ -1001,12 +1029,15 @@ int cvb_knn_l2_u8_batch_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint
 static int l2_host(cvb_ctx* ctx, const float* q, int nq, const float* t, const int32_t* seg_ptr, int n_seg, int dim,
                    int k, bool filter, float thr, float ratio, int32_t* out_i, float* out_d, int32_t* n_matches) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   CVB_REQUIRE(ctx, seg_ptr && n_seg >= 1 && nq >= 0, "bad arguments");
   if (dim != 128) return cvb_fail(ctx, CVB_ERR_UNSUPPORTED, "L2 k-NN is implemented for dim == 128 (SIFT), got %d", dim);
-  const size_t rows = (size_t)seg_ptr[n_seg];
+  size_t rows = 0;
+  int rc = host_rows(ctx, seg_ptr, n_seg, &rows);
+  if (rc) return rc;
   void *d_qf, *d_tf;
   int32_t* d_seg;
-  int rc = stage_inputs(ctx, q, (size_t)nq * dim * 4, t, rows * dim * 4, seg_ptr, n_seg, &d_qf, &d_tf, &d_seg);
+  rc = stage_inputs(ctx, q, (size_t)nq * dim * 4, t, rows * dim * 4, seg_ptr, n_seg, &d_qf, &d_tf, &d_seg);
   if (rc) return rc;
   uint8_t* d_q8 = (uint8_t*)cvb_ws(ctx, WS_TMP0, (size_t)nq * dim);
   uint8_t* d_t8 = (uint8_t*)cvb_ws(ctx, WS_TMP1, rows * dim);
@@ -1054,6 +1085,7 @@ int cvb_landmark_match_batch_dev(cvb_ctx* ctx, const uint8_t* d_A, const uint8_t
                                  int n_seg, float thr, int num_best, int32_t* d_outA, int32_t* d_outB, float* d_outD,
                                  int32_t* d_n_out, void* stream) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   cudaStream_t st = cvb_stream(ctx, stream);
   CVB_REQUIRE(ctx, num_best >= 1 && num_best <= 4, "num_best must be in 1..4");
   CVB_REQUIRE(ctx, nA >= 0, "bad nA");
@@ -1105,11 +1137,14 @@ int cvb_landmark_match_batch(cvb_ctx* ctx, const uint8_t* A, const uint8_t* skip
                              const uint8_t* skipB, const int32_t* seg_ptr, int n_seg, float thr, int num_best,
                              int32_t* outA, int32_t* outB, float* outD, int32_t* n_out) {
   if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   CVB_REQUIRE(ctx, seg_ptr && n_seg >= 1 && nA >= 0, "bad arguments");
-  const size_t rows = (size_t)seg_ptr[n_seg];
+  size_t rows = 0;
+  int rc = host_rows(ctx, seg_ptr, n_seg, &rows);
+  if (rc) return rc;
   void *d_A, *d_B;
   int32_t* d_seg;
-  int rc = stage_inputs(ctx, A, (size_t)nA * 32, B, rows * 32, seg_ptr, n_seg, &d_A, &d_B, &d_seg);
+  rc = stage_inputs(ctx, A, (size_t)nA * 32, B, rows * 32, seg_ptr, n_seg, &d_A, &d_B, &d_seg);
   if (rc) return rc;
   uint8_t* d_sA = nullptr;
   uint8_t* d_sB = nullptr;

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) popc_kernel(int iters, uint32_t seed, uin
 
 extern "C" int cvb_microbench_popc(cvb_ctx* ctx, int iters, double* gpopc_per_s) {
   if (!ctx || !gpopc_per_s || iters <= 0) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   uint32_t* d = (uint32_t*)cvb_ws(ctx, WS_MISC, 256);
   if (!d) return CVB_ERR_CUDA;
   const int blocks = ctx->sm_count * 8;
@@ -116,6 +117,7 @@ __global__ void latency_kernel(double* out, double seed, int n) {
 
 extern "C" int cvb_microbench_latency(cvb_ctx* ctx, double* out8) {
   if (!ctx || !out8) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   double* d = (double*)cvb_ws(ctx, WS_MISC, 256);
   if (!d) return CVB_ERR_CUDA;
   cudaEvent_t e0, e1;
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(256) minmax_kernel(unsigned* out, unsigned see
 
 extern "C" int cvb_microbench_minmax(cvb_ctx* ctx, double* out2) {
   if (!ctx || !out2) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
   unsigned* d = (unsigned*)cvb_ws(ctx, WS_MISC, 256);
   if (!d) return CVB_ERR_CUDA;
   cudaEvent_t e0, e1;

@@ -210,7 +210,6 @@ __device__ __forceinline__ uint32_t row_offset(int r) {
 // keys: Hamming → the distance; L2 → the bit pattern of sqrtf(d2) (non-negative floats order like their bits), which
 // is what OpenCV compares.  kInfKey is larger than any real key of either kind.
 constexpr int kInfKey = 0x7F000000;
-constexpr int kIdxBits = 22;   // Hamming packed key: distance << 22 | segment-local train index (segments < 4 Mi rows)
 
 template <class M, int K>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams p) {

@@ -4,6 +4,8 @@
 
 namespace cvb_tc {
 
+constexpr int kIdxBits = 22;   // Hamming packed key: distance << 22 | segment-local train index (segments < 4 Mi rows)
+
 struct TcParams {
   const uint8_t* q;
   int nq;
