@@ -3,13 +3,19 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--gba-config C3]
 
-Metric (BASELINE.json): global-BA iterations/s & descriptor-match Gpairs/s on the 5-agent EuRoC-sized
-synthetic map (config C3: 2000 KF / 100k LM / 800k obs; 1000 ORB features per KF).  One "step" is one pass
-of the hot path: one outer trust-region iteration of the visual-inertial global BA (linearise → Schur → Cholesky →
-dogleg → candidate cost) and one query keyframe matched against every keyframe of the rank's map shard (2 Gpairs,
-fused k-NN + ratio filter).  The two legs are timed separately; the JSON line carries the GBA rate as `value`
-and the matching rate under `match` (each with its own e2e / roofline / cpu_baseline); `pgo` carries the pose-graph
-optimisation rate on the same map, `match.sift_l2` / `match.landmark_descriptor` the SIFT and ComputeDescriptor kernels.
+Metric (BASELINE.json): global-BA iterations/s & descriptor-match Gpairs/s on the 5-agent EuRoC-sized synthetic map
+(config C3: 2000 KF / 100k LM / ~800k obs; 1000 ORB features per KF).  One "step" is one pass of the hot path: one outer
+trust-region iteration of the visual-inertial global BA (linearise → Schur → Cholesky → dogleg → candidate cost) and one
+query keyframe matched against every keyframe of the rank's map shard (2 Gpairs, fused k-NN + ratio filter).  The legs
+are timed separately; the JSON line carries the GBA rate as `value` and the matching rate under `match` (each with its
+own e2e / roofline / cpu_baseline); `pgo` carries the pose-graph optimisation rate on the same map, `match.sift_l2` /
+`match.landmark_descriptor` the SIFT and ComputeDescriptor kernels.  Scalars of the nested legs are repeated at the top
+level (`match_gpairs_per_sec`, `pgo_iterations_per_sec`, …) so that per-N scaling records carry them.
+
+`--impl reference`: the CPU arm — the compiled CPU port of the optimisation path (oracle/ba_port.cpp: analytic Jacobians,
+Schur complement, tile-sparse BLAS-3 Cholesky, Ceres dogleg; OpenMP on all host cores) on the SAME config and the SAME
+number of trust-region iterations, and OpenCV's own BFMatcher.knnMatch (cv2, the library call the reference makes) for the
+matching leg.  The reference binary itself (Ceres/CHOLMOD/robopt/ROS) cannot be built offline.
 """
 from __future__ import annotations
 
@@ -30,13 +36,28 @@ N_KF, N_FEAT = 2000, 1000          # C3: 5 agents x 400 KF, 1000 ORB features pe
 THR, RATIO = 40.0, 0.8             # config/config_backend.yaml:38-39
 N_COPIES = 4                       # 4 x 64 MB map copies rotated per step → inputs (256 MB) > L2 (126 MB)
 
+WORKLOAD = ("C3 5-agent EuRoC-sized synthetic map (2000 KF / 100k LM / ~800k obs, 1000 ORB features per KF): "
+            "visual-inertial global-BA trust-region iterations + ORB k-NN(k=2)+ratio-filter of one query KF vs every KF")
+
+
+def _measured():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
 
 def _peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), "measured"
-    return 6650.0, "fallback"
+    d = _measured()
+    return (d["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in d else (6650.0, "fallback (B200_PROFILING.md)")
+
+
+def _traffic(key):
+    """dram bytes per launch of a dominant kernel, from the committed ncu --set full captures (profiles/r02_traffic.json,
+    written by tools/r02_traffic.py out of the .ncu-rep files); None when no capture is committed for `key`."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(key)
+    return (d["dram_bytes"], d.get("source")) if d else (None, None)
 
 
 class ClockSampler:
@@ -88,21 +109,67 @@ class ClockSampler:
 
 
 def dist_info():
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _cores():
+    """usable host cores: affinity mask capped by the cgroup CPU quota (the GPU boxes expose 128 CPUs with a 16-core quota)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except Exception:
+        pass
+    return n
 
 
 # ==================================================================================================
-# reference arm: the reference's own CPU implementation of the path on the host cores
+# CPU legs (oracle/ is the checker and the timed CPU port, never the product)
 # ==================================================================================================
-def run_reference(args):
-    rank, world, _ = dist_info()
-    if rank != 0:
-        return
+def cpu_gba(config, iters, warmup=0):
+    """The compiled CPU port of the optimisation path on `config`: `iters` trust-region iterations of the visual-inertial
+    GBA solve (the same solve the GPU arm times), all host cores.  Returns (cpu_baseline dict, e2e value)."""
+    from covins_b200 import synth_map
+    from oracle import ba_port as bp
+    cores = _cores()
+    p = synth_map.make_config(config)
+    if warmup > 0:
+        bp.solve(p, warmup, visual_only=False, threads=cores)
+    done, t_solve, t_total, ph = 0, 0.0, 0.0, None
+    while done < iters:                     # a solve that converges early is repeated from the initial state
+        t0 = time.perf_counter()
+        r = bp.solve(p, iters - done, visual_only=False, threads=cores)
+        dt = time.perf_counter() - t0
+        n = max(int(r["iterations"]), 1)
+        done += n; t_total += dt; t_solve += dt - r["phase_s"]["setup"]; ph = r["phase_s"]
+    base = {"value": done / t_solve, "unit": "iterations/s", "cores": cores, "kind": "port", "iterations": done,
+            "sample": f"oracle/ba_port.cpp (C++17/OpenMP x{cores}: analytic Jacobians, Schur complement, tile-sparse Cholesky on "
+                      f"scipy's OpenBLAS dgemm/dsyrk/dtrsm/dpotrf {'(in use)' if bp.lib().blas else '(NOT found: plain loops)'}, Ceres dogleg): "
+                      f"{done} trust-region iterations of the visual-inertial GBA on synthetic config {config} "
+                      f"({p['K']} KF / {p['L']} LM / {len(p['obs_kf'])} obs) in {t_solve:.1f} s (+ {t_total - t_solve:.1f} s problem set-up); "
+                      f"restated CPU path, not the Ceres/CHOLMOD binary (unavailable offline)",
+            "phase_s_last_call": {k: round(v, 3) for k, v in ph.items()},
+            "factor_gflops": round(r["factor_flops"] * max(int(r["iterations"]), 1) / max(ph["factor"], 1e-9) / 1e9, 1)}
+    return base, done / t_total
+
+
+def cpu_pgo(p, edges, iters):
+    from oracle import ba_port as bp
+    cores = _cores()
+    pp = dict(K=p["K"], L=0, pose=p["pose"], pose_const=p["pose_const"], extr=p["extr"], cam_of_kf=p.get("cam_of_kf"))
+    t0 = time.perf_counter()
+    r = bp.solve(pp, iters, visual_only=True, cauchy_reproj=0.0, cauchy_edge=0.5, edges=edges, threads=cores)
+    dt = time.perf_counter() - t0 - r["phase_s"]["setup"]
+    n = max(int(r["iterations"]), 1)
+    return {"value": n / dt, "unit": "iterations/s", "cores": cores, "kind": "port", "iterations": n,
+            "sample": f"oracle/ba_port.cpp (OpenMP x{cores}) on the same pose graph: {n} iterations in {dt:.2f} s"}
+
+
+def cpu_match_cv2(steps, warmup, n_cand=48):
+    """cv2.BFMatcher(NORM_HAMMING).knnMatch — the OpenCV call of placerec_gen_be.cpp:99 — per candidate keyframe"""
     from covins_b200 import synth
     cores = _cores()
-    n_cand = 48  # bounded sample: 48 candidate KFs x 1000 x 1000 = 48 Mpair per step
     desc, _ = synth.orb_keyframes(seed=3, n_kf=n_cand + 1, n_feat=N_FEAT)
     q, cands = desc[0], desc[1:]
     kind = "reference"
@@ -126,48 +193,17 @@ def run_reference(args):
             i, d = ora.knn_hamming_batch(q, t, seg, 2, threads=cores)
             return int(ora.ratio_filter(i, d.astype(np.float32), THR, RATIO)[2].sum())
         sample = f"oracle/knn_oracle.c (OpenMP, {cores} threads), 1000-feature query KF vs {n_cand} candidate KFs per step"
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, min(warmup, 2))):
         step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    gp = n_cand * N_FEAT * N_FEAT * args.steps / dt / 1e9
-    match = {"metric": "match_gpairs_per_sec", "value": gp, "unit": "Gpairs/s", "ms_per_step": dt / args.steps * 1e3,
-             "cpu_baseline": {"value": gp, "unit": "Gpairs/s", "cores": cores, "kind": kind, "sample": sample}}
-    gba = cpu_baseline_gba(max(2, min(args.steps, 4)))
-    line = {
-        "impl": "reference", "metric": "gba_iterations_per_sec", "value": gba["value"], "unit": "iterations/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / gba["value"],
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm runs a bounded sample, see cpu_baseline.sample"},
-        "cpu_baseline": gba,
-        "e2e": {"value": gba["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "match": match,
-    }
-    print(json.dumps(line))
+    gp = n_cand * N_FEAT * N_FEAT * steps / dt / 1e9
+    return {"value": gp, "unit": "Gpairs/s", "cores": cores, "kind": kind, "sample": sample}, dt / steps * 1e3
 
 
-# ==================================================================================================
-# CPU baselines (bounded samples; oracle/ is the checker and the timed CPU port, never the product)
-# ==================================================================================================
-WORKLOAD = ("C3 5-agent EuRoC-sized synthetic map (2000 KF / 100k LM / ~800k obs, 1000 ORB features per KF): "
-            "visual-inertial global-BA trust-region iterations + ORB k-NN(k=2)+ratio-filter of one query KF vs every KF")
-
-
-def _cores():
-    """usable host cores: affinity mask capped by the cgroup CPU quota (the GPU boxes expose 128 CPUs with a 16-core quota)"""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    try:
-        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
-        if q != "max":
-            n = max(1, min(n, int(int(q) / int(per))))
-    except Exception:
-        pass
-    return n
-
-
-def cpu_baseline_match(budget_s=10.0):
+def cpu_match_port(budget_s=8.0):
     """oracle port (OpenMP, all cores) on a bounded sample of the same workload."""
     from covins_b200 import synth
     from oracle import knn as ora
@@ -187,26 +223,45 @@ def cpu_baseline_match(budget_s=10.0):
                       f"{reps} repetitions in {dt:.1f} s"}
 
 
-def cpu_baseline_gba(iters=3, config=None):
-    """The CPU restatement of the Ceres/robopt path (oracle/ba_oracle.py: torch fp64 autograd + scipy sparse Schur +
-    LAPACK Cholesky) on a bounded sample.  The reference binary itself is not buildable offline."""
-    import torch
-    from covins_b200 import synth_map
-    from oracle import ba_oracle as bo
-    config = config or os.environ.get("COVINS_CPU_GBA_CONFIG", "C1")
+def cpu_sift_port(budget_s=6.0):
+    from covins_b200 import synth
+    from oracle import knn as ora
     cores = _cores()
-    torch.set_num_threads(min(cores, 32))
-    p = synth_map.make_config(config)
-    pr = bo.Problem(p, visual_only=False, loop_loss=1.0)
-    t0 = time.perf_counter()
-    res = bo.solve(pr, iters)
+    n_cand, nf = 64, 300
+    desc, _ = synth.sift_keyframes(seed=5, n_kf=n_cand + 1, n_feat=nf)
+    q, t, seg = desc[0], desc[1:].reshape(-1, 128), synth.seg_ptr_uniform(n_cand, nf)
+    ora.knn_l2_batch(q, t, seg, 2, threads=cores)
+    t0 = time.perf_counter(); reps = 0
+    while time.perf_counter() - t0 < budget_s and reps < 400:
+        ora.knn_l2_batch(q, t, seg, 2, threads=cores); reps += 1
     dt = time.perf_counter() - t0
-    n = max(res["iterations"], 1)
-    return {"value": n / dt, "unit": "iterations/s", "cores": min(cores, 32), "kind": "port",
-            "sample": f"oracle/ba_oracle.py (restated Ceres dogleg + Schur, torch/scipy/LAPACK threads={min(cores, 32)}): "
-                      f"{n} trust-region iterations of the visual-inertial GBA on synthetic config {config} "
-                      f"({p['K']} KF / {p['L']} LM / {len(p['obs_kf'])} obs) in {dt:.1f} s incl. problem build — a bounded "
-                      f"sample: the C3 problem takes minutes per iteration on the CPU path"}
+    return {"value": n_cand * nf * nf * reps / dt / 1e9, "unit": "Gpairs/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/knn_oracle.c (exact brute-force L2, OpenMP x{cores}): 300 SIFT queries vs {n_cand} candidate KFs x 300 rows, {reps} repetitions in {dt:.1f} s"}
+
+
+# ==================================================================================================
+# reference arm
+# ==================================================================================================
+def run_reference(args):
+    rank, world, _ = dist_info()
+    if rank != 0:
+        return
+    gba, e2e = cpu_gba(args.gba_config, args.steps, warmup=min(args.warmup, 1))
+    match_base, ms_match = cpu_match_cv2(args.steps, args.warmup)
+    match = {"metric": "match_gpairs_per_sec", "value": match_base["value"], "unit": "Gpairs/s", "ms_per_step": ms_match,
+             "cpu_baseline": match_base}
+    line = {
+        "impl": "reference", "metric": "gba_iterations_per_sec", "value": gba["value"], "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": gba["iterations"], "warmup": min(args.warmup, 1), "ms_per_step": 1e3 / gba["value"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "gba_config": args.gba_config,
+                   "note": "same map, same solve and the same number of trust-region iterations as the GPU arm; the matching "
+                           "leg is a bounded sample (48 candidate keyframes per step), see match.cpu_baseline.sample"},
+        "cpu_baseline": gba,
+        "e2e": {"value": e2e, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "match": match, "match_gpairs_per_sec": match["value"],
+    }
+    print(json.dumps(line))
 
 
 # ==================================================================================================
@@ -225,6 +280,25 @@ def fp64_gemm_peak(dev):
         e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def int8_gemm_peak(dev):
+    """int8 x int8 -> int32 tensor throughput of this GPU (cuBLASLt IGEMM 8192^3 via torch._int_mm): the measured
+    denominator of the kind::i8 matcher (MEASURED_PEAKS.json holds no int8 figure)."""
+    import torch
+    try:
+        n = 8192
+        a = torch.randint(-8, 8, (n, n), device=dev, dtype=torch.int8); b = torch.randint(-8, 8, (n, n), device=dev, dtype=torch.int8)
+        torch._int_mm(a, b); torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12, "cuBLASLt IGEMM 8192^3 (torch._int_mm) measured in this run"
+    except Exception as ex:  # noqa: BLE001
+        bf = _measured().get("bf16_tflops", 1590.0)
+        return 2.0 * bf, f"2 x bf16_tflops of MEASURED_PEAKS.json (torch._int_mm unavailable: {type(ex).__name__})"
 
 
 def run_ours(args):
@@ -254,25 +328,27 @@ def run_ours(args):
         return v
 
     # =============================================================================================
-    # leg 1: global BA (strong scaling: the same C3 map, landmark blocks sharded over ranks, the reduced normal
-    # equations all-reduced over NVLink every iteration)
+    # leg 1: global BA (strong scaling: the same C3 map; landmark blocks sharded over ranks, the reduced camera system
+    # reduce-scattered onto tile-column owners over NVLink, factorisation distributed by tile columns)
     # =============================================================================================
     t_gen = time.perf_counter()
     prob = synth_map.make_config(args.gba_config)
     t_gen = time.perf_counter() - t_gen
     n_obs = len(prob["obs_kf"])
     solver = O.BaSolver(ctx, prob, visual_only=False, rank=rank, world=world, allreduce=O.torch_allreduce() if world > 1 else None)
+    p2p = bool(solver.p2p)
 
     def run_iters(n):
         done = 0
         while done < n:
             k = solver.iterate(n - done)
             done += k
-            if done < n:            # converged / terminated early: start again from the initial state
+            if done < n:            # converged / terminated early: back to the initial state (cvb_ba_restart), solve again
                 solver.restart()
         return done
 
     run_iters(args.warmup)
+    solver.restart()                # the timed region starts from the initial state: its first iterations are real work
     solver.timing(reset=True)
     ctx.sync(); barrier()
     l0 = ctx.launch_count()
@@ -300,7 +376,7 @@ def run_ours(args):
         t1 = time.perf_counter()
         done = s2.iterate(e2e_iters)
         t2 = time.perf_counter()
-        r2 = s2.result()
+        r2 = s2.result()   # noqa: F841  (the D2H read-back is part of the call)
         ctx.sync()
         e2e_runs.append((max_over_ranks(time.perf_counter() - t0), done))
         if os.environ.get("COVINS_BENCH_VERBOSE") and rank == 0:
@@ -318,6 +394,7 @@ def run_ours(args):
         edges = O.pgo_edges(prob, prob["pose"])
         pp = dict(K=prob["K"], L=0, pose=prob["pose"], pose_const=prob["pose_const"], extr=prob["extr"], cam_of_kf=prob.get("cam_of_kf"))
         ps = O.BaSolver(ctx, pp, visual_only=True, cauchy_reproj=0.0, cauchy_edge=0.5, edges=edges)
+
         def pgo_iters(n):
             done_ = 0
             while done_ < n:
@@ -327,25 +404,39 @@ def run_ours(args):
                     ps.restart()
             return done_
         pgo_steps = max(args.steps, 10)
-        pgo_iters(args.warmup)
+        pgo_iters(args.warmup); ps.restart()
         ctx.sync(); lp = ctx.launch_count(); t0 = time.perf_counter()
         pgo_iters(pgo_steps)
         ctx.sync(); dt_pgo = time.perf_counter() - t0
         rp = ps.result(); ps.close()
+        n_e = int(len(edges["i"]))
+        pgo_bytes = (2 * 56 + 48 * 8) * n_e + 288 * (prob["K"] + n_e)          # per-iteration algorithmic bytes
         pgo = {"metric": "pgo_iterations_per_sec", "value": pgo_steps / dt_pgo, "unit": "iterations/s", "ms_per_step": dt_pgo / pgo_steps * 1e3,
                "steps": pgo_steps, "gpu_launches": int(ctx.launch_count() - lp), "dtype": "f64",
                "config": {"workload": "PoseGraphOptimization on the same map: poses only (6K dofs), loop + successor + predecessor between-factors",
-                          "K": int(prob["K"]), "n_edges": int(len(edges["i"])), "n_loop": int(edges["robust"].sum())},
-               "initial_cost": rp["initial_cost"], "final_cost": rp["final_cost"]}
-    # roofline of the dominant GBA kernel: syrk_kernel (FP64 DMMA trailing update of the dense RCS Cholesky)
+                          "K": int(prob["K"]), "n_edges": n_e, "n_loop": int(edges["robust"].sum())},
+               "initial_cost": rp["initial_cost"], "final_cost": rp["final_cost"],
+               "roofline": {"bound": "hbm", "achieved": pgo_bytes / (dt_pgo / pgo_steps) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": pgo_bytes / (dt_pgo / pgo_steps) / 1e9 / hbm_peak, "traffic": None,
+                            "note": "latency-bound: a 12k-dof block-banded system factored as dependent tile columns; the roofline "
+                                    "says how far from bandwidth-bound this leg is"}}
+        if world == 1 and not os.environ.get("COVINS_SKIP_CPU_BASELINE"):
+            pgo["cpu_baseline"] = cpu_pgo(prob, edges, 10)
+    # roofline of the dominant GBA kernel: syrk_kernel (FP64 DMMA trailing update of the tile-sparse Cholesky)
     dgemm_peak = fp64_gemm_peak(dev) if rank == 0 else 0.0
+    # factor_flops = tile-GEMM flops THIS rank executed; world > 1: the work is split by tile columns
     chol_tflops = tm["factor_flops"] / (tm["factor_ms"] * 1e-3) / 1e12 if tm["factor_ms"] > 0 else 0.0
 
     # =============================================================================================
     # leg 2: matching (weak scaling: every rank holds a C3-sized shard of keyframes; no data-path collective)
     # =============================================================================================
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
-    maps = [torch.randint(0, 256, (N_KF * N_FEAT, 32), dtype=torch.uint8, device=dev, generator=g) for _ in range(N_COPIES)]
+    # ORB-like keyframes with shared landmarks (synth.orb_keyframes: matched Hamming ~16, unmatched ~128), so the ratio test
+    # accepts real matches and the compaction / D2H of accepted matches is exercised; copy c = the map with its keyframes rotated
+    base_desc, _ = synth.orb_keyframes(seed=3 + rank, n_kf=N_KF, n_feat=N_FEAT)
+    h_base = np.ascontiguousarray(base_desc.reshape(N_KF * N_FEAT, 32))
+    d_base = torch.from_numpy(h_base).to(dev)
+    maps = [d_base] + [torch.roll(d_base.view(N_KF, N_FEAT, 32), 97 * c, 0).reshape(-1, 32).contiguous() for c in range(1, N_COPIES)]
     q = maps[0][123 * N_FEAT:124 * N_FEAT].clone()
     h_seg = synth.seg_ptr_uniform(N_KF, N_FEAT)
     d_seg = torch.from_numpy(h_seg).to(dev)
@@ -362,11 +453,12 @@ def run_ours(args):
     l0 = ctx.launch_count()
     e0.record()
     for i in range(m_steps):
-        step_match(i)
+        out_m = step_match(i)
     e1.record()
     barrier()
     ms_match = max_over_ranks(e0.elapsed_time(e1))
     match_launches = ctx.launch_count() - l0
+    n_accepted = int(out_m[2].sum().item())
     gp = pairs * world * m_steps / (ms_match * 1e-3) / 1e9
 
     h_q = q.cpu().pin_memory().numpy()
@@ -386,7 +478,7 @@ def run_ours(args):
     dbs = []
     for c in range(N_COPIES):
         db = M.DescriptorDatabase(ctx, reserve_rows=N_KF * N_FEAT)
-        db.append(h_maps_np[c % 2] if c < 2 else maps[c].cpu().numpy(), np.full(N_KF, N_FEAT, np.int32))
+        db.append(h_maps_np[c] if c < 2 else maps[c].cpu().numpy(), np.full(N_KF, N_FEAT, np.int32))
         dbs.append(db)
     h_queries = [np.ascontiguousarray(h_maps_np[0][k * N_FEAT:(k + 1) * N_FEAT]) for k in (123, 777, 1500, 42)]
     db_steps = max(args.steps, 30)
@@ -412,8 +504,7 @@ def run_ours(args):
     hbm_gbs = alg_bytes / (ms_step * 1e-3) / 1e9
     # dominant kernel: tc_scan_kernel<TcHamming,2> — u8 x u8 -> s32 tcgen05 GEMM (K = 256 expanded bits) + fused top-2/filter
     tops = 2.0 * 256 * pairs / (ms_step * 1e-3) / 1e12
-    bf16_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0
-    i8_peak = 2.0 * bf16_peak
+    i8_peak, i8_src = int8_gemm_peak(dev) if rank == 0 else (1.0, "")
     # the scalar POPC kernel (previous formulation, still used for small / DenseMatcher shapes) for comparison
     os.environ["COVINS_B200_MATCH_KERNEL"] = "popc"
     for i in range(2):
@@ -439,8 +530,13 @@ def run_ours(args):
             M.knn_match_l2(ctx, qs, ts, (ds, hs), 2)
         e1.record(); torch.cuda.synchronize()
         ms_l2 = e0.elapsed_time(e1) / 5
+        l2_tops = 2.0 * 128 * n_kf5 * nf5 * nf5 / (ms_l2 * 1e-3) / 1e12
         sift = {"metric": "match_l2_gpairs_per_sec", "value": n_kf5 * nf5 * nf5 / (ms_l2 * 1e-3) / 1e9, "unit": "Gpairs/s",
-                "ms_per_step": ms_l2, "config": "C5 shard: 300 SIFT queries vs 10000 KF x 300 rows x 128-d u8 (384 MB), k=2, exact brute force"}
+                "ms_per_step": ms_l2, "config": "C5 shard: 300 SIFT queries vs 10000 KF x 300 rows x 128-d u8 (384 MB), k=2, exact brute force",
+                "roofline": {"bound": "tensor", "achieved": l2_tops, "peak": i8_peak, "unit": "TOP/s", "frac": l2_tops / i8_peak, "traffic": None,
+                             "peak_source": i8_src}}
+        if world == 1 and not os.environ.get("COVINS_SKIP_CPU_BASELINE"):
+            sift["cpu_baseline"] = cpu_sift_port()
         del ts
     # Landmark::ComputeDescriptor batched over the C3 map's landmarks: 100k landmarks x 8 observers
     lmdesc = None
@@ -462,11 +558,14 @@ def run_ours(args):
                                "frac": b7 / (ms7 * 1e-3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_launch": b7,
                                "note": "32 B per observation read once + 36 B per landmark written; includes the clone of the old descriptors"}}
         del c7
+    tr_match, tr_match_src = _traffic("tc_scan_kernel_hamming")
     match = {
         "metric": "match_gpairs_per_sec", "value": gp, "unit": "Gpairs/s", "ms_per_step": ms_step, "steps": m_steps,
         "scaling": "weak", "dtype": "u8",
         "config": {"workload": "fused k-NN(k=2)+ratio filter of one 1000-feature ORB query KF against the 2000 KFs x 1000 "
                                "features of the rank's map shard (cvb_match_hamming_batch_dev, inputs resident in HBM)",
+                   "data": "synth.orb_keyframes: keyframes share landmarks (matched Hamming ~16, unmatched ~128)",
+                   "accepted_matches_per_step": n_accepted,
                    "pairs_per_step_per_gpu": pairs,
                    "l2_policy": f"{N_COPIES} map copies (256 MB > 126 MB L2) rotated per step",
                    "parallelism": f"map sharded by keyframe x{world}, no data-path collective"},
@@ -482,31 +581,32 @@ def run_ours(args):
                                       "api": "cvb_match_hamming_batch: the whole 64 MB map re-uploaded from host memory on "
                                              "every call and the dense [n_kf][nq] result matrices downloaded (PCIe-bound)"}},
         "gpu_launches": int(match_launches),
-        "roofline": {"bound": "tensor", "achieved": tops, "peak": i8_peak, "unit": "TOP/s", "frac": tops / i8_peak, "traffic": 67.5e6,
-                     "traffic_note": "bytes per launch from profiles/r01_ncu_summary.md §2 (ncu --set full of this launch: dram read 64.1 MB + write 3.4 MB; algorithmic 80 MB incl. 16 MB of results still in L2 at capture end)",
-                     "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (kind::i8 issues at twice the bf16 rate); no measured int8 figure exists",
+        "roofline": {"bound": "tensor", "achieved": tops, "peak": i8_peak, "unit": "TOP/s", "frac": tops / i8_peak, "traffic": tr_match,
+                     "traffic_source": tr_match_src, "peak_source": i8_src,
                      "kernel": "cvb_tc::tc_scan_kernel<TcHamming,2> (tcgen05.mma kind::i8, TMEM accumulators, fused top-2 + ratio filter)",
-                     "note": "ncu: tensor pipe ~30 % active, ALU pipe ~60 %: the per-pair integer min/max selection in the epilogue "
-                             "co-limits the kernel; HBM is irrelevant (see hbm)",
                      "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": hbm_peak, "frac": hbm_gbs / hbm_peak, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes},
                      "scalar_popc_kernel": {"ms_per_step": ms_popc, "gpairs_per_s": pairs / (ms_popc * 1e-3) / 1e9,
                                             "int_pipe_frac": (8 * pairs / (ms_popc * 1e-3) / 1e9) / popc_peak if popc_peak else None,
-                                            "peak_gpopc_s": popc_peak, "note": "previous formulation: 94 % of the POPC-pipe roofline"}},
+                                            "peak_gpopc_s": popc_peak}},
         "sift_l2": sift,
         "landmark_descriptor": lmdesc,
     }
 
+    tr_gba, tr_gba_src = _traffic("syrk_kernel")
     line = {
         "metric": "gba_iterations_per_sec", "value": gba_rate, "unit": "iterations/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt_gba / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "gba_config": args.gba_config, "K": int(prob["K"]), "L": int(prob["L"]), "n_obs": int(n_obs),
                    "n_imu": int(len(prob["imu_i"])), "n_loop": int(len(prob["loop_i"])), "reduced_system_dim": int(15 * prob["K"]),
-                   "l2_policy": "working set (0.8 GB of touched tiles of the reduced camera system + 0.5 GB of observation records at C3) >> 126 MB L2",
-                   "parallelism": f"landmark blocks sharded x{world}; all-reduce of the reduced normal equations; solve replicated",
-                   "iteration_counting": "trust-region iterations as Ceres counts them (accepted + rejected); the solver is "
-                                         "restarted from the initial state if it converges inside the timed region",
+                   "l2_policy": "working set (0.8 GB of packed tiles of the reduced camera system + 0.5 GB of observation records at C3) >> 126 MB L2",
+                   "parallelism": (f"landmark blocks sharded x{world}; reduced camera system reduce-scattered by peer pull (CUDA IPC over NVLink) onto "
+                                   f"tile-column owners; Cholesky distributed by tile columns, panels handed over through peer memory; small vectors all-reduced (NCCL)"
+                                   if p2p else f"landmark blocks sharded x{world}; all-reduce of the reduced normal equations; solve replicated") if world > 1 else "single GPU",
+                   "peer_path": p2p,
+                   "iteration_counting": "trust-region iterations as Ceres counts them (accepted + rejected); the timed region starts at the "
+                                         "initial state; a solve that converges inside it is restarted from the initial state (cvb_ba_restart)",
                    "map_generation_s": round(t_gen, 1)},
         "e2e": {"value": done / dt_e2e, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_gba // max(done, 1)),
                 "d2h_bytes_per_step": int(d2h_gba // max(done, 1)), "steps": int(done),
@@ -518,18 +618,24 @@ def run_ours(args):
         "device_ms_per_step": dev_ms / args.steps,
         "final_cost": res["final_cost"], "initial_cost": res["initial_cost"],
         "roofline": {"bound": "tensor", "achieved": chol_tflops, "peak": dgemm_peak, "unit": "TFLOP/s",
-                     "frac": chol_tflops / dgemm_peak if dgemm_peak else None, "traffic": 1.073e9,
-                     "traffic_note": "bytes of ONE syrk_kernel launch (bulk update of the first pose tile column at C3, 4278 tile pairs) from profiles/r01_ncu_summary.md §3: dram read 570 MB + write 503 MB = each C tile read and written once (algorithmic 4278 x 256 KB = 1.12 GB); operands served by L2",
+                     "frac": chol_tflops / dgemm_peak if dgemm_peak else None, "traffic": tr_gba, "traffic_source": tr_gba_src,
                      "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (FP64; MEASURED_PEAKS.json holds no FP64 figure)",
-                     "kernel": "cvb_chol::syrk_kernel (FP64 DMMA m8n8k4, 64x64x128 per CTA, 3 CTAs/SM) inside the tile-sparse Cholesky of the reduced camera system; achieved = executed tile-GEMM flops / factorisation time (includes the latency-bound diagonal-tile chain)",
+                     "kernel": "cvb_chol::syrk_kernel (FP64 DMMA m8n8k4, 64x64x128 per CTA, 3 CTAs/SM) inside the tile-sparse Cholesky of the reduced camera system; "
+                               "achieved = tile-GEMM flops executed by rank 0 / factorisation time (includes the latency-bound diagonal-tile chain)",
                      "flops_per_factorisation_dense_equivalent": (15.0 * prob["K"]) ** 3 / 3.0},
         "match": match,
         "pgo": pgo,
+        # scalars of the nested legs at the top level (per-N scaling records keep them)
+        "match_gpairs_per_sec": gp, "match_e2e_gpairs_per_sec": e2e_db_gp,
+        "pgo_iterations_per_sec": pgo["value"] if pgo else None,
+        "sift_l2_gpairs_per_sec": sift["value"] if sift else None,
+        "gba_e2e_iterations_per_sec": done / dt_e2e,
     }
     if rank == 0:
         if world == 1 and not os.environ.get("COVINS_SKIP_CPU_BASELINE"):
-            line["cpu_baseline"] = cpu_baseline_gba(3)
-            line["match"]["cpu_baseline"] = cpu_baseline_match()
+            # bounded sample of the same workload on the host cores (the full same-steps run is `--impl reference`)
+            line["cpu_baseline"], _ = cpu_gba(args.gba_config, 4)
+            line["match"]["cpu_baseline"] = cpu_match_port()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

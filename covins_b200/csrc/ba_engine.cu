@@ -17,8 +17,15 @@
 // Every accumulation is a gather in a fixed order (no floating-point atomics): results are bit-reproducible.
 //
 // HBM layout: per observation an 160-B record {r[2], Jp[12], Jl[6]} and a 288-B record {W[18], Y[18]} (AoS so the
-// per-keyframe and per-pair gathers read whole records), per landmark Hll/Hll^-1/b (15 doubles), S dense
-// row-major (n_c_pad^2 doubles, lower triangle), state double-buffered for accept/reject.
+// per-keyframe and per-pair gathers read whole records), per landmark Hll/Hll^-1/b (15 doubles), S as the packed list
+// of the 128x128 tiles of L's structure (cholesky.cuh: TilePlan::h_tile_of; lower triangle), state double-buffered for
+// accept/reject.
+//
+// Multi-GPU (one process per GPU): landmark blocks are sharded, every rank builds its partial S; the tile columns of S
+// are OWNED by ranks (IMU chain → one rank, pose columns cyclic).  With peer access (CUDA IPC over NVLink,
+// cvb_ba_enable_p2p) the owners pull-and-sum the partial tiles of their columns out of the peers' memory (reduce-scatter
+// without a staging buffer) and the factorisation is distributed by columns (cholesky.cu: DistView); without it the
+// packed tiles are all-reduced through the injected collective and the factorisation is replicated.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -52,6 +59,19 @@ struct ObsWY {
 __device__ __forceinline__ int cam_col(const int* __restrict__ off_pose, const int* __restrict__ off_sb, int kf, int c) {
   return c < 6 ? off_pose[kf] + c : off_sb[kf] + (c - 6);
 }
+
+// View of the packed reduced camera system: element (r >= c) lives in tile (r/128, c/128) of L's structure.
+struct SView {
+  double* p;
+  const int* __restrict__ tile_of;
+  int nt;
+};
+__device__ __forceinline__ double* s_at(const SView& S, int r, int c) {
+  const int t = S.tile_of[(size_t)(r >> 7) * S.nt + (c >> 7)];
+  if (t < 0) __trap();   // an element outside L's structure (or above the diagonal): a bug, never silent
+  return S.p + ((size_t)t << 14) + ((r & 127) << 7) + (c & 127);
+}
+static_assert(cvb_chol::T == 128, "s_at assumes 128-wide tiles");
 
 constexpr int RED_BLOCKS = 512;   // fixed grid for reducing kernels → fixed summation order
 constexpr int RED_SLOTS = 8;
@@ -95,11 +115,20 @@ struct Engine {
   DevArr<double> pose[2], sb[2], lm[2];
   DevArr<double> pose0, sb0, lm0;   // the state the problem was created with (cvb_ba_restart returns to it)
   DevArr<uint8_t> pose_const;
-  DevArr<int> off_pose, off_sb, xt_i, xt_j;   // xt_*: tile list of the multi-GPU exchange
-  DevArr<int> zt_i, zt_j;                     // tiles of L's structure (incl. fill): the only part of S that is ever read
-  int n_zt = 0;
-  DevArr<double> xbuf;
-  int n_xt = 0;
+  DevArr<int> off_pose, off_sb;
+  // multi-GPU exchange of the reduced camera system: packed ids of the structurally non-zero (pre-fill) tiles — all of
+  // them (all-reduce fallback, through xbuf) / those of the tile columns this rank owns (reduce-scatter by peer pull)
+  DevArr<int> xt_all, xt_own, col_owner;
+  DevArr<double> xbuf, flagd;
+  int n_xt_all = 0, n_xt_own = 0;
+  size_t n_tiles = 0;                           // tiles of L's structure = length of S in tiles
+  // peer access (CUDA IPC): S, linv and the panel flags of every rank are mapped here (cvb_ba_enable_p2p)
+  bool p2p = false;
+  double* S_raw = nullptr;                      // cudaMalloc'ed (IPC-exportable) when world > 1, else pool memory
+  double* linv_raw = nullptr;
+  int* pflag_raw = nullptr;
+  cvb_chol::DistView dv;
+  double** d_peer_S = nullptr;
   std::vector<int> h_off_pose, h_off_sb;
   cvb_chol::TilePlan plan;
   DevArr<double> extr_kf, intr_kf, dist_kf;
@@ -156,7 +185,7 @@ struct Engine {
     };
     for (int i = 0; i < 2; i++) { pose[i].free_(); sb[i].free_(); lm[i].free_(); }
     pose0.free_(); sb0.free_(); lm0.free_();
-    pose_const.free_(); off_pose.free_(); off_sb.free_(); xt_i.free_(); xt_j.free_(); zt_i.free_(); zt_j.free_(); xbuf.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
+    pose_const.free_(); off_pose.free_(); off_sb.free_(); xt_all.free_(); xt_own.free_(); col_owner.free_(); xbuf.free_(); flagd.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
     obs_kf.free_(); obs_lm.free_(); lm_ptr.free_(); kf_ptr.free_(); kf_obs.free_(); obs_uv.free_(); obs_sigma.free_();
     lin.free_(); wy.free_(); Hll.free_(); HllInv.free_(); bl.free_();
     pre.free_(); imu_i.free_(); imu_j.free_(); Jimu.free_(); rimu.free_();
@@ -165,8 +194,22 @@ struct Engine {
     fb_hi.free_(); fb_lo.free_(); fb_ptr.free_(); ft_type.free_(); ft_fac.free_(); ft_rhi.free_(); ft_rlo.free_();
     sb_hi.free_(); sb_lo.free_(); sb_ptr.free_(); sp_a.free_(); sp_b.free_();
     scale.free_(); colsq.free_(); diag.free_(); gvec.free_(); grad.free_(); sgrad.free_(); gn.free_(); step.free_();
-    xsol.free_(); yb.free_(); gs.free_(); tmp.free_(); S.free_(); linv.free_(); flag.free_(); partials.free_();
+    xsol.free_(); yb.free_(); gs.free_(); tmp.free_();
+    if (S_raw) { S.p = nullptr; linv.p = nullptr; }
+    S.free_(); linv.free_(); flag.free_(); partials.free_();
     scalars.free_(); rankmax.free_();
+    for (int g = 0; g < dv.world && p2p; g++) {
+      if (g == dv.rank) continue;
+      if (dv.peer_S[g]) cudaIpcCloseMemHandle(dv.peer_S[g]);
+      if (dv.peer_linv[g]) cudaIpcCloseMemHandle(dv.peer_linv[g]);
+      if (dv.peer_flag[g]) cudaIpcCloseMemHandle(dv.peer_flag[g]);
+    }
+    if (S_raw) cudaFree(S_raw);
+    if (linv_raw) cudaFree(linv_raw);
+    if (pflag_raw) cudaFree(pflag_raw);
+    if (dv.d_epoch) cudaFree(dv.d_epoch);
+    if (dv.d_peer_flag) cudaFree(dv.d_peer_flag);
+    if (d_peer_S) cudaFree(d_peer_S);
     lap("device arrays");
     if (h_scalars) cudaFreeHost(h_scalars);
     lap("pinned scalars");
@@ -344,7 +387,7 @@ __global__ void obs_Y_kernel(int n_obs, const int* __restrict__ obs_lm, const do
 __global__ void __launch_bounds__(128) kf_visual_kernel(int K, const int* __restrict__ kf_ptr, const int* __restrict__ kf_obs,
                                                         const int* __restrict__ obs_lm, const ObsLin* __restrict__ lin,
                                                         const ObsWY* __restrict__ wy, const double* __restrict__ bl,
-                                                        const int* __restrict__ off_pose, size_t ld, double* __restrict__ S,
+                                                        const int* __restrict__ off_pose, SView S,
                                                         double* __restrict__ g_c, double* __restrict__ yb, int what) {
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (k >= K) return;
@@ -382,11 +425,11 @@ __global__ void __launch_bounds__(128) kf_visual_kernel(int K, const int* __rest
     }
   }
   if (lane == 0) {
-    const size_t base = (size_t)off_pose[k];
+    const int base = off_pose[k];
     if (what == 0) {
       int idx = 0;
       for (int r = 0; r < 6; r++)
-        for (int c = 0; c <= r; c++) S[(base + r) * ld + base + c] = h[idx++];   // lower triangle only
+        for (int c = 0; c <= r; c++) *s_at(S, base + r, base + c) = h[idx++];   // lower triangle only
       for (int r = 0; r < 6; r++) g_c[base + r] = b[r];
     } else {
       for (int r = 0; r < 6; r++) yb[base + r] = y[r];
@@ -624,8 +667,8 @@ __global__ void __launch_bounds__(256) factor_gather_kernel(int n_fb, const int*
                                                             const int* __restrict__ ft_rlo, const double* __restrict__ Jimu,
                                                             const double* __restrict__ rimu, const double* __restrict__ Jedge,
                                                             const double* __restrict__ redge, const int* __restrict__ off_pose,
-                                                            const int* __restrict__ off_sb, int per, size_t ld,
-                                                            double* __restrict__ S, double* __restrict__ g_c) {
+                                                            const int* __restrict__ off_sb, int per, SView S,
+                                                            double* __restrict__ g_c) {
   const int b = blockIdx.x;
   if (b >= n_fb) return;
   const int hi = fb_hi[b], lo = fb_lo[b];
@@ -633,10 +676,12 @@ __global__ void __launch_bounds__(256) factor_gather_kernel(int n_fb, const int*
   if (r >= 15) return;
   if (hi == lo && c > r) return;
   double acc = 0.0, gacc = 0.0;
+  bool touched = false;   // an entry no factor of this block reaches is not part of S's structure (edge-only blocks: 6x6)
   for (int t = fb_ptr[b]; t < fb_ptr[b + 1]; t++) {
     const int type = ft_type[t], f = ft_fac[t];
     const int d = type == 0 ? 15 : 6, rows = type == 0 ? 15 : 6, ncol = type == 0 ? 30 : 12;
     if (r >= d || c >= d) continue;
+    touched = true;
     const double* J = (type == 0 ? Jimu + (size_t)f * 450 : Jedge + (size_t)f * 72);
     const double* res = (type == 0 ? rimu + (size_t)f * 15 : redge + (size_t)f * 6);
     const int ca = ft_rhi[t] * d + r, cb = ft_rlo[t] * d + c;
@@ -648,20 +693,19 @@ __global__ void __launch_bounds__(256) factor_gather_kernel(int n_fb, const int*
     acc += s;
     gacc += gs;
   }
-  if (r < per && c < per) {
+  if (touched && r < per && c < per) {
     int ri = cam_col(off_pose, off_sb, hi, r), ci = cam_col(off_pose, off_sb, lo, c);
     if (ri < ci) { const int t2 = ri; ri = ci; ci = t2; }
-    S[(size_t)ri * ld + ci] += acc;
+    *s_at(S, ri, ci) += acc;
   }
-  if (hi == lo && c == 0 && r < per) g_c[cam_col(off_pose, off_sb, hi, r)] += gacc;
+  if (touched && hi == lo && c == 0 && r < per) g_c[cam_col(off_pose, off_sb, hi, r)] += gacc;
 }
 
 // camera part, step 1: colsq = diag(J^T J) (before damping / Schur)
-__global__ void cam_colsq_kernel(int n_c_pad, const double* __restrict__ scale, size_t ld, const double* __restrict__ S,
-                                 double* __restrict__ colsq) {
+__global__ void cam_colsq_kernel(int n_c_pad, const double* __restrict__ scale, SView S, double* __restrict__ colsq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_c_pad) return;
-  colsq[i] = scale[i] != 0.0 ? S[(size_t)i * ld + i] : 0.0;
+  colsq[i] = scale[i] != 0.0 ? *s_at(S, i, i) : 0.0;
 }
 __global__ void cam_diag_kernel(int n_c_pad, const double* __restrict__ scale, const double* __restrict__ colsq,
                                 double* __restrict__ diag) {
@@ -669,18 +713,22 @@ __global__ void cam_diag_kernel(int n_c_pad, const double* __restrict__ scale, c
   if (i >= n_c_pad) return;
   diag[i] = scale[i] != 0.0 ? sqrt(clamp_diag(colsq[i])) : 1.0;
 }
-// camera part, step 2 (after the Schur subtraction): damping, reduced gradient, inactive rows → identity
-__global__ void cam_finish_kernel(int n_c_pad, const double* __restrict__ scale, size_t ld, double* __restrict__ S,
+// camera part, step 2 (after the Schur subtraction): damping, reduced gradient, inactive rows → identity.  With a column
+// owner map (distributed factorisation) a rank finishes only the diagonal of ITS tile columns — the others' diagonal
+// tiles still hold this rank's partial sums, which their owners may be reading over NVLink at this moment.
+__global__ void cam_finish_kernel(int n_c_pad, const double* __restrict__ scale, SView S,
                                   const double* __restrict__ diag, const double* __restrict__ g_c,
-                                  const double* __restrict__ yb, double* __restrict__ gs, double mu) {
+                                  const double* __restrict__ yb, double* __restrict__ gs, double mu,
+                                  const int* __restrict__ col_owner, int rank) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_c_pad) return;
+  const bool mine = col_owner == nullptr || col_owner[i >> 7] == rank;
   if (scale[i] != 0.0) {
     const double dg = diag[i];
-    S[(size_t)i * ld + i] += mu * dg * dg;
+    if (mine) *s_at(S, i, i) += mu * dg * dg;
     gs[i] = g_c[i] - yb[i];
   } else {
-    S[(size_t)i * ld + i] = 1.0;
+    if (mine) *s_at(S, i, i) = 1.0;
     gs[i] = 0.0;
   }
 }
@@ -689,7 +737,7 @@ __global__ void cam_finish_kernel(int n_c_pad, const double* __restrict__ scale,
 __global__ void __launch_bounds__(128) schur_kernel(int n_sb, const int* __restrict__ sb_hi, const int* __restrict__ sb_lo,
                                                     const int* __restrict__ sb_ptr, const int* __restrict__ sp_a,
                                                     const int* __restrict__ sp_b, const ObsWY* __restrict__ wy,
-                                                    const int* __restrict__ off_pose, size_t ld, double* __restrict__ S) {
+                                                    const int* __restrict__ off_pose, SView S) {
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= n_sb) return;
   double acc[36];
@@ -720,38 +768,43 @@ __global__ void __launch_bounds__(128) schur_kernel(int n_sb, const int* __restr
       if (i == e) v = acc[i];
     // the pose columns are laid out chain by chain, so a block of keyframes hi > lo may belong above the diagonal:
     // store it transposed in the lower triangle then
-    const size_t br = (size_t)off_pose[hi], bc = (size_t)off_pose[lo];
-    if (br >= bc) S[(br + r) * ld + bc + c] -= v;
-    else S[(bc + c) * ld + br + r] -= v;
+    const int br = off_pose[hi], bc = off_pose[lo];
+    if (hi == lo && c > r) continue;   // diagonal block: lower triangle only (the packed layout has no upper tiles)
+    if (br >= bc) *s_at(S, br + r, bc + c) -= v;
+    else *s_at(S, bc + c, br + r) -= v;
   }
 }
 
-// S is cleared tile-wise: only the tiles of L's structure (symbolic fill included) are ever read or written — at C3 that is
-// 0.8 GB of the 7.4 GB dense allocation.
-__global__ void __launch_bounds__(256) zero_tiles_kernel(double* __restrict__ S, size_t ld, const int* __restrict__ ti,
-                                                         const int* __restrict__ tj) {
-  const int t = blockIdx.x;
-  double* base = S + ((size_t)ti[t] * cvb_chol::T) * ld + (size_t)tj[t] * cvb_chol::T;
+// Multi-GPU exchange without peer access: the structurally non-zero tiles of the (pre-fill) lower triangle of S are
+// packed into one buffer and summed across ranks by the injected all-reduce.  pack: tiles → buffer; unpack: buffer → tiles.
+__global__ void __launch_bounds__(256) pack_tiles_kernel(double* __restrict__ St, const int* __restrict__ tid, double* __restrict__ buf,
+                                                         int unpack) {
+  double2* t = reinterpret_cast<double2*>(St + ((size_t)tid[blockIdx.x] << 14));
+  double2* b = reinterpret_cast<double2*>(buf + ((size_t)blockIdx.x << 14));
   for (int u = threadIdx.x; u < cvb_chol::T * cvb_chol::T / 2; u += blockDim.x) {
-    const int r = u / (cvb_chol::T / 2), c = (u % (cvb_chol::T / 2)) * 2;
-    *reinterpret_cast<double2*>(base + (size_t)r * ld + c) = make_double2(0.0, 0.0);
+    if (unpack) t[u] = b[u];
+    else b[u] = t[u];
   }
 }
 
-// Multi-GPU exchange: only the structurally non-zero 128x128 tiles of the (pre-fill) lower triangle of S are summed
-// across ranks.  pack: S tiles → contiguous buffer; unpack: buffer → S tiles.
-__global__ void __launch_bounds__(256) pack_tiles_kernel(const double* __restrict__ S, size_t ld, const int* __restrict__ ti,
-                                                         const int* __restrict__ tj, double* __restrict__ buf, int unpack,
-                                                         double* __restrict__ Sw) {
-  const int t = blockIdx.x;
-  const size_t base = ((size_t)ti[t] * cvb_chol::T) * ld + (size_t)tj[t] * cvb_chol::T;
-  double* b = buf + (size_t)t * cvb_chol::T * cvb_chol::T;
-  for (int u = threadIdx.x; u < cvb_chol::T * cvb_chol::T; u += blockDim.x) {
-    const int r = u / cvb_chol::T, c = u % cvb_chol::T;
-    if (unpack) Sw[base + (size_t)r * ld + c] = b[u];
-    else b[u] = S[base + (size_t)r * ld + c];
+// Reduce-scatter by pull (peer access): the owner of a tile column adds the peers' partial tiles — read straight out of
+// their packed arrays over NVLink (same packed offset on every rank) — to its own, in rank order.  One CTA per owned
+// exchange tile; 16-byte loads, L1 bypassed (the peers' memory is written by other GPUs between launches).
+__global__ void __launch_bounds__(256) reduce_pull_kernel(double* __restrict__ St, double* const* __restrict__ peer_S, int world, int rank,
+                                                          const int* __restrict__ tid) {
+  const size_t off = (size_t)tid[blockIdx.x] << 14;
+  double2* mine = reinterpret_cast<double2*>(St + off);
+  for (int u = threadIdx.x; u < cvb_chol::T * cvb_chol::T / 2; u += blockDim.x) {
+    double2 acc = make_double2(0.0, 0.0);
+    for (int g = 0; g < world; g++) {
+      const double2 v = g == rank ? mine[u] : __ldcg(reinterpret_cast<const double2*>(peer_S[g] + off) + u);
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+    mine[u] = acc;
   }
 }
+__global__ void flag_to_double_kernel(const int* __restrict__ flag, double* __restrict__ out) { out[0] = (double)(flag[0] & 1); }
 
 // landmark back-substitution: x_l = Hll^-1 (b_l - sum W^T x_c)
 __global__ void backsub_kernel(int L, const int* __restrict__ lm_ptr, const int* __restrict__ obs_kf,
@@ -1284,21 +1337,37 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     mark(E.h_off_pose[p->edge_i[e]], 6, E.h_off_pose[p->edge_i[e]], 6);
     mark(E.h_off_pose[p->edge_j[e]], 6, E.h_off_pose[p->edge_j[e]], 6);
   }
-  std::vector<int> h_xt_i, h_xt_j;
-  for (int i = 0; i < nt; i++)
-    for (int j = 0; j <= i; j++)
-      if (tmask[(size_t)i * nt + j] || i == j) { h_xt_i.push_back(i); h_xt_j.push_back(j); }
-  E.n_xt = (int)h_xt_i.size();
-  E.plan.build(nt, tmask);
-  std::vector<int> h_zt_i, h_zt_j;
-  for (int k = 0; k < nt; k++) {
-    h_zt_i.push_back(k); h_zt_j.push_back(k);
-    for (int q = E.plan.h_col_ptr[k]; q < E.plan.h_col_ptr[k + 1]; q++) { h_zt_i.push_back(E.plan.h_row_idx[q]); h_zt_j.push_back(k); }
-  }
-  E.n_zt = (int)h_zt_i.size();
-  E.plan.h_col_group.assign(nt, -1);
+  // column groups (IMU chains) first: the owner map of a distributed factorisation follows them
+  std::vector<int> col_group(nt, -1);
   for (size_t g = 0; g < sb_ranges.size(); g++)
-    for (int t = sb_ranges[g].first / TT; t <= (sb_ranges[g].second - 1) / TT; t++) E.plan.h_col_group[t] = (int)g;
+    for (int t = sb_ranges[g].first / TT; t <= (sb_ranges[g].second - 1) / TT; t++) col_group[t] = (int)g;
+  // ownership of the tile columns (world > 1): an IMU chain's speed-bias columns — a pure latency chain — stay on one
+  // rank, the remaining (pose) columns go round the ranks in blocks of COVINS_B200_DIST_BLOCK columns (default 1)
+  std::vector<int> h_owner;
+  if (E.world > 1) {
+    int blk = 1;
+    if (const char* e = getenv("COVINS_B200_DIST_BLOCK")) blk = std::max(1, atoi(e));
+    h_owner.assign(nt, 0);
+    int seq = 0;
+    for (int k = 0; k < nt; k++) {
+      if (col_group[k] >= 0) h_owner[k] = col_group[k] % E.world;
+      else h_owner[k] = ((seq++) / blk) % E.world;
+    }
+  }
+  std::vector<uint8_t> pre_fill(tmask);
+  E.plan.build(nt, tmask, E.world > 1 ? &h_owner : nullptr, E.rank);
+  E.n_tiles = (size_t)E.plan.n_tiles_L;
+  std::vector<int> h_xt_all, h_xt_own;
+  for (int j = 0; j < nt; j++)
+    for (int i = j; i < nt; i++)
+      if (pre_fill[(size_t)i * nt + j] || i == j) {
+        const int id = E.plan.h_tile_of[(size_t)i * nt + j];
+        h_xt_all.push_back(id);
+        if (E.world > 1 && h_owner[j] == E.rank) h_xt_own.push_back(id);
+      }
+  E.n_xt_all = (int)h_xt_all.size();
+  E.n_xt_own = (int)h_xt_own.size();
+  E.plan.h_col_group = col_group;
   lap("tile structure + plan");
   // ---- by-keyframe CSR ----
   std::vector<int> h_kf_ptr(K + 1, 0), h_kf_obs(E.n_obs);
@@ -1455,17 +1524,27 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   if ((rc = upload(E, E.scale, h_scale))) return rc;
   if ((rc = upload(E, E.off_pose, E.h_off_pose)) || (rc = upload(E, E.off_sb, E.h_off_sb))) return rc;
   if ((rc = E.plan.upload(E.ctx, E.st))) return rc;
-  if ((rc = upload(E, E.zt_i, h_zt_i)) || (rc = upload(E, E.zt_j, h_zt_j))) return rc;
   if (E.world > 1) {
-    if ((rc = upload(E, E.xt_i, h_xt_i)) || (rc = upload(E, E.xt_j, h_xt_j))) return rc;
-    if ((rc = zalloc(E, E.xbuf, (size_t)E.n_xt * cvb_chol::T * cvb_chol::T))) return rc;
+    if ((rc = upload(E, E.xt_all, h_xt_all)) || (rc = upload(E, E.xt_own, h_xt_own)) || (rc = upload(E, E.col_owner, h_owner))) return rc;
+    if ((rc = zalloc(E, E.flagd, 2))) return rc;
   }
   DevArr<double>* vecs[] = {&E.colsq, &E.diag, &E.gvec, &E.grad, &E.sgrad, &E.gn, &E.step, &E.xsol, &E.yb, &E.gs, &E.tmp};
   for (auto* v : vecs)
     if ((rc = zalloc(E, *v, (size_t)E.n_vec))) return rc;
-  // S is not cleared here: every iteration clears exactly the tiles it uses (zero_tiles_kernel), nothing else is read
-  if (E.S.alloc((size_t)E.n_c_pad * E.n_c_pad)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (reduced camera system, %zu bytes)", (size_t)E.n_c_pad * E.n_c_pad * 8);
-  if ((rc = zalloc(E, E.linv, (size_t)E.n_c_pad * cvb_chol::T))) return rc;
+  // S = the packed tiles of L's structure; cleared at the start of every linearisation (cam_blocks).  With several ranks
+  // S, the tile inverses and the panel flags come from cudaMalloc so that they can be exported through CUDA IPC.
+  const size_t s_doubles = E.n_tiles * cvb_chol::T * cvb_chol::T, linv_doubles = (size_t)E.n_c_pad * cvb_chol::T;
+  if (E.world > 1) {
+    if (cudaMalloc(&E.S_raw, s_doubles * 8) != cudaSuccess || cudaMalloc(&E.linv_raw, linv_doubles * 8) != cudaSuccess ||
+        cudaMalloc(&E.pflag_raw, sizeof(int) * (size_t)E.plan.nt) != cudaSuccess)
+      return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (reduced camera system, %zu bytes)", s_doubles * 8);
+    ENG_CUDA(cudaMemsetAsync(E.linv_raw, 0, linv_doubles * 8, E.st));
+    ENG_CUDA(cudaMemsetAsync(E.pflag_raw, 0, sizeof(int) * (size_t)E.plan.nt, E.st));
+    E.S.p = E.S_raw; E.S.n = s_doubles; E.linv.p = E.linv_raw; E.linv.n = linv_doubles;
+  } else {
+    if (E.S.alloc(s_doubles)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (reduced camera system, %zu bytes)", s_doubles * 8);
+    if ((rc = zalloc(E, E.linv, linv_doubles))) return rc;
+  }
   if ((rc = zalloc(E, E.partials, (size_t)RED_SLOTS * RED_BLOCKS)) || (rc = zalloc(E, E.scalars, RED_SLOTS)) ||
       (rc = zalloc(E, E.rankmax, (size_t)E.world)))
     return rc;
@@ -1537,23 +1616,23 @@ int ar(Engine& E, double* p, size_t n) {
 // camera blocks of J^T J (before Schur / damping) into S, camera gradient into gvec
 int cam_blocks(Engine& E) {
   const size_t ld = (size_t)E.n_c_pad;
-  zero_tiles_kernel<<<E.n_zt, 256, 0, E.st>>>(E.S.p, ld, E.zt_i.p, E.zt_j.p);
-  ENG_LAUNCH();
+  const SView Sv{E.S.p, E.plan.d_tile_of, E.plan.nt};
+  ENG_CUDA(cudaMemsetAsync(E.S.p, 0, E.n_tiles * cvb_chol::T * cvb_chol::T * sizeof(double), E.st));
   ENG_CUDA(cudaMemsetAsync(E.gvec.p, 0, ld * sizeof(double), E.st));
   kf_visual_kernel<<<grid1((size_t)E.K * 32, 128), 128, 0, E.st>>>(E.K, E.kf_ptr.p, E.kf_obs.p, E.obs_lm.p, E.lin.p, E.wy.p,
-                                                                  E.bl.p, E.off_pose.p, ld, E.S.p, E.gvec.p, E.yb.p, 0);
+                                                                  E.bl.p, E.off_pose.p, Sv, E.gvec.p, E.yb.p, 0);
   ENG_LAUNCH();
   if (E.n_fb > 0) {
     factor_gather_kernel<<<E.n_fb, 256, 0, E.st>>>(E.n_fb, E.fb_hi.p, E.fb_lo.p, E.fb_ptr.p, E.ft_type.p, E.ft_fac.p,
-                                                   E.ft_rhi.p, E.ft_rlo.p, E.Jimu.p, E.rimu.p, E.Jedge.p, E.redge.p, E.off_pose.p, E.off_sb.p, E.per, ld,
-                                                   E.S.p, E.gvec.p);
+                                                   E.ft_rhi.p, E.ft_rlo.p, E.Jimu.p, E.rimu.p, E.Jedge.p, E.redge.p, E.off_pose.p, E.off_sb.p, E.per, Sv,
+                                                   E.gvec.p);
     ENG_LAUNCH();
   }
   return CVB_OK;
 }
 
 int cam_colsq(Engine& E) {
-  cam_colsq_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, (size_t)E.n_c_pad, E.S.p, E.colsq.p);
+  cam_colsq_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, SView{E.S.p, E.plan.d_tile_of, E.plan.nt}, E.colsq.p);
   ENG_LAUNCH();
   return ar(E, E.colsq.p, (size_t)E.n_c_pad);
 }
@@ -1561,6 +1640,8 @@ int cam_colsq(Engine& E) {
 // damped Schur complement + Cholesky for the given mu; *ok = false if the factorisation broke down
 int factor_rcs(Engine& E, double mu, bool* ok) {
   const size_t ld = (size_t)E.n_c_pad;
+  const SView Sv{E.S.p, E.plan.d_tile_of, E.plan.nt};
+  const bool dist = E.p2p && E.world > 1;
   tick(E, 0);
   if (E.L_in > 0) {
     lm_damp_inv_kernel<<<grid1(E.L_in), 256, 0, E.st>>>(E.L_in, E.Hll.p, E.colsq.p + E.n_c_pad, mu, E.HllInv.p);
@@ -1572,34 +1653,42 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
   }
   ENG_CUDA(cudaMemsetAsync(E.yb.p, 0, ld * sizeof(double), E.st));
   kf_visual_kernel<<<grid1((size_t)E.K * 32, 128), 128, 0, E.st>>>(E.K, E.kf_ptr.p, E.kf_obs.p, E.obs_lm.p, E.lin.p, E.wy.p,
-                                                                  E.bl.p, E.off_pose.p, ld, E.S.p, E.gvec.p, E.yb.p, 1);
+                                                                  E.bl.p, E.off_pose.p, Sv, E.gvec.p, E.yb.p, 1);
   ENG_LAUNCH();
   if (E.n_sb > 0) {
     schur_kernel<<<grid1((size_t)E.n_sb * 32, 128), 128, 0, E.st>>>(E.n_sb, E.sb_hi.p, E.sb_lo.p, E.sb_ptr.p, E.sp_a.p,
-                                                                   E.sp_b.p, E.wy.p, E.off_pose.p, ld, E.S.p);
+                                                                   E.sp_b.p, E.wy.p, E.off_pose.p, Sv);
     ENG_LAUNCH();
   }
   // the one exchange of the data path: sum the rank-partial reduced normal equations over NVLink
   int rc = CVB_OK;
-  if (E.allreduce && E.world > 1) {
-    pack_tiles_kernel<<<E.n_xt, 256, 0, E.st>>>(E.S.p, ld, E.xt_i.p, E.xt_j.p, E.xbuf.p, 0, nullptr);
+  if (E.allreduce && E.world > 1 && !dist) {
+    if (!E.xbuf.p && (rc = zalloc(E, E.xbuf, (size_t)E.n_xt_all * cvb_chol::T * cvb_chol::T))) return rc;
+    pack_tiles_kernel<<<E.n_xt_all, 256, 0, E.st>>>(E.S.p, E.xt_all.p, E.xbuf.p, 0);
     ENG_LAUNCH();
-    if ((rc = ar(E, E.xbuf.p, (size_t)E.n_xt * cvb_chol::T * cvb_chol::T))) return rc;
-    pack_tiles_kernel<<<E.n_xt, 256, 0, E.st>>>(nullptr, ld, E.xt_i.p, E.xt_j.p, E.xbuf.p, 1, E.S.p);
+    if ((rc = ar(E, E.xbuf.p, (size_t)E.n_xt_all * cvb_chol::T * cvb_chol::T))) return rc;
+    pack_tiles_kernel<<<E.n_xt_all, 256, 0, E.st>>>(E.S.p, E.xt_all.p, E.xbuf.p, 1);
     ENG_LAUNCH();
   }
+  // this all-reduce is also the hand-shake of the peer pull below: when it completes here, every rank has finished
+  // writing its partial S (stream order on each rank)
   if ((rc = ar(E, E.yb.p, ld))) return rc;
-  cam_finish_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, ld, E.S.p, E.diag.p, E.gvec.p, E.yb.p, E.gs.p, mu);
+  if (dist && E.n_xt_own > 0) {
+    reduce_pull_kernel<<<E.n_xt_own, 256, 0, E.st>>>(E.S.p, E.d_peer_S, E.world, E.rank, E.xt_own.p);
+    ENG_LAUNCH();
+  }
+  cam_finish_kernel<<<grid1(E.n_c_pad), 256, 0, E.st>>>(E.n_c_pad, E.scale.p, Sv, E.diag.p, E.gvec.p, E.yb.p, E.gs.p, mu,
+                                                        dist ? E.col_owner.p : nullptr, E.rank);
   ENG_LAUNCH();
   tick(E, 1);
   // first call: plain launches (sets kernel attributes); second call: stream-capture into a graph; then replay
   if (E.g_factor) {
     ENG_CUDA(cudaGraphLaunch(E.g_factor, E.st));
-    E.ctx->launches += 1 + (int64_t)E.plan.nt * 3;
+    E.ctx->launches += 1 + (int64_t)E.plan.nt * 3;   // kernels inside the graph (distributed: pulls are copies, not kernels)
   } else if (E.n_factor_calls == 1) {
     cudaGraph_t g = nullptr;
     ENG_CUDA(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
-    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st, &E.fs);
+    rc = cvb_chol::factor(E.ctx, E.S.p, E.linv.p, E.flag.p, E.plan, E.st, &E.fs, dist ? &E.dv : nullptr);
     cudaError_t ce = cudaStreamEndCapture(E.st, &g);
     if (rc) return rc;
     if (ce != cudaSuccess) return cvb_fail(E.ctx, CVB_ERR_CUDA, "graph capture of the factorisation failed: %s", cudaGetErrorString(ce));
@@ -1607,14 +1696,24 @@ int factor_rcs(Engine& E, double mu, bool* ok) {
     cudaGraphDestroy(g);
     ENG_CUDA(cudaGraphLaunch(E.g_factor, E.st));
   } else {
-    rc = cvb_chol::factor(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.flag.p, E.plan, E.st, &E.fs);
+    rc = cvb_chol::factor(E.ctx, E.S.p, E.linv.p, E.flag.p, E.plan, E.st, &E.fs, dist ? &E.dv : nullptr);
     if (rc) return rc;
   }
   E.n_factor_calls++;
   tick(E, 2);
   int flag = 0;
-  ENG_CUDA(cudaMemcpyAsync(&flag, E.flag.p, sizeof(int), cudaMemcpyDeviceToHost, E.st));
-  ENG_CUDA(cudaStreamSynchronize(E.st));
+  if (dist) {   // a pivot failure on any owner fails the factorisation on every rank
+    flag_to_double_kernel<<<1, 1, 0, E.st>>>(E.flag.p, E.flagd.p);
+    ENG_LAUNCH();
+    if ((rc = ar(E, E.flagd.p, 1))) return rc;
+    double fd = 0.0;
+    ENG_CUDA(cudaMemcpyAsync(&fd, E.flagd.p, sizeof(double), cudaMemcpyDeviceToHost, E.st));
+    ENG_CUDA(cudaStreamSynchronize(E.st));
+    flag = fd != 0.0 ? 1 : 0;
+  } else {
+    ENG_CUDA(cudaMemcpyAsync(&flag, E.flag.p, sizeof(int), cudaMemcpyDeviceToHost, E.st));
+    ENG_CUDA(cudaStreamSynchronize(E.st));
+  }
   tock(E, 0, 1, 1);
   tock(E, 1, 2, 2);
   E.chol_flops += E.plan.flops;
@@ -1712,7 +1811,7 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
     } else if (E.n_solve_calls == 1) {
       cudaGraph_t g = nullptr;
       ENG_CUDA(cudaStreamBeginCapture(E.st, cudaStreamCaptureModeThreadLocal));
-      rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st, &E.fs);
+      rc = cvb_chol::solve(E.ctx, E.S.p, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st, &E.fs);
       cudaError_t ce = cudaStreamEndCapture(E.st, &g);
       if (rc) return rc;
       if (ce != cudaSuccess) return cvb_fail(E.ctx, CVB_ERR_CUDA, "graph capture of the solve failed: %s", cudaGetErrorString(ce));
@@ -1720,7 +1819,7 @@ int prepare_step(Engine& E, bool* solver_ok, bool* grad_converged) {
       cudaGraphDestroy(g);
       ENG_CUDA(cudaGraphLaunch(E.g_solve, E.st));
     } else {
-      if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.n_c_pad, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st, &E.fs))) return rc;
+      if ((rc = cvb_chol::solve(E.ctx, E.S.p, E.linv.p, E.gs.p, E.tmp.p, E.xsol.p, E.plan, E.st, &E.fs))) return rc;
     }
     E.n_solve_calls++;
     if (E.L_in > 0) {
@@ -1972,6 +2071,81 @@ int cvb_ba_set_allreduce(cvb_ba* h, cvb_allreduce_fn fn, void* user) {
     h->E.allreduce = [fn, user, st](void* p, size_t n) { return fn(user, p, n, (void*)st); };
   else
     h->E.allreduce = nullptr;
+  return CVB_OK;
+}
+
+// Peer access for the multi-GPU path (one process per GPU on one NVLink node): exports this rank's packed S, tile
+// inverses and panel flags through CUDA IPC, gathers every rank's handles with the installed collective (each rank writes
+// its bytes into its slot of a zeroed table, the SUM all-reduce is the all-gather) and maps the peers' buffers.  From then
+// on the reduced camera system is reduce-scattered by peer pull and the factorisation is distributed by tile columns.
+int cvb_ba_enable_p2p(cvb_ba* h) {
+  if (!h) return CVB_ERR_INVALID;
+  BaEnter enter(h);
+  Engine& E = h->E;
+  if (E.world <= 1) return CVB_OK;
+  if (E.p2p) return CVB_OK;
+  if (!E.allreduce) return cvb_fail(E.ctx, CVB_ERR_INVALID, "cvb_ba_enable_p2p: install the all-reduce first (cvb_ba_set_allreduce)");
+  if (E.world > 16) return cvb_fail(E.ctx, CVB_ERR_UNSUPPORTED, "peer path supports up to 16 ranks");
+  if (E.g_factor) return cvb_fail(E.ctx, CVB_ERR_INVALID, "cvb_ba_enable_p2p must precede the first iterations");
+  constexpr int HB = (int)sizeof(cudaIpcMemHandle_t);   // 64
+  const int per_rank = 3 * HB + 1;                     // three handles + an "ok" byte
+  std::vector<double> table((size_t)E.world * per_rank, 0.0);
+  cudaIpcMemHandle_t hs[3];
+  bool ok = cudaIpcGetMemHandle(&hs[0], E.S_raw) == cudaSuccess && cudaIpcGetMemHandle(&hs[1], E.linv_raw) == cudaSuccess &&
+            cudaIpcGetMemHandle(&hs[2], E.pflag_raw) == cudaSuccess;
+  cudaGetLastError();
+  for (int q = 0; q < 3 && ok; q++)
+    for (int b = 0; b < HB; b++) table[(size_t)E.rank * per_rank + q * HB + b] = (double)reinterpret_cast<unsigned char*>(&hs[q])[b];
+  table[(size_t)E.rank * per_rank + 3 * HB] = ok ? 1.0 : 0.0;
+  DevArr<double> d_table;
+  int rc;
+  if ((rc = upload(E, d_table, table))) return rc;
+  if ((rc = ar(E, d_table.p, table.size()))) return rc;
+  ENG_CUDA(cudaMemcpyAsync(table.data(), d_table.p, table.size() * sizeof(double), cudaMemcpyDeviceToHost, E.st));
+  ENG_CUDA(cudaStreamSynchronize(E.st));
+  d_table.free_();
+  for (int g = 0; g < E.world; g++) ok = ok && table[(size_t)g * per_rank + 3 * HB] == 1.0;
+  cvb_chol::DistView dv;
+  dv.rank = E.rank; dv.world = E.world;
+  double opened = ok ? 1.0 : 0.0;
+  for (int g = 0; g < E.world && ok; g++) {
+    if (g == E.rank) { dv.peer_S[g] = E.S_raw; dv.peer_linv[g] = E.linv_raw; dv.peer_flag[g] = E.pflag_raw; continue; }
+    cudaIpcMemHandle_t ph[3];
+    for (int q = 0; q < 3; q++)
+      for (int b = 0; b < HB; b++) reinterpret_cast<unsigned char*>(&ph[q])[b] = (unsigned char)table[(size_t)g * per_rank + q * HB + b];
+    void* ptr[3] = {nullptr, nullptr, nullptr};
+    for (int q = 0; q < 3; q++)
+      if (cudaIpcOpenMemHandle(&ptr[q], ph[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { opened = 0.0; cudaGetLastError(); }
+    dv.peer_S[g] = (double*)ptr[0]; dv.peer_linv[g] = (double*)ptr[1]; dv.peer_flag[g] = (int*)ptr[2];
+  }
+  // everybody must have mapped everybody: min over ranks via the sum of (1 - opened)
+  {
+    DevArr<double> d_ok;
+    std::vector<double> v(1, 1.0 - opened);
+    if ((rc = upload(E, d_ok, v))) return rc;
+    if ((rc = ar(E, d_ok.p, 1))) return rc;
+    ENG_CUDA(cudaMemcpyAsync(v.data(), d_ok.p, sizeof(double), cudaMemcpyDeviceToHost, E.st));
+    ENG_CUDA(cudaStreamSynchronize(E.st));
+    d_ok.free_();
+    if (v[0] != 0.0) {
+      for (int g = 0; g < E.world; g++) {
+        if (g == E.rank) continue;
+        if (dv.peer_S[g]) cudaIpcCloseMemHandle(dv.peer_S[g]);
+        if (dv.peer_linv[g]) cudaIpcCloseMemHandle(dv.peer_linv[g]);
+        if (dv.peer_flag[g]) cudaIpcCloseMemHandle(dv.peer_flag[g]);
+      }
+      return cvb_fail(E.ctx, CVB_ERR_UNSUPPORTED, "CUDA IPC peer mapping is not available between all ranks (all-reduce fallback stays in use)");
+    }
+  }
+  ENG_CUDA(cudaMalloc(&dv.d_epoch, sizeof(int)));
+  ENG_CUDA(cudaMemsetAsync(dv.d_epoch, 0, sizeof(int), E.st));
+  ENG_CUDA(cudaMalloc(&dv.d_peer_flag, sizeof(int*) * 16));
+  ENG_CUDA(cudaMemcpyAsync(dv.d_peer_flag, dv.peer_flag, sizeof(int*) * 16, cudaMemcpyHostToDevice, E.st));
+  ENG_CUDA(cudaMalloc(&E.d_peer_S, sizeof(double*) * 16));
+  ENG_CUDA(cudaMemcpyAsync(E.d_peer_S, dv.peer_S, sizeof(double*) * 16, cudaMemcpyHostToDevice, E.st));
+  ENG_CUDA(cudaStreamSynchronize(E.st));
+  E.dv = dv;
+  E.p2p = true;
   return CVB_OK;
 }
 

@@ -1,10 +1,13 @@
 // cholesky.cu — dense FP64 Cholesky factorisation + triangular solves of the reduced camera system (K8).
 //
 // Replaces the CHOLMOD factorisation inside Ceres' SPARSE_SCHUR (optimization_be.cpp:258,561,1025).  The
-// reduced camera matrix S (n = 6K or 15K) is stored dense, row-major, lower triangle significant, padded to a
-// multiple of the 128 tile.  At EuRoC scale every keyframe is covisible with hundreds of others (all agents fly
-// the same hall), so S is ~10 % block-dense before fill and a dense tiled factorisation is the right shape for
-// the GPU; this is the one BA stage that is a true GEMM and runs on the FP64 tensor cores (DMMA,
+// reduced camera matrix S (n = 6K or 15K, padded to a multiple of the 128 tile) is stored as a PACKED list of the
+// 128x128 tiles of L's structure (lower triangle, symbolic fill included; row-major inside a tile, a tile column's
+// tiles contiguous — TilePlan::h_col_base / h_tile_of): memory is proportional to nnz(L) at tile granularity (0.8 GB at
+// C3 instead of 7.4 GB dense; C5 fits), every tile is one contiguous 128 KB block, and a panel is one contiguous range.
+// At EuRoC scale every keyframe is covisible with hundreds of others (all agents fly the same hall), so the pose part
+// of S is ~10 % block-dense before fill and fills in almost completely: a tiled dense-tile factorisation is the right
+// shape for the GPU; this is the one BA stage that is a true GEMM and runs on the FP64 tensor cores (DMMA,
 // mma.sync.m8n8k4.f64 — tcgen05 has no FP64 kind).
 //
 // Right-looking, panel width 128:
@@ -97,17 +100,19 @@ __device__ __forceinline__ void gemm_abt_64(const double* __restrict__ A, size_t
 }
 
 constexpr int TRSM_THREADS = 256, SYRK_THREADS = 128;
+constexpr size_t TT = (size_t)T * T;   // doubles per tile
 constexpr size_t kTrsmSmem = (size_t)GEMM_STAGES * (64 + 128) * LDS * sizeof(double);   //  92160 B → 2 CTAs / SM
 constexpr size_t kSyrkSmem = (size_t)GEMM_STAGES * (64 + 64) * LDS * sizeof(double);    //  61440 B → 3 CTAs / SM
 
 // A(i,k) <- A(i,k) * Linv_k^T for the structurally non-zero row tiles i of tile column k (rows[]).  Two CTAs per tile,
 // each owns 64 full rows (it has consumed all of them as the A operand before it overwrites them).
-__global__ void __launch_bounds__(TRSM_THREADS, 2) trsm_kernel(double* __restrict__ S, size_t ld, int k,
-                                                                const double* __restrict__ linv_k,
-                                                                const int* __restrict__ rows) {
+// `panel` = first row tile of the column (the column's row tiles are contiguous in the packed array).
+__global__ void __launch_bounds__(TRSM_THREADS, 2) trsm_kernel(double* __restrict__ panel,
+                                                                const double* __restrict__ linv_k) {
   extern __shared__ __align__(16) double smem_d[];
-  const int i = rows[blockIdx.x >> 1], half = blockIdx.x & 1;
-  double* At = S + ((size_t)i * T + half * 64) * ld + (size_t)k * T;
+  constexpr size_t ld = T;
+  const int half = blockIdx.x & 1;
+  double* At = panel + (size_t)(blockIdx.x >> 1) * TT + (size_t)half * 64 * T;
   double acc[4][4][2];
   gemm_abt_64<128>(At, ld, linv_k, T, acc, smem_d);
   __syncthreads();   // every warp is done reading this CTA's rows (they were all staged through shared memory)
@@ -124,15 +129,16 @@ __global__ void __launch_bounds__(TRSM_THREADS, 2) trsm_kernel(double* __restric
 // A(i,j) -= A(i,k) A(j,k)^T for the tile pairs (i >= j) of column k's non-zero rows: pi[]/pj[] enumerate them.
 // Four CTAs per pair, one 64x64 quadrant each (consecutive CTAs share the pair's operands in L2); the quadrant above
 // the diagonal of a diagonal tile is skipped.
-__global__ void __launch_bounds__(SYRK_THREADS, 3) syrk_kernel(double* __restrict__ S, size_t ld, int k,
-                                                                const int* __restrict__ pi, const int* __restrict__ pj) {
+__global__ void __launch_bounds__(SYRK_THREADS, 3) syrk_kernel(double* __restrict__ S, const int* __restrict__ tile_of, int nt,
+                                                                int k, const int* __restrict__ pi, const int* __restrict__ pj) {
   extern __shared__ __align__(16) double smem_d[];
+  constexpr size_t ld = T;
   const int p = blockIdx.x >> 2, qr = (blockIdx.x >> 1) & 1, qc = blockIdx.x & 1;
   const int i = pi[p], j = pj[p];
   if (i == j && qc > qr) return;
-  const double* Ai = S + ((size_t)i * T + qr * 64) * ld + (size_t)k * T;
-  const double* Aj = S + ((size_t)j * T + qc * 64) * ld + (size_t)k * T;
-  double* C = S + ((size_t)i * T + qr * 64) * ld + (size_t)j * T + qc * 64;
+  const double* Ai = S + (size_t)tile_of[(size_t)i * nt + k] * TT + (size_t)qr * 64 * T;
+  const double* Aj = S + (size_t)tile_of[(size_t)j * nt + k] * TT + (size_t)qc * 64 * T;
+  double* C = S + (size_t)tile_of[(size_t)i * nt + j] * TT + (size_t)qr * 64 * T + qc * 64;
   double acc[4][4][2];
   gemm_abt_64<64>(Ai, ld, Aj, ld, acc, smem_d);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 1, wn = warp & 1;
@@ -457,9 +463,11 @@ __device__ __forceinline__ void matvec_cols(const double* __restrict__ A, size_t
 }
 
 // forward step k: y_k = Linv_k b_k (written by CTA 0), b_i -= L(i,k) y_k for the non-zero row tiles i > k (rows[])
-__global__ void __launch_bounds__(SOLVE_THREADS) fwd_kernel(const double* __restrict__ L, size_t ld, int k,
+// `panel` = first row tile of column k (row tiles contiguous)
+__global__ void __launch_bounds__(SOLVE_THREADS) fwd_kernel(const double* __restrict__ panel, int k,
                                                             const double* __restrict__ linv, double* __restrict__ b,
                                                             double* __restrict__ y, const int* __restrict__ rows) {
+  constexpr size_t ld = T;
   __shared__ double bk[T], yk[T], upd[T];
   const int tid = threadIdx.x;
   if (tid < T) bk[tid] = b[(size_t)k * T + tid];
@@ -471,15 +479,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS) fwd_kernel(const double* __rest
     return;
   }
   const int i = rows[blockIdx.x - 1];
-  matvec_rows(L + (size_t)i * T * ld + (size_t)k * T, ld, yk, upd);
+  matvec_rows(panel + (size_t)(blockIdx.x - 1) * TT, ld, yk, upd);
   __syncthreads();
   if (tid < T) b[(size_t)i * T + tid] -= upd[tid];
 }
 
 // backward step k: x_k = Linv_k^T y_k (CTA 0), y_i -= L(k,i)^T x_k for the non-zero column tiles i < k of row k (cols[])
-__global__ void __launch_bounds__(SOLVE_THREADS) bwd_kernel(const double* __restrict__ L, size_t ld, int k,
-                                                            const double* __restrict__ linv, double* __restrict__ y,
+__global__ void __launch_bounds__(SOLVE_THREADS) bwd_kernel(const double* __restrict__ L, const int* __restrict__ tile_of, int nt,
+                                                            int k, const double* __restrict__ linv, double* __restrict__ y,
                                                             double* __restrict__ x, const int* __restrict__ cols) {
+  constexpr size_t ld = T;
   __shared__ double ykk[T], xk[T], upd[T], part[4 * T];
   const int tid = threadIdx.x;
   if (tid < T) ykk[tid] = y[(size_t)k * T + tid];
@@ -490,21 +499,28 @@ __global__ void __launch_bounds__(SOLVE_THREADS) bwd_kernel(const double* __rest
     return;
   }
   const int i = cols[blockIdx.x - 1];
-  matvec_cols(L + (size_t)k * T * ld + (size_t)i * T, ld, xk, upd, part);
+  matvec_cols(L + (size_t)tile_of[(size_t)k * nt + i] * TT, ld, xk, upd, part);
   if (tid < T) y[(size_t)i * T + tid] -= upd[tid];
 }
 
 // Symbolic phase (host): tile-level structure of L from the tile-level structure of S (lower, nt x nt, row-major
 // bools, diagonal forced).  Right-looking elimination: the non-zero rows of column k become a clique.
-void TilePlan::build(int nt_, std::vector<uint8_t> mask) {
+void TilePlan::build(int nt_, std::vector<uint8_t> mask, const std::vector<int>* owner, int rank) {
   nt = nt_;
+  my_rank = rank;
+  h_owner.clear();
+  if (owner) h_owner = *owner;
+  const bool dist = !h_owner.empty();
   h_col_ptr.assign(1, 0); h_row_idx.clear(); h_pair_ptr.assign(1, 0); h_pair_i.clear(); h_pair_j.clear(); h_pair_split.clear();
   for (int k = 0; k < nt; k++) mask[(size_t)k * nt + k] = 1;
+  double n_trsm = 0.0;
   for (int k = 0; k < nt; k++) {
     std::vector<int> rows;
     for (int i = k + 1; i < nt; i++)
       if (mask[(size_t)i * nt + k]) rows.push_back(i);
-    // pairs whose column tile is k+1 first ("panel" part: all the next step's potrf/trsm depend on), then the rest
+    if (!dist || h_owner[k] == rank) n_trsm += (double)rows.size();
+    // pairs whose column tile is k+1 first ("panel" part: all the next step's potrf/trsm depend on), then the rest.
+    // Distributed: the structure (fill) is the global one, but a rank lists only the pairs of the columns it owns.
     int n_a = 0;
     for (int pass = 0; pass < 2; pass++)
       for (size_t a = 0; a < rows.size(); a++)
@@ -512,6 +528,7 @@ void TilePlan::build(int nt_, std::vector<uint8_t> mask) {
           const bool is_a = rows[b] == k + 1;
           if ((pass == 0) != is_a) continue;
           mask[(size_t)rows[a] * nt + rows[b]] = 1;
+          if (dist && h_owner[rows[b]] != rank) continue;
           h_pair_i.push_back(rows[a]);
           h_pair_j.push_back(rows[b]);
           if (is_a) n_a++;
@@ -528,8 +545,17 @@ void TilePlan::build(int nt_, std::vector<uint8_t> mask) {
     h_rowc_ptr.push_back((int)h_rowc_idx.size());
   }
   n_tiles_L = (long)h_row_idx.size() + nt;
-  // flops actually executed: one 128^3 GEMM (2 flop per MAC) per trsm tile and per syrk pair
-  flops = 2.0 * T * T * T * ((double)h_row_idx.size() + (double)h_pair_i.size());
+  // packed layout: column by column, diagonal tile first
+  h_col_base.assign(nt, 0);
+  h_tile_of.assign((size_t)nt * nt, -1);
+  int next = 0;
+  for (int k = 0; k < nt; k++) {
+    h_col_base[k] = next;
+    h_tile_of[(size_t)k * nt + k] = next++;
+    for (int q = h_col_ptr[k]; q < h_col_ptr[k + 1]; q++) h_tile_of[(size_t)h_row_idx[q] * nt + k] = next++;
+  }
+  // flops this rank executes: one 128^3 GEMM (2 flop per MAC) per trsm tile and per syrk pair
+  flops = 2.0 * T * T * T * (n_trsm + (double)h_pair_i.size());
 }
 
 int TilePlan::upload(cvb_ctx* ctx, cudaStream_t st) {
@@ -542,7 +568,7 @@ int TilePlan::upload(cvb_ctx* ctx, cudaStream_t st) {
   };
   int rc;
   if ((rc = up(&d_row_idx, h_row_idx)) || (rc = up(&d_pair_i, h_pair_i)) || (rc = up(&d_pair_j, h_pair_j)) ||
-      (rc = up(&d_rowc_idx, h_rowc_idx)))
+      (rc = up(&d_rowc_idx, h_rowc_idx)) || (rc = up(&d_tile_of, h_tile_of)))
     return rc;
   CVB_CUDA(ctx, cudaStreamSynchronize(st));
   return CVB_OK;
@@ -553,11 +579,37 @@ void TilePlan::release() {
   if (d_pair_i) cudaFree(d_pair_i);
   if (d_pair_j) cudaFree(d_pair_j);
   if (d_rowc_idx) cudaFree(d_rowc_idx);
-  d_row_idx = d_pair_i = d_pair_j = d_rowc_idx = nullptr;
+  if (d_tile_of) cudaFree(d_tile_of);
+  d_row_idx = d_pair_i = d_pair_j = d_rowc_idx = d_tile_of = nullptr;
 }
 
-int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
-           const FactorStreams* fs) {
+// ---- cross-GPU hand-over of a finished panel (distributed factorisation) -------------------------------------------
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__global__ void bump_epoch_kernel(int* epoch) { *epoch += 1; }
+// owner: all writes of the preceding kernels on this stream (the panel, the tile inverse) are ordered before the
+// system-scope release store of the flag into every peer's memory (NVLink store)
+__global__ void signal_panel_kernel(int* const* __restrict__ peer_flag, int k, const int* __restrict__ epoch, int world, int rank) {
+  const int g = threadIdx.x;
+  if (g < world && g != rank) {
+    __threadfence_system();
+    st_release_sys(peer_flag[g] + k, *epoch);
+  }
+}
+// peer: spin on the LOCAL flag (one thread, one CTA: nothing else of this GPU is held up)
+__global__ void wait_panel_kernel(const int* __restrict__ flag, const int* __restrict__ epoch) {
+  const int e = *epoch;
+  while (ld_acquire_sys(flag) < e) __nanosleep(200);
+}
+
+int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
+           const FactorStreams* fs, const DistView* dv) {
   static bool attr = false;
   if (!attr) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
@@ -565,17 +617,23 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
     CVB_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
     attr = true;
   }
-  const int nt = n_pad / T;
-  CVB_REQUIRE(ctx, plan.nt == nt, "tile plan does not match the matrix");
+  const int nt = plan.nt;
+  const bool dist = dv != nullptr && dv->world > 1 && !plan.h_owner.empty();
+  CVB_REQUIRE(ctx, plan.d_tile_of != nullptr && (int)plan.h_col_base.size() == nt, "tile plan not built / uploaded");
   CVB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  if (dist) {
+    bump_epoch_kernel<<<1, 1, 0, st>>>(dv->d_epoch);
+    CVB_CHECK_LAUNCH(ctx);
+  }
   cudaStream_t st2 = fs ? fs->bulk : nullptr;
   cudaEvent_t* ev = fs ? fs->ev : nullptr;
   const int n_gs = (fs && !plan.h_col_group.empty()) ? fs->n_group : 0;
   // Lookahead (depth 1) when a second stream is given: the diagonal-tile kernel and the panel solve of step k+1 only
   // need the "panel" part of step k's trailing update (pairs in tile column k+1); the bulk of the update runs on the
-  // second (low-priority) stream concurrently.  ev[2k] = panel solve of step k done, ev[2k+1] = bulk update done.
+  // second (low-priority) stream concurrently.  ev[2k] = panel of step k available, ev[2k+1] = bulk update done.
   // Independent column groups (the IMU chains of different agents, see TilePlan::h_col_group) run on their own
   // streams: their tile columns are pure latency chains (diagonal tile → panel → tiny update) that do not share tiles.
+  // Distributed: "panel available" = factored here (owner) or pulled from the owner's memory (everyone else).
   const bool la = st2 != nullptr && ev != nullptr;
   // Development trace (COVINS_B200_FACTOR_TRACE=<csv path>): per-column timeline of the first non-captured call.
   static bool traced = false;
@@ -616,14 +674,33 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
       forked = false;
     }
     if (tr) cudaEventRecord(tev[(size_t)k * 5 + 0], s);
-    potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, s>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T, d_flag, nullptr, 0);
-    CVB_CHECK_LAUNCH(ctx);
-    if (tr) cudaEventRecord(tev[(size_t)k * 5 + 1], s);
     const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
-    if (m > 0) {
-      trsm_kernel<<<2 * m, TRSM_THREADS, kTrsmSmem, s>>>(S, (size_t)n_pad, k, linv + (size_t)k * T * T,
-                                                     plan.d_row_idx + plan.h_col_ptr[k]);
+    double* diag = S + (size_t)plan.h_col_base[k] * TT;
+    double* linv_k = linv + (size_t)k * TT;
+    const bool mine = !dist || plan.h_owner[k] == dv->rank;
+    if (mine) {
+      potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, s>>>(diag, (size_t)T, 0, linv_k, d_flag, nullptr, 0);
       CVB_CHECK_LAUNCH(ctx);
+      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 1], s);
+      if (m > 0) {
+        trsm_kernel<<<2 * m, TRSM_THREADS, kTrsmSmem, s>>>(diag + TT, linv_k);
+        CVB_CHECK_LAUNCH(ctx);
+      }
+      if (dist) {
+        signal_panel_kernel<<<1, 32, 0, s>>>(dv->d_peer_flag, k, dv->d_epoch, dv->world, dv->rank);
+        CVB_CHECK_LAUNCH(ctx);
+      }
+    } else {
+      const int o = plan.h_owner[k];
+      wait_panel_kernel<<<1, 1, 0, s>>>(dv->peer_flag[dv->rank] + k, dv->d_epoch);
+      CVB_CHECK_LAUNCH(ctx);
+      // the column's tiles are contiguous and sit at the same packed offset on every rank: one NVLink copy each
+      CVB_CUDA(ctx, cudaMemcpyAsync(diag, dv->peer_S[o] + (size_t)plan.h_col_base[k] * TT, (size_t)(1 + m) * TT * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, s));
+      CVB_CUDA(ctx, cudaMemcpyAsync(linv_k, dv->peer_linv[o] + (size_t)k * TT, TT * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 1], s);
+    }
+    if (m > 0) {
       if (tr) cudaEventRecord(tev[(size_t)k * 5 + 2], s);
       const bool la_k = la && grp < 0;
       const int p0 = plan.h_pair_ptr[k], np = plan.h_pair_ptr[k + 1] - p0, na = la_k ? plan.h_pair_split[k] : np;
@@ -632,13 +709,13 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
         if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(s, ev[2 * last_bulk + 1], 0));
       }
       if (na > 0) {
-        syrk_kernel<<<4 * na, SYRK_THREADS, kSyrkSmem, s>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
+        syrk_kernel<<<4 * na, SYRK_THREADS, kSyrkSmem, s>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
         CVB_CHECK_LAUNCH(ctx);
       }
       if (tr) cudaEventRecord(tev[(size_t)k * 5 + 3], s);
       if (la_k && np - na > 0) {
         CVB_CUDA(ctx, cudaStreamWaitEvent(st2, ev[2 * k], 0));
-        syrk_kernel<<<4 * (np - na), SYRK_THREADS, kSyrkSmem, st2>>>(S, (size_t)n_pad, k, plan.d_pair_i + p0 + na,
+        syrk_kernel<<<4 * (np - na), SYRK_THREADS, kSyrkSmem, st2>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0 + na,
                                                                      plan.d_pair_j + p0 + na);
         CVB_CHECK_LAUNCH(ctx);
         CVB_CUDA(ctx, cudaEventRecord(ev[2 * k + 1], st2));
@@ -658,7 +735,7 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
     cudaStreamSynchronize(st);
     FILE* f = fopen(trace_path, "w");
     if (f) {
-      fprintf(f, "k,group,n_rows,n_pairs,n_panel_pairs,t_start_us,t_potrf_us,t_trsm_us,t_syrk_a_us,t_bulk_us\n");
+      fprintf(f, "k,group,owner,n_rows,n_pairs,n_panel_pairs,t_start_us,t_panel_ready_us,t_trsm_us,t_syrk_a_us,t_bulk_us\n");
       for (int k = 0; k < nt; k++) {
         float t[5];
         for (int e = 0; e < 5; e++) {
@@ -668,9 +745,9 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
             if (cudaEventElapsedTime(&ms, tev[(size_t)nt * 5], tev[(size_t)k * 5 + e]) == cudaSuccess) t[e] = ms * 1e3f;
           }
         }
-        fprintf(f, "%d,%d,%d,%d,%d,%.1f,%.1f,%.1f,%.1f,%.1f\n", k, plan.h_col_group.empty() ? -1 : plan.h_col_group[k],
-                plan.h_col_ptr[k + 1] - plan.h_col_ptr[k], plan.h_pair_ptr[k + 1] - plan.h_pair_ptr[k],
-                plan.h_pair_split[k], t[0], t[1], t[2], t[3], t[4]);
+        fprintf(f, "%d,%d,%d,%d,%d,%d,%.1f,%.1f,%.1f,%.1f,%.1f\n", k, plan.h_col_group.empty() ? -1 : plan.h_col_group[k],
+                plan.h_owner.empty() ? 0 : plan.h_owner[k], plan.h_col_ptr[k + 1] - plan.h_col_ptr[k],
+                plan.h_pair_ptr[k + 1] - plan.h_pair_ptr[k], plan.h_pair_split[k], t[0], t[1], t[2], t[3], t[4]);
       }
       fclose(f);
     }
@@ -681,9 +758,9 @@ int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const 
 }
 
 // solves L L^T x = b; b is destroyed, tmp is scratch (n_pad), result in x
-int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
+int solve(cvb_ctx* ctx, const double* L, const double* linv, double* b, double* tmp, double* x,
           const TilePlan& plan, cudaStream_t st, const FactorStreams* fs) {
-  const int nt = n_pad / T;
+  const int nt = plan.nt;
   // The leading tile columns that belong to independent column groups (IMU chains, TilePlan::h_col_group) touch only
   // their own chain's rows of b / y, so the chains' substitution steps — pure launch-latency chains — run concurrently
   // on the group streams, forward before and backward after the sequential part.
@@ -722,7 +799,8 @@ int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* 
     if (k < n_grouped && (rc = stream_of(k, &s))) return rc;
     if (k == n_grouped && n_grouped > 0 && (rc = join())) return rc;
     const int m = plan.h_col_ptr[k + 1] - plan.h_col_ptr[k];
-    fwd_kernel<<<1 + m, SOLVE_THREADS, 0, s>>>(L, (size_t)n_pad, k, linv, b, tmp, plan.d_row_idx + plan.h_col_ptr[k]);
+    fwd_kernel<<<1 + m, SOLVE_THREADS, 0, s>>>(L + (size_t)(plan.h_col_base[k] + 1) * TT, k, linv, b, tmp,
+                                               plan.d_row_idx + plan.h_col_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
   if (n_grouped == nt && n_grouped > 0 && (rc = join())) return rc;
@@ -731,7 +809,7 @@ int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* 
     if (k == n_grouped - 1 && (rc = fork())) return rc;
     if (k < n_grouped && (rc = stream_of(k, &s))) return rc;
     const int m = plan.h_rowc_ptr[k + 1] - plan.h_rowc_ptr[k];
-    bwd_kernel<<<1 + m, SOLVE_THREADS, 0, s>>>(L, (size_t)n_pad, k, linv, tmp, x, plan.d_rowc_idx + plan.h_rowc_ptr[k]);
+    bwd_kernel<<<1 + m, SOLVE_THREADS, 0, s>>>(L, plan.d_tile_of, nt, k, linv, tmp, x, plan.d_rowc_idx + plan.h_rowc_ptr[k]);
     CVB_CHECK_LAUNCH(ctx);
   }
   if (n_grouped > 0 && (rc = join())) return rc;
@@ -818,36 +896,37 @@ extern "C" int cvb_dense_cholesky_solve(cvb_ctx* ctx, const double* A, int n, co
   using namespace cvb_chol;
   const int np = ((n + T - 1) / T) * T;
   cudaStream_t st = ctx->stream;
-  double* dS = (double*)cvb_ws(ctx, WS_T, (size_t)np * np * sizeof(double));
+  const int nt = np / T;
+  // tile structure of the input (zero tiles are skipped) → symbolic fill → packed tiles
+  std::vector<uint8_t> mask((size_t)nt * nt, 0);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++)
+      if (A[(size_t)i * n + j] != 0.0) mask[(size_t)(i / T) * nt + (j / T)] = 1;
+  TilePlan plan;
+  plan.build(nt, mask);
+  std::vector<double> hs((size_t)plan.n_tiles_L * TT, 0.0), hb(np, 0.0);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++)
+      if (A[(size_t)i * n + j] != 0.0) hs[plan.tile_index(i / T, j / T) * TT + (size_t)(i % T) * T + (j % T)] = A[(size_t)i * n + j];
+  for (int i = n; i < np; i++) hs[plan.tile_index(i / T, i / T) * TT + (size_t)(i % T) * T + (i % T)] = 1.0;
+  for (int i = 0; i < n; i++) hb[i] = b[i];
+  double* dS = (double*)cvb_ws(ctx, WS_T, hs.size() * sizeof(double));
   double* dl = (double*)cvb_ws(ctx, WS_Q, (size_t)np * T * sizeof(double));
   double* dv = (double*)cvb_ws(ctx, WS_OUT0, (size_t)np * 3 * sizeof(double));
   int* dflag = (int*)cvb_ws(ctx, WS_FLAG, 16);
   if (!dS || !dl || !dv || !dflag) return CVB_ERR_CUDA;
-  std::vector<double> hs((size_t)np * np, 0.0), hb(np, 0.0);
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j <= i; j++) hs[(size_t)i * np + j] = A[(size_t)i * n + j];
-  for (int i = n; i < np; i++) hs[(size_t)i * np + i] = 1.0;
-  for (int i = 0; i < n; i++) hb[i] = b[i];
   CVB_CUDA(ctx, cudaMemcpyAsync(dS, hs.data(), hs.size() * sizeof(double), cudaMemcpyHostToDevice, st));
   CVB_CUDA(ctx, cudaMemcpyAsync(dv, hb.data(), np * sizeof(double), cudaMemcpyHostToDevice, st));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  // tile structure of the input (zero tiles are skipped) → symbolic fill
-  const int nt = np / T;
-  std::vector<uint8_t> mask((size_t)nt * nt, 0);
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j <= i; j++)
-      if (hs[(size_t)i * np + j] != 0.0) mask[(size_t)(i / T) * nt + (j / T)] = 1;
-  TilePlan plan;
-  plan.build(nt, mask);
   int rc = plan.upload(ctx, st);
   if (rc) return rc;
   cudaEventRecord(e0, st);
-  rc = factor(ctx, dS, np, dl, dflag, plan, st, nullptr);
+  rc = factor(ctx, dS, dl, dflag, plan, st, nullptr);
   cudaEventRecord(e1, st);
   if (rc) return rc;
-  rc = solve(ctx, dS, np, dl, dv, dv + np, dv + 2 * np, plan, st);
+  rc = solve(ctx, dS, dl, dv, dv + np, dv + 2 * np, plan, st);
   if (rc) return rc;
   int flag = 0;
   CVB_CUDA(ctx, cudaMemcpyAsync(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost, st));

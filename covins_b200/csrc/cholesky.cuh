@@ -17,10 +17,20 @@ struct TilePlan {
   std::vector<int> h_rowc_ptr, h_rowc_idx;         // per tile row k: non-zero column tiles i < k (backward solve)
   std::vector<int> h_col_group;                    // optional, per tile column: id (>= 0) of an independent column group
                                                    // (its columns share no tile with other groups), -1 = main sequence
-  int *d_row_idx = nullptr, *d_pair_i = nullptr, *d_pair_j = nullptr, *d_rowc_idx = nullptr;
+  // Packed tile storage: only the tiles of L's structure exist.  Column k's tiles are contiguous — the diagonal tile at
+  // h_col_base[k], then its row tiles in h_row_idx order — so a panel is one contiguous block (one peer copy when the
+  // factorisation is distributed).  h_tile_of[i * nt + j] = packed index of tile (i >= j) or -1.
+  std::vector<int> h_col_base, h_tile_of;
+  // Distributed factorisation: h_owner[k] = rank that factors tile column k and applies every update to it (empty =
+  // single GPU).  With an owner map the pair lists hold only the pairs whose TARGET column this rank owns.
+  std::vector<int> h_owner;
+  int my_rank = 0;
+  int *d_row_idx = nullptr, *d_pair_i = nullptr, *d_pair_j = nullptr, *d_rowc_idx = nullptr, *d_tile_of = nullptr;
   long n_tiles_L = 0;
   double flops = 0.0;   // flops of one numeric factorisation with this plan
-  void build(int nt, std::vector<uint8_t> lower_mask);
+  // owner (optional, nt entries) + rank: distributed plan.  flops = the tile GEMMs this rank executes.
+  void build(int nt, std::vector<uint8_t> lower_mask, const std::vector<int>* owner = nullptr, int rank = 0);
+  size_t tile_index(int i, int j) const { return (size_t)h_tile_of[(size_t)i * nt + j]; }
   int upload(cvb_ctx* ctx, cudaStream_t st);
   void release();
 };
@@ -33,9 +43,22 @@ struct FactorStreams {
   int n_group = 0;
   cudaEvent_t fork = nullptr, join[8] = {};
 };
-int factor(cvb_ctx* ctx, double* S, int n_pad, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
-           const FactorStreams* fs);
-int solve(cvb_ctx* ctx, const double* L, int n_pad, const double* linv, double* b, double* tmp, double* x,
+// Peer view of a distributed factorisation (one process per GPU, buffers mapped with CUDA IPC over NVLink):
+// every rank owns the tile columns h_owner says; after trsm of column k the owner raises flag[k] = epoch in every
+// peer's flag array, the peers wait on their LOCAL flag and pull the panel (and the tile inverse) out of the owner's
+// memory straight into the same place of their own packed array — so every rank ends up with the complete factor.
+struct DistView {
+  int rank = 0, world = 1;
+  double* peer_S[16] = {};       // packed tile arrays of all ranks (own entry = local pointer)
+  double* peer_linv[16] = {};
+  int* peer_flag[16] = {};       // [nt] per rank
+  int* d_epoch = nullptr;        // local factorisation counter (device)
+  int** d_peer_flag = nullptr;   // device copy of peer_flag[]
+};
+// S: packed tiles (plan.h_col_base / h_tile_of), linv: nt tile inverses
+int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
+           const FactorStreams* fs, const DistView* dv = nullptr);
+int solve(cvb_ctx* ctx, const double* L, const double* linv, double* b, double* tmp, double* x,
           const TilePlan& plan, cudaStream_t st, const FactorStreams* fs = nullptr);
 
 }  // namespace cvb_chol

@@ -123,7 +123,10 @@ class BaSolver:
     """create → iterate(n) → result(); one ceres::Problem/Solve equivalent living on the GPU."""
 
     def __init__(self, ctx: Context, p: dict, visual_only=False, cauchy_reproj=1.0, cauchy_edge=1.0, edges=None,
-                 obs_skip=None, rank=0, world=1, allreduce=None):
+                 obs_skip=None, rank=0, world=1, allreduce=None, p2p=None):
+        import os
+        if p2p is None:
+            p2p = os.environ.get("COVINS_B200_P2P", "1") != "0"
         self.ctx = ctx
         self.flat = _Flat(p, edges=edges, obs_skip=obs_skip, use_imu=not visual_only)
         o = BaOptions(0, int(visual_only), float(cauchy_reproj), float(cauchy_edge), rank, world)
@@ -132,9 +135,17 @@ class BaSolver:
         # the all-reduce must be installed before iteration 0 runs inside create() when world > 1: create() only
         # evaluates rank-local quantities that are summed lazily, so we create first and restart after installing it.
         ctx.check(lib().cvb_ba_create(ctx.handle, C.byref(self.flat.s), C.byref(o), C.byref(self.h)))
+        self.p2p = False
         if allreduce is not None:
             self._cb = ALLREDUCE_FN(allreduce)
             ctx.check(lib().cvb_ba_set_allreduce(self.h, self._cb, None))
+            if world > 1 and p2p:
+                # peer path (CUDA IPC over NVLink): reduce-scatter by pull + column-distributed factorisation; falls back to
+                # the all-reduce + replicated factorisation when peer mapping is unavailable (CVB_ERR_UNSUPPORTED = 3)
+                rc = lib().cvb_ba_enable_p2p(self.h)
+                if rc not in (0, 3):
+                    ctx.check(rc)
+                self.p2p = rc == 0
             ctx.check(lib().cvb_ba_restart(self.h))
 
     def restart(self):

@@ -80,3 +80,62 @@ def sift_keyframes(seed: int, n_kf: int, n_feat: int = 300, lm_frac: float = 0.4
 
 def seg_ptr_uniform(n_seg: int, n_per: int) -> np.ndarray:
     return (np.arange(n_seg + 1, dtype=np.int64) * n_per).astype(np.int32)
+
+
+def _rot(rvec):
+    th = np.linalg.norm(rvec)
+    if th < 1e-12:
+        return np.eye(3)
+    k = rvec / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def se3_search_scene(seed: int, n_kp: int = 1000, n_shared: int = 300, pix_noise: float = 1.0, pose_noise: float = 0.01,
+                     img_w: int = 752, img_h: int = 480, n_octaves_data: int = 1):
+    """Two keyframes looking at a common set of landmarks, as FeatureMatcher::SearchBySE3 sees them after the first RANSAC
+    (feature_matcher_be.cpp:293-498): per keyframe keypoints (float), octaves, ORB descriptors, and for the keypoints that
+    carry a landmark its world position / max distance / representative descriptor.  KF1 and KF2 each own DIFFERENT landmark
+    objects for the same physical points (that is what the search is meant to associate).  Returns plain dict inputs for
+    covins_b200.placerec.KfView plus the relative pose T12 (slightly perturbed) and the already-matched masks."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1.0]])
+    # camera 1 at the origin, camera 2 displaced; points in front of both
+    Rwc = [np.eye(3), _rot(rng.normal(0, 0.08, 3))]
+    twc = [np.zeros(3), rng.normal(0, 0.25, 3)]
+    n_pts = 3 * n_shared
+    uv = np.stack([rng.uniform(20, img_w - 20, n_pts), rng.uniform(20, img_h - 20, n_pts)], -1)
+    depth = rng.uniform(2.0, 12.0, n_pts)
+    rays = np.linalg.solve(K, np.concatenate([uv, np.ones((n_pts, 1))], -1).T).T
+    pw = rays * depth[:, None]                       # in camera-1 = world coordinates
+    codes = rng.integers(0, 256, (n_pts, ORB_BYTES), dtype=np.uint8)
+    views = []
+    for c in range(2):
+        Rcw = Rwc[c].T; tcw = -Rcw @ twc[c]
+        pc = pw @ Rcw.T + tcw
+        pr = pc @ K.T
+        u = pr[:, :2] / pr[:, 2:3]
+        vis = np.flatnonzero((pc[:, 2] > 0.5) & (u[:, 0] > 10) & (u[:, 0] < img_w - 10) & (u[:, 1] > 10) & (u[:, 1] < img_h - 10))
+        sel = vis[rng.permutation(len(vis))[:min(len(vis), n_shared + n_shared // 2)]]
+        n_lm = len(sel)
+        kp = np.zeros((n_kp, 2), np.float32); octave = rng.integers(0, n_octaves_data, n_kp).astype(np.float32)
+        desc = rng.integers(0, 256, (n_kp, ORB_BYTES), dtype=np.uint8)
+        kp[:] = np.stack([rng.uniform(0, img_w, n_kp), rng.uniform(0, img_h, n_kp)], -1)
+        slots = rng.choice(n_kp, n_lm, replace=False)
+        kp[slots] = (u[sel] + rng.normal(0, pix_noise, (n_lm, 2))).astype(np.float32)
+        desc[slots] = codes[sel] ^ _flip_mask(rng, (n_lm, ORB_BYTES))
+        lm_valid = np.zeros(n_kp, np.uint8); lm_valid[slots] = 1
+        lm_valid[slots[rng.random(n_lm) < 0.05]] = 0                        # a few invalid landmarks
+        lm_pos = np.zeros((n_kp, 3)); lm_pos[slots] = pw[sel] + rng.normal(0, 0.01, (n_lm, 3))
+        lm_maxdist = np.ones(n_kp); lm_maxdist[slots] = np.linalg.norm(pc[sel], axis=1) * rng.uniform(0.9, 2.5, n_lm)
+        lm_desc = rng.integers(0, 256, (n_kp, ORB_BYTES), dtype=np.uint8); lm_desc[slots] = codes[sel] ^ _flip_mask(rng, (n_lm, ORB_BYTES))
+        Tcw = np.eye(4); Tcw[:3, :3] = Rcw; Tcw[:3, 3] = tcw
+        views.append(dict(kp=kp, octave=octave, desc=desc, lm_valid=lm_valid, lm_pos=lm_pos, lm_maxdist=lm_maxdist, lm_desc=lm_desc,
+                          K=K.copy(), Tcw=Tcw, img_bounds=np.array([0.0, img_w, 0.0, img_h]), point_of_slot=dict(zip(slots.tolist(), sel.tolist()))))
+    # T12 = T_c1_c2 (maps camera-2 coordinates to camera-1 coordinates), perturbed like a RANSAC estimate
+    T12 = views[0]["Tcw"] @ np.linalg.inv(views[1]["Tcw"])
+    dT = np.eye(4); dT[:3, :3] = _rot(rng.normal(0, pose_noise * 0.2, 3)); dT[:3, 3] = rng.normal(0, pose_noise, 3)
+    T12 = T12 @ dT
+    T21 = np.linalg.inv(T12)
+    already1 = (rng.random(n_kp) < 0.1).astype(np.uint8); already2 = (rng.random(n_kp) < 0.1).astype(np.uint8)
+    return views, T12, T21, already1, already2

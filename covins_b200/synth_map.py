@@ -289,6 +289,37 @@ CONFIGS = {
 }
 
 
+_CACHE_VERSION = "r02a"   # bump when make_map changes
+
+
 def make_config(name: str, seed: int | None = None, **kw):
+    """Named BASELINE config.  The map is a pure function of (name, seed, kw): the big ones (C2 14 s, C3 60 s of numpy)
+    are cached as .npz under $COVINS_B200_CACHE (default /tmp/covins_b200_cache) so that the tests, bench.py and its CPU arm
+    — separate processes on the same box — generate them once."""
+    import os
     cfg = dict(CONFIGS[name]); cfg.update(kw)
-    return make_map(seed if seed is not None else list(CONFIGS).index(name), **cfg)
+    seed = seed if seed is not None else list(CONFIGS).index(name)
+    K = cfg["n_agents"] * cfg["kf_per_agent"]
+    path = None
+    if K >= 400 and os.environ.get("COVINS_B200_CACHE", "") != "off":
+        d = os.environ.get("COVINS_B200_CACHE", "/tmp/covins_b200_cache")
+        tag = "_".join(f"{k}={v}" for k, v in sorted(cfg.items()))
+        path = os.path.join(d, f"{_CACHE_VERSION}_{name}_{seed}_{tag}.npz")
+        if os.path.exists(path):
+            try:
+                with np.load(path) as z:
+                    p = {k: z[k] for k in z.files}
+                p["K"] = int(p["K"]); p["L"] = int(p["L"])
+                return p
+            except Exception:
+                pass
+    p = make_map(seed, **cfg)
+    if path is not None:
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            tmp = path + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, **p)
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    return p

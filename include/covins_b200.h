@@ -116,7 +116,7 @@ CVB_API int cvb_db_match_hamming(cvb_ctx* ctx, cvb_db* db, const uint8_t* q, int
  * Replaces the SIFT branch, cv::FlannBasedMatcher()::knnMatch(query, train, out, 2)
  *   (placerec_gen_be.cpp:86-87,99; RelNonCentralPosSolver.cpp:310-311,323), with the EXACT brute-force
  *   result cv::BFMatcher(NORM_L2) gives (FLANN is approximate and randomised).
- * q/t are CV_32F rows of `dim` floats (dim % 16 == 0, dim <= 256; SIFT: 128).  Descriptors must be
+ * q/t are CV_32F rows of `dim` floats (dim == 128, SIFT; other lengths → CVB_ERR_UNSUPPORTED).  Descriptors must be
  * integer-valued in [0,255] (what cv::xfeatures2d::SIFT emits) — then every fp32 partial sum of the
  * reference is exact and the result is bit-identical to OpenCV; other inputs → CVB_ERR_UNSUPPORTED.
  * dist = sqrtf(sum (a-b)^2) as float.
@@ -185,6 +185,81 @@ CVB_API int cvb_landmark_match_batch_dev(cvb_ctx* ctx, const uint8_t* d_A, const
                                          const int32_t* h_seg_ptr, int n_seg, float thr, int num_best,
                                          int32_t* d_outA, int32_t* d_outB, float* d_outD, int32_t* d_n_out,
                                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Guided search and geometric-verification scoring
+ * ---------------------------------------------------------------------------------------------- */
+
+/* What FeatureMatcher::SearchBySE3 reads of one keyframe (src/covins_backend/feature_matcher_be.cpp:293-498), flattened
+ * by the host shim; all pointers HOST memory, arrays indexed by keypoint. */
+typedef struct cvb_kf_view {
+  int32_t n;                 /* keypoints_distorted_.size() == GetLandmarks().size() */
+  const float* kp;           /* [n][2] keypoints_distorted_ (float, typedefs_base.hpp:130) */
+  const float* octave;       /* [n]    keypoints_aors_[i][1]; the reference truncates it to int (:379,:456) */
+  const uint8_t* desc;       /* [n][32] descriptors_ rows (GetDescriptorCV, keyframe_base.cpp:258-260) */
+  const uint8_t* lm_valid;   /* [n]    1 = GetLandmarks()[i] != nullptr && !IsInvalid() (:335-341,:411-419) */
+  const double* lm_pos;      /* [n][3] GetWorldPos() */
+  const double* lm_maxdist;  /* [n]    max_distance_ (LandmarkBase::PredictScale, landmark_base.cpp:120-133) */
+  const uint8_t* lm_desc;    /* [n][32] Landmark::GetDescriptor() */
+  const int32_t* grid_ptr;   /* [64*48+1] CSR of keypoint_grid_[ix][iy], cell = ix*48 + iy (FRAME_GRID_COLS x ROWS,
+                                typedefs_base.hpp:59-60), members in insertion (= ascending keypoint) order
+                                (KeyframeBase::AssignFeaturesToGrid, keyframe_base.cpp:122-143) */
+  const int32_t* grid_idx;   /* [grid_ptr[3072]] */
+  double grid_w_inv, grid_h_inv;   /* grid_width_inv_, grid_height_inv_ */
+  double K[9];               /* calibration_.K, row-major */
+  double Tcw[16];            /* GetPoseTcw(), row-major 4x4 */
+  double img[4];             /* img_dim_x_min_, img_dim_x_max_, img_dim_y_min_, img_dim_y_max_ (IsInImage, keyframe_base.cpp:414-416) */
+} cvb_kf_view;
+
+typedef struct cvb_search_params {
+  double th;                 /* search radius factor (matcher.search_radius_SE3 = 9.5) */
+  int32_t desc_th_low;       /* matcher.desc_matching_th_low = 50 */
+  int32_t num_octaves;       /* feat.num_octaves */
+  double scale_factor;       /* feat.scale_factor (PredictScale); the radius itself uses pow(2.0, level) (:366,:443) */
+} cvb_search_params;
+
+/*
+ * Replaces FeatureMatcher::SearchBySE3(pKF1, pKF2, matches12, T12, th) for a batch of candidate keyframes pKF2[p]
+ * (the loop of placerec_be.cpp:113-160 calls it once per surviving candidate).  T12 / T21 [n_pairs][16] row-major: T21 is
+ * T12.inverse() as the caller's Eigen computes it (:300).  already1 [n_pairs][kf1->n] / already2 (concatenated,
+ * kf2[p].n each): the alreadyMatched1/2 masks of :312-324.  Reference behaviour reproduced on purpose:
+ *   - direction 2→1 tests pKF2->IsInImage for a projection into KF1 (:433);
+ *   - the agreement test reads match2[i], not match2[idx2] (:489) (i >= n2 counts as no match — the reference indexes
+ *     out of bounds there);
+ *   - direction 1→2 accepts bestDist <= th_low (float), direction 2→1 bestDist < th_low (int) (:403,:479);
+ *   - keypoints whose grid cell index falls outside the 64x48 grid (x*grid_w_inv rounds to 64) are not in the grid
+ *     (the reference writes out of bounds there).
+ * Outputs: match12 [n_pairs][kf1->n] = index of the KF2 keypoint whose landmark becomes matches12[i], or -1;
+ * n_found [n_pairs] = the return value; match1 [n_pairs][n1] / match2 (concatenated like already2) = the two
+ * directional results (nullable, for tests).
+ */
+CVB_API int cvb_search_by_se3_batch(cvb_ctx* ctx, const cvb_kf_view* kf1, const cvb_kf_view* kf2, int n_pairs,
+                                    const double* T12, const double* T21, const uint8_t* already1, const uint8_t* already2,
+                                    const cvb_search_params* prm, int32_t* match12, int32_t* n_found, int32_t* match1,
+                                    int32_t* match2);
+
+/*
+ * RANSAC hypothesis scoring, batched over hypotheses (the inner loop of opengv's Ransac::computeModel —
+ * countWithinDistance / selectWithinDistance over all correspondences — for every hypothesis in one launch; sampling and the
+ * minimal solvers stay with the caller, SURVEY §8a V1: "given the same sampled minimal sets, identical scores / inlier masks").
+ *
+ * Absolute pose (Se3Solver::projectiveAlignment, Se3Solver.cpp:59-110, GP3P; score of
+ * include/covins/matcher/opengv/sac_problems/FrameAbsolutePoseSacProblem.h:95-126):
+ *   model [n_hyp][12] = 3x4 [R|t] row-major (body in world); per correspondence i: world point pts[i], bearing f[i],
+ *   camera offset/rotation (one camera: cam_off[3], cam_rot[9] row-major), sigma[i] = getSigmaAngle(i);
+ *   score = |normalize(Rc^T (R^T (p - t) - c)) - f|^2 / sigma;  inlier iff score < threshold (opengv Ransac).
+ * Relative pose (RelNonCentralPosSolver::computePose, RelNonCentralPosSolver.cpp:343-377;
+ * frame-relative-pose-sac-problem.hpp:69-104 with opengv::triangulation::triangulate2):
+ *   model [n_hyp][12] = [R12|t12]; bearings f1[i], f2[i], sigma1[i], sigma2[i];
+ *   score = 0.5 |normalize(X) - f1|^2 / sigma1 + 0.5 |normalize(R12^T (X - t12)) - f2|^2 / sigma2, X = triangulate2.
+ * Outputs: scores [n_hyp][n] (nullable), inlier [n_hyp][n] u8 (nullable), n_inliers [n_hyp].
+ */
+CVB_API int cvb_score_absolute_pose_batch(cvb_ctx* ctx, const double* model, int n_hyp, const double* pts, const double* f,
+                                          const double* sigma, int n, const double* cam_off, const double* cam_rot,
+                                          double threshold, double* scores, uint8_t* inlier, int32_t* n_inliers);
+CVB_API int cvb_score_relative_pose_batch(cvb_ctx* ctx, const double* model, int n_hyp, const double* f1, const double* f2,
+                                          const double* sigma1, const double* sigma2, int n, double threshold,
+                                          double* scores, uint8_t* inlier, int32_t* n_inliers);
 
 /* INT-pipe microbenchmark used for the Hamming roofline denominator (SURVEY.md §8d asks the builder to
  * measure the popc issue peak): runs `iters` dependent-free XOR+POPC+ADD rounds on every SM and
@@ -285,7 +360,17 @@ typedef struct cvb_ba cvb_ba;
 /* Replaces the ceres::Problem + ceres::Solve of one optimisation (SPARSE_SCHUR + DOGLEG, optimization_be.cpp:257-265,
  * 560-567, 1024-1031).  create = problem construction + iteration 0; iterate = that many trust-region iterations. */
 CVB_API int cvb_ba_create(cvb_ctx* ctx, const cvb_ba_problem* p, const cvb_ba_options* o, cvb_ba** out);
+/* Multi-GPU (o->world > 1; one process per GPU, the same problem on every rank, landmark blocks sharded by rank): the call
+ * sequence is  cvb_ba_create → cvb_ba_set_allreduce → [cvb_ba_enable_p2p] → cvb_ba_restart → cvb_ba_iterate.
+ * cvb_ba_create runs iteration 0 on the rank-local partial sums only; cvb_ba_restart repeats it with the collective
+ * installed (and returns to the state the problem was created with), so it is REQUIRED before iterating when world > 1.
+ * cvb_ba_enable_p2p (optional, all ranks on one NVLink node): maps every rank's reduced camera system through CUDA IPC;
+ * the reduced normal equations are then reduce-scattered by peer pull onto tile-column owners and the factorisation is
+ * distributed by tile columns (panels handed over through peer memory).  CVB_ERR_UNSUPPORTED → not available, the
+ * all-reduce of the packed tiles + replicated factorisation stay in use. */
 CVB_API int cvb_ba_set_allreduce(cvb_ba* h, cvb_allreduce_fn fn, void* user);
+CVB_API int cvb_ba_enable_p2p(cvb_ba* h);
+/* back to the state the problem was created with (bit-identical repeat of the solve), then iteration 0 */
 CVB_API int cvb_ba_restart(cvb_ba* h);
 CVB_API int cvb_ba_iterate(cvb_ba* h, int max_iterations, int* iterations_done);
 CVB_API int cvb_ba_result_get(cvb_ba* h, const cvb_ba_problem* p, cvb_ba_result* r);

@@ -183,3 +183,57 @@ def test_gba_from_serialized_map_equals_flat_problem(ctx, tmp_path):
     assert _rel(b["pose"][:, 4:], a["pose"][:, 4:]) < 1e-8 and _rel(b["speedbias"], a["speedbias"]) < 1e-8
     inc = a["lm_owner"][keep] >= 0
     assert _rel(b["lm"][inc], a["lm"][keep][inc]) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------- BASELINE-sized parity
+# The compiled CPU port (oracle/ba_port.cpp; pinned against the autograd oracle in tests/test_ba_port.py) makes the
+# BASELINE configs affordable as ORACLE-parity cases: same iteration count, same accept/reject sequence, same outlier
+# set, states within the 1e-5 of north_star.
+def _port_compare(got, ref, p, lm_mask=None, cost_rtol=1e-6):
+    assert got["iterations"] == ref["iterations"], (got["iterations"], ref["iterations"], got["termination"], ref["termination"])
+    assert got["steps"] == ref["steps"]
+    assert np.allclose(got["cost"][:len(ref["cost"])], ref["cost"], rtol=cost_rtol, atol=0), (got["cost"], ref["cost"])
+    assert _rel(got["pose"], ref["pose"]) < RTOL and _rel(got["speedbias"], ref["speedbias"]) < RTOL
+    if p.get("L", 0):
+        m = slice(None) if lm_mask is None else lm_mask
+        assert _rel(got["lm"][m], ref["lm"][m]) < RTOL
+
+
+def test_gba_c1_matches_cpu_oracles(ctx):
+    """BASELINE config 1 (200 KF / 10k LM / ~80k obs): Optimization::GlobalBundleAdjustment, both rounds, 10 iterations —
+    CUDA vs the compiled port, and the round-2 solve also vs the independent autograd oracle."""
+    from oracle import ba_port as bp
+    p = synth_map.make_config("C1")
+    got = O.global_bundle_adjustment(ctx, p, iterations_limit=10)
+    ref = bp.global_bundle_adjustment(p, iterations_limit=10)
+    assert np.array_equal(got["obs_removed"], ref["obs_removed"]) and got["obs_removed"].sum() > 1000
+    well = (got["lm_owner"] >= 0) & (np.abs(ref["lm"]).max(1) < 100.0)
+    _port_compare(got, ref, p, lm_mask=well)
+    # autograd oracle on the same round-2 problem (≈ 1 iteration/s): 3 iterations
+    a = O.solve(ctx, p, 3, visual_only=False, obs_skip=got["obs_removed"].astype(np.uint8))
+    r = bo.solve(bo.Problem(p, visual_only=False, loop_loss=1.0, use_obs=~got["obs_removed"]), 3)
+    assert a["iterations"] == r["iterations"] and np.allclose(a["cost"], r["cost"], rtol=1e-6)
+    assert _rel(a["pose"], r["pose"].numpy()) < RTOL and _rel(a["speedbias"], r["sb"].numpy()) < RTOL
+
+
+def test_pgo_c2_matches_cpu_port(ctx):
+    """BASELINE config 2 (800 KF): Optimization::PoseGraphOptimization, 10 iterations, edges from the product's host logic"""
+    from oracle import ba_port as bp
+    p = synth_map.make_config("C2")
+    edges = O.pgo_edges(p, p["pose"])
+    got = O.pose_graph_optimization(ctx, p, edges, iterations=10)
+    pp = dict(K=p["K"], L=0, pose=p["pose"], pose_const=p["pose_const"], extr=p["extr"], cam_of_kf=p.get("cam_of_kf"))
+    ref = bp.solve(pp, 10, visual_only=True, cauchy_reproj=0.0, cauchy_edge=0.5, edges=edges)
+    assert got["iterations"] == ref["iterations"] and got["steps"] == ref["steps"]
+    assert np.allclose(got["cost"], ref["cost"], rtol=1e-6) and _rel(got["pose"], ref["pose"]) < RTOL
+
+
+def test_gba_c3_matches_cpu_port(ctx):
+    """BASELINE config 3 (the headline: 2000 KF / 100k LM / ~800k obs, visual-inertial): 4 trust-region iterations of the
+    round-2 problem, CUDA vs the compiled CPU port"""
+    from oracle import ba_port as bp
+    p = synth_map.make_config("C3")
+    got = O.solve(ctx, p, 4, visual_only=False)
+    ref = bp.solve(p, 4, visual_only=False)
+    well = (got["lm_owner"] >= 0) & (np.abs(ref["lm"]).max(1) < 100.0)
+    _port_compare(got, ref, p, lm_mask=well, cost_rtol=1e-5)
