@@ -131,7 +131,8 @@ struct Engine {
   double** d_peer_S = nullptr;
   std::vector<int> h_off_pose, h_off_sb;
   cvb_chol::TilePlan plan;
-  DevArr<double> extr_kf, intr_kf, dist_kf;
+  DevArr<double> extr_kf, intr_kf, dist_kf, xi_kf;
+  DevArr<int> model_kf;   // cam model | dist model << 8, per keyframe
   DevArr<int> obs_kf, obs_lm, lm_ptr, kf_ptr, kf_obs;
   DevArr<double> obs_uv, obs_sigma;
   DevArr<ObsLin> lin;
@@ -185,7 +186,7 @@ struct Engine {
     };
     for (int i = 0; i < 2; i++) { pose[i].free_(); sb[i].free_(); lm[i].free_(); }
     pose0.free_(); sb0.free_(); lm0.free_();
-    pose_const.free_(); off_pose.free_(); off_sb.free_(); xt_all.free_(); xt_own.free_(); col_owner.free_(); xbuf.free_(); flagd.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_();
+    pose_const.free_(); off_pose.free_(); off_sb.free_(); xt_all.free_(); xt_own.free_(); col_owner.free_(); xbuf.free_(); flagd.free_(); plan.release(); extr_kf.free_(); intr_kf.free_(); dist_kf.free_(); xi_kf.free_(); model_kf.free_();
     obs_kf.free_(); obs_lm.free_(); lm_ptr.free_(); kf_ptr.free_(); kf_obs.free_(); obs_uv.free_(); obs_sigma.free_();
     lin.free_(); wy.free_(); Hll.free_(); HllInv.free_(); bl.free_();
     pre.free_(); imu_i.free_(); imu_j.free_(); Jimu.free_(); rimu.free_();
@@ -272,7 +273,8 @@ __global__ void __launch_bounds__(256) lin_obs_kernel(int n_obs, const int* __re
                                                       const double* __restrict__ obs_uv, const double* __restrict__ obs_sigma,
                                                       const double* __restrict__ pose, const double* __restrict__ lm,
                                                       const double* __restrict__ extr_kf, const double* __restrict__ intr_kf,
-                                                      const double* __restrict__ dist_kf, const double* __restrict__ scale,
+                                                      const double* __restrict__ dist_kf, const int* __restrict__ model_kf,
+                                                      const double* __restrict__ xi_kf, const double* __restrict__ scale,
                                                       const int* __restrict__ off_pose, int n_c_pad, double a2, int mode,
                                                       ObsLin* __restrict__ lin,
                                                       ObsWY* __restrict__ wy, double* __restrict__ norms,
@@ -281,7 +283,9 @@ __global__ void __launch_bounds__(256) lin_obs_kernel(int n_obs, const int* __re
   for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_obs; o += gridDim.x * blockDim.x) {
     const int k = obs_kf[o], l = obs_lm[o];
     double r[2], Jp[12], Jl[6];
-    reproj(pose + 7 * k, extr_kf + 7 * k, intr_kf + 4 * k, dist_kf + 4 * k, lm + 3 * l, obs_uv[2 * o], obs_uv[2 * o + 1],
+    const int mk = model_kf[k];
+    const CamModel cm{mk & 0xff, mk >> 8, xi_kf[k]};
+    reproj(pose + 7 * k, extr_kf + 7 * k, intr_kf + 4 * k, dist_kf + 4 * k, cm, lm + 3 * l, obs_uv[2 * o], obs_uv[2 * o + 1],
            obs_sigma[o], r, Jp, Jl, mode == 0);
     const double s = r[0] * r[0] + r[1] * r[1];
     double sc, c;
@@ -1441,15 +1445,25 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   if ((rc = zalloc(E, E.lm[1], (size_t)3 * E.L_in))) return rc;
   if ((rc = upload(E, E.pose0, p->pose, (size_t)7 * K)) || (rc = upload(E, E.sb0, h_sb)) || (rc = upload(E, E.lm0, h_lm))) return rc;
   if ((rc = upload(E, E.pose_const, p->pose_const, (size_t)K))) return rc;
-  std::vector<double> ex((size_t)7 * K), in((size_t)4 * K), di((size_t)4 * K);
+  std::vector<double> ex((size_t)7 * K), in((size_t)4 * K), di((size_t)4 * K), xi(K, 0.0);
+  std::vector<int> mdl(K, 0);
   for (int k = 0; k < K; k++) {
     const int c = p->cam_of_kf ? p->cam_of_kf[k] : 0;
     CVB_REQUIRE(ctx, c >= 0 && c < p->n_cam, "cam_of_kf out of range");
+    const int cam = p->cam_model ? p->cam_model[c] : 0, dm = p->dist_model ? p->dist_model[c] : 0;
+    // optimization_be.cpp:186-231: "Unknown projection type" / "Unknown distortion type" → exit(-1) in the reference
+    if (cam < 0 || cam > 1) return cvb_fail(ctx, CVB_ERR_UNSUPPORTED, "Unknown projection type (%d) for camera %d", cam, c);
+    if (dm < 0 || dm > 2) return cvb_fail(ctx, CVB_ERR_UNSUPPORTED, "Unknown distortion type (%d) for camera %d", dm, c);
+    CVB_REQUIRE(ctx, cam == 0 || p->cam_xi, "unified projection camera needs cam_xi");
+    mdl[k] = cam | (dm << 8);
+    xi[k] = (cam == 1) ? p->cam_xi[c] : 0.0;
     std::memcpy(&ex[7 * (size_t)k], p->extr + 7 * (size_t)c, 7 * sizeof(double));
     std::memcpy(&in[4 * (size_t)k], p->intr + 4 * (size_t)c, 4 * sizeof(double));
     std::memcpy(&di[4 * (size_t)k], p->dist + 4 * (size_t)c, 4 * sizeof(double));
   }
-  if ((rc = upload(E, E.extr_kf, ex)) || (rc = upload(E, E.intr_kf, in)) || (rc = upload(E, E.dist_kf, di))) return rc;
+  if ((rc = upload(E, E.extr_kf, ex)) || (rc = upload(E, E.intr_kf, in)) || (rc = upload(E, E.dist_kf, di)) ||
+      (rc = upload(E, E.model_kf, mdl)) || (rc = upload(E, E.xi_kf, xi)))
+    return rc;
   if ((rc = upload(E, E.obs_kf, h_obs_kf)) || (rc = upload(E, E.obs_lm, h_obs_lm)) || (rc = upload(E, E.lm_ptr, h_lm_ptr)) ||
       (rc = upload(E, E.kf_ptr, h_kf_ptr)) || (rc = upload(E, E.kf_obs, h_kf_obs)) || (rc = upload(E, E.obs_uv, h_uv)) ||
       (rc = upload(E, E.obs_sigma, h_sigma)))
@@ -1573,7 +1587,7 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
 int evaluate(Engine& E, int b, int mode, double* cost_out) {
   const int rg = RED_BLOCKS;
   lin_obs_kernel<<<rg, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.obs_uv.p, E.obs_sigma.p, E.pose[b].p, E.lm[b].p,
-                                       E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.scale.p, E.off_pose.p, E.n_c_pad, E.a2_reproj, mode,
+                                       E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.model_kf.p, E.xi_kf.p, E.scale.p, E.off_pose.p, E.n_c_pad, E.a2_reproj, mode,
                                        E.lin.p, E.wy.p, nullptr, E.partials.p, 0);
   ENG_LAUNCH();
   lin_imu_kernel<<<rg, 256, 0, E.st>>>(E.n_imu, E.imu_i.p, E.imu_j.p, E.pre.p, E.pose[b].p, E.sb[b].p, E.scale.p, E.off_pose.p, E.off_sb.p, E.g,
@@ -1978,7 +1992,7 @@ int engine_corrected_norms(Engine& E, double* h_norms_full, int n_obs_full) {
   DevArr<double> d;
   if (d.alloc((size_t)E.n_obs)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed");
   lin_obs_kernel<<<RED_BLOCKS, 256, 0, E.st>>>(E.n_obs, E.obs_kf.p, E.obs_lm.p, E.obs_uv.p, E.obs_sigma.p, E.pose[E.cur].p,
-                                               E.lm[E.cur].p, E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.scale.p, E.off_pose.p, E.n_c_pad,
+                                               E.lm[E.cur].p, E.extr_kf.p, E.intr_kf.p, E.dist_kf.p, E.model_kf.p, E.xi_kf.p, E.scale.p, E.off_pose.p, E.n_c_pad,
                                                E.a2_reproj, 2, E.lin.p, E.wy.p, d.p, E.partials.p, 0);
   ENG_LAUNCH();
   std::vector<double> h(E.n_obs);

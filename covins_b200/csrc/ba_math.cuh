@@ -6,7 +6,8 @@
 //   pose block [qx,qy,qz,qw,x,y,z] = T_ws            keyframe_base.cpp:486-499
 //   Plus [A]   delta = [dtheta, dp]; q+ = Exp(dtheta) * q (world-side), p+ = p + dp
 //              (robopt::local_param::PoseQuaternionLocalParameterization, optimization_be.cpp:69,303,843)
-//   reprojection [A]  robopt::reprojection::GlobalEuclideanReprError<Pinhole,RadTan> (optimization_be.cpp:193-199)
+//   reprojection [A]  robopt::reprojection::GlobalEuclideanReprError<Camera,Distortion>, all six instantiations
+//                     (optimization_be.cpp:186-231)
 //   between [A]       robopt::posegraph::SixDofBetweenError, kImu (optimization_be.cpp:252,554,934,968,1017)
 //   IMU [A]           robopt::imu::PreintegrationFactor over VINS-Mono style midpoint preintegration
 //                     (optimization_be.cpp:140-143, 396-416)
@@ -133,9 +134,99 @@ __host__ __device__ inline void cauchy(double s, double a2, double* scale, doubl
   }
 }
 
+// ---- camera models of robopt::reprojection::GlobalEuclideanReprError<Camera, Distortion> (optimization_be.cpp:186-231,
+// 480-525): Camera ∈ {aslam::PinholeCamera, aslam::UnifiedProjectionCamera}, Distortion ∈ {RadTan, Equidistant, Fisheye}.
+// The formulas are the published aslam_cv2 ones [A] (the library is not in the tree):
+//   pinhole   x = X/Z, y = Y/Z
+//   unified   x = X/(Z + xi |p|), y = Y/(Z + xi |p|)            (intrinsics [xi, fu, fv, cu, cv])
+//   radtan    (k1,k2,p1,p2): xd = x(1+k1 r2+k2 r4) + 2 p1 x y + p2 (r2+2x2),  yd = y(...) + p1 (r2+2y2) + 2 p2 x y
+//   equidist  (k1..k4): theta = atan r, thd = theta (1 + k1 th2 + k2 th4 + k3 th6 + k4 th8), (xd,yd) = (thd/r)(x,y)
+//   fisheye   FOV model (w): (xd,yd) = atan(2 r tan(w/2)) / (w r) (x,y); w*w < 1e-5 → identity; r*r < 1e-5 → 2 tan(w/2)/w
+//   u = fu xd + cu, v = fv yd + cv.
+constexpr int CAM_PINHOLE = 0, CAM_UNIFIED = 1;
+constexpr int DIST_RADTAN = 0, DIST_EQUI = 1, DIST_FISHEYE = 2;
+struct CamModel {
+  int cam, dist;
+  double xi;
+};
+
+// normalised image point (x, y) of a camera-frame point and its 2x3 Jacobian N (row-major); false = not projectable
+__host__ __device__ inline bool cam_normalise(const CamModel& cm, V3 pc, double* x, double* y, double N[6], bool want_jac) {
+  if (cm.cam == CAM_PINHOLE) {
+    if (!(pc.z > 1e-10)) return false;   // aslam::ProjectionResult::POINT_BEHIND_CAMERA [A]
+    const double iz = 1.0 / pc.z;
+    *x = pc.x * iz; *y = pc.y * iz;
+    if (want_jac) { N[0] = iz; N[1] = 0.0; N[2] = -pc.x * iz * iz; N[3] = 0.0; N[4] = iz; N[5] = -pc.y * iz * iz; }
+    return true;
+  }
+  const double d = sqrt(pc.x * pc.x + pc.y * pc.y + pc.z * pc.z);
+  const double den = pc.z + cm.xi * d;
+  if (!(den > 1e-10) || !(d > 0.0)) return false;   // outside the unified model's field of view [A]
+  const double rz = 1.0 / den;
+  *x = pc.x * rz; *y = pc.y * rz;
+  if (want_jac) {
+    const double k = cm.xi / d, rz2 = rz * rz;
+    // d den / d pc = (xi X/d, xi Y/d, 1 + xi Z/d)
+    const double dx = k * pc.x, dy = k * pc.y, dz = 1.0 + k * pc.z;
+    N[0] = rz - pc.x * rz2 * dx; N[1] = -pc.x * rz2 * dy; N[2] = -pc.x * rz2 * dz;
+    N[3] = -pc.y * rz2 * dx; N[4] = rz - pc.y * rz2 * dy; N[5] = -pc.y * rz2 * dz;
+  }
+  return true;
+}
+
+// distorted point and its 2x2 Jacobian D (row-major) w.r.t. (x, y)
+__host__ __device__ inline void cam_distort(const CamModel& cm, const double* dist, double x, double y, double* xd, double* yd, double D[4],
+                                            bool want_jac) {
+  const double r2 = x * x + y * y;
+  if (cm.dist == DIST_RADTAN) {
+    const double k1 = dist[0], k2 = dist[1], p1 = dist[2], p2 = dist[3];
+    const double rad = 1.0 + k1 * r2 + k2 * r2 * r2;
+    *xd = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+    *yd = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+    if (want_jac) {
+      const double c = k1 + 2.0 * k2 * r2;
+      D[0] = rad + 2.0 * x * x * c + 2.0 * p1 * y + 6.0 * p2 * x;
+      D[1] = 2.0 * x * y * c + 2.0 * p1 * x + 2.0 * p2 * y;
+      D[2] = D[1];
+      D[3] = rad + 2.0 * y * y * c + 6.0 * p1 * y + 2.0 * p2 * x;
+    }
+    return;
+  }
+  double s, ds_dr_over_r;   // (xd,yd) = s (x,y);  ds/dr divided by r (finite at r → 0)
+  if (cm.dist == DIST_EQUI) {
+    const double r = sqrt(r2);
+    if (r < 1e-8) { s = 1.0; ds_dr_over_r = 0.0; }
+    else {
+      const double th = atan(r), t2 = th * th, t4 = t2 * t2, t6 = t4 * t2, t8 = t4 * t4;
+      const double thd = th * (1.0 + dist[0] * t2 + dist[1] * t4 + dist[2] * t6 + dist[3] * t8);
+      const double dthd = 1.0 + 3.0 * dist[0] * t2 + 5.0 * dist[1] * t4 + 7.0 * dist[2] * t6 + 9.0 * dist[3] * t8;
+      s = thd / r;
+      ds_dr_over_r = (dthd / (1.0 + r2) * r - thd) / (r2 * r);
+    }
+  } else {   // DIST_FISHEYE (FOV)
+    const double w = dist[0];
+    if (w * w < 1e-5) { s = 1.0; ds_dr_over_r = 0.0; }
+    else {
+      const double c = 2.0 * tan(0.5 * w);
+      if (r2 < 1e-5) { s = c / w; ds_dr_over_r = 0.0; }
+      else {
+        const double r = sqrt(r2), at = atan(c * r);
+        s = at / (w * r);
+        ds_dr_over_r = (c * r / (1.0 + c * c * r2) - at) / (w * r2 * r);
+      }
+    }
+  }
+  *xd = s * x; *yd = s * y;
+  if (want_jac) {
+    D[0] = s + x * x * ds_dr_over_r; D[1] = x * y * ds_dr_over_r;
+    D[2] = D[1]; D[3] = s + y * y * ds_dr_over_r;
+  }
+}
+
 // ---- reprojection: r (2), Jl = dr/dp_w (2x3, row-major), Jp = dr/d[dtheta,dp] (2x6).  Returns false if the
-// point is not in front of the camera (Z <= 1e-10): the residual is then defined as zero with zero Jacobian.
-__host__ __device__ inline bool reproj(const double* pose, const double* extr, const double* intr, const double* dist,
+// point is not projectable (behind the camera / outside the model's field of view): the residual is then defined as zero
+// with zero Jacobian.
+__host__ __device__ inline bool reproj(const double* pose, const double* extr, const double* intr, const double* dist, const CamModel& cm,
                                        const double* lm, double u_obs, double v_obs, double sigma, double r[2],
                                        double Jp[12], double Jl[6], bool want_jac) {
   const Pose Pw = load_pose(pose), Ps = load_pose(extr);
@@ -143,7 +234,8 @@ __host__ __device__ inline bool reproj(const double* pose, const double* extr, c
   const V3 d = V3{lm[0], lm[1], lm[2]} - Pw.t;
   const V3 ps = mulT(Rws, d);
   const V3 pc = mulT(Rsc, ps - Ps.t);
-  if (!(pc.z > 1e-10)) {   // aslam::ProjectionResult::POINT_BEHIND_CAMERA [A]
+  double x, y, N[6];
+  if (!cam_normalise(cm, pc, &x, &y, N, want_jac)) {
     r[0] = r[1] = 0.0;
     if (want_jac) {
       for (int i = 0; i < 12; i++) Jp[i] = 0.0;
@@ -151,24 +243,16 @@ __host__ __device__ inline bool reproj(const double* pose, const double* extr, c
     }
     return false;
   }
-  const double iz = 1.0 / pc.z, x = pc.x * iz, y = pc.y * iz;
-  const double k1 = dist[0], k2 = dist[1], p1 = dist[2], p2 = dist[3];
-  const double r2 = x * x + y * y, rad = 1.0 + k1 * r2 + k2 * r2 * r2;
-  const double xd = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
-  const double yd = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+  double xd, yd, D[4];
+  cam_distort(cm, dist, x, y, &xd, &yd, D, want_jac);
   const double is = 1.0 / sigma;
   r[0] = (intr[0] * xd + intr[2] - u_obs) * is;
   r[1] = (intr[1] * yd + intr[3] - v_obs) * is;
   if (!want_jac) return true;
-  const double c = k1 + 2.0 * k2 * r2;
-  const double dxdx = rad + 2.0 * x * x * c + 2.0 * p1 * y + 6.0 * p2 * x;
-  const double dxdy = 2.0 * x * y * c + 2.0 * p1 * x + 2.0 * p2 * y;
-  const double dydx = 2.0 * x * y * c + 2.0 * p1 * x + 2.0 * p2 * y;
-  const double dydy = rad + 2.0 * y * y * c + 6.0 * p1 * y + 2.0 * p2 * x;
-  // d(u,v)/d pc (2x3), already divided by sigma
+  // d(u,v)/d pc (2x3), already divided by sigma:  diag(fx, fy)/sigma * D * N
   const double fx = intr[0] * is, fy = intr[1] * is;
-  const double a00 = fx * dxdx * iz, a01 = fx * dxdy * iz, a02 = -fx * (dxdx * x + dxdy * y) * iz;
-  const double a10 = fy * dydx * iz, a11 = fy * dydy * iz, a12 = -fy * (dydx * x + dydy * y) * iz;
+  const double a00 = fx * (D[0] * N[0] + D[1] * N[3]), a01 = fx * (D[0] * N[1] + D[1] * N[4]), a02 = fx * (D[0] * N[2] + D[1] * N[5]);
+  const double a10 = fy * (D[2] * N[0] + D[3] * N[3]), a11 = fy * (D[2] * N[1] + D[3] * N[4]), a12 = fy * (D[2] * N[2] + D[3] * N[5]);
   // B = A * Rsc^T (2x3): derivative w.r.t. p_s
   const double b00 = a00 * Rsc.m[0] + a01 * Rsc.m[1] + a02 * Rsc.m[2], b01 = a00 * Rsc.m[3] + a01 * Rsc.m[4] + a02 * Rsc.m[5],
                b02 = a00 * Rsc.m[6] + a01 * Rsc.m[7] + a02 * Rsc.m[8];

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,9 @@ struct cvb_ctx {
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
   void* ba = nullptr;  // BA state (owned by ba_*.cu)
+  // every extern "C" entry point holds this lock for its duration (cvb_device_guard): a ctx may be shared between host
+  // threads — calls on one ctx are serialised, concurrency comes from one ctx per thread
+  mutable std::recursive_mutex mtx;
 };
 
 enum { WS_Q = 0, WS_T, WS_SEG, WS_OUT0, WS_OUT1, WS_OUT2, WS_PART_I, WS_PART_D, WS_LIST_I, WS_LIST_D, WS_SKIPA,
@@ -59,16 +63,20 @@ void* cvb_pinned(cvb_ctx* ctx, size_t bytes);
 
 static inline cudaStream_t cvb_stream(cvb_ctx* ctx, void* s) { return s ? (cudaStream_t)s : ctx->stream; }
 
-// Scoped device guard: every extern "C" entry point makes the ctx's device current for the calling thread (a new host
-// thread defaults to device 0; two ctxs on different GPUs may be driven from one thread) and restores the previous one.
+// Scoped guard of every extern "C" entry point: takes the ctx's lock (calls on one ctx are serialised, so a ctx may be
+// shared between host threads) and makes the ctx's device current for the calling thread (a new host thread defaults to
+// device 0; two ctxs on different GPUs may be driven from one thread), restoring the previous device on exit.
 struct cvb_device_guard {
   int prev = -1;
   bool switched = false;
-  explicit cvb_device_guard(const cvb_ctx* c) {
+  const cvb_ctx* ctx = nullptr;
+  explicit cvb_device_guard(const cvb_ctx* c) : ctx(c) {
+    if (c) c->mtx.lock();
     if (c && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
   }
   ~cvb_device_guard() {
     if (switched) cudaSetDevice(prev);
+    if (ctx) ctx->mtx.unlock();
   }
   cvb_device_guard(const cvb_device_guard&) = delete;
   cvb_device_guard& operator=(const cvb_device_guard&) = delete;

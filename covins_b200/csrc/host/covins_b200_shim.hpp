@@ -69,6 +69,12 @@ struct Adapter {
   // camera: pinhole intrinsics [fx,fy,cx,cy] + radtan [k1,k2,p1,p2]   (aslam::PinholeCamera::getParameters(),
   // getDistortion().getParameters(); optimization_be.cpp:95-103).  Returns false for unsupported models.
   static bool camera(const KF& kf, double intr[4], double dist[4]) { return kf.GetCameraParams(intr, dist); }
+  // camera / distortion type of the keyframe's aslam camera — the template arguments the reference picks for
+  // GlobalEuclideanReprError at optimization_be.cpp:186-231: cam 0 = kPinhole, 1 = kUnifiedProjection (xi = its first
+  // intrinsic); dist 0 = kRadTan, 1 = kEquidistant, 2 = kFisheye.  The default serves containers without the notion
+  // (ORB-SLAM3 agents only send pinhole + radtan, orb_slam3/src/KeyFrame.cc:64-65); specialise for the real Keyframe:
+  //   cam = kf.camera_->getType() == aslam::Camera::Type::kUnifiedProjection, dist from getDistortion().getType().
+  static void camera_model(const KF& kf, int* cam, int* dist, double* xi) { (void)kf; *cam = 0; *dist = 0; *xi = 0.0; }
   // raw IMU samples of the KF's preintegration (robopt PreintegrationBase::getReadingsByIndex / getTimeDiffByIndex,
   // keyframe_base.cpp:145-173) and its first reading + noise (keyframe_be.cpp:187-203)
   static size_t imu_count(const KF& kf) { return kf.ImuDt().size(); }
@@ -188,7 +194,8 @@ inline bool sqrt_info_from_cov(const double* cov /*36 row-major*/, double* out /
 // Flattened problem with owning storage + the cvb_ba_problem view
 struct Flat {
   std::vector<double> pose, sb, extr, intr, dist, lm, obs_sigma, imu_dt, imu_acc, imu_gyr, imu_acc0, imu_gyr0, edge_q, edge_t,
-      edge_S;
+      edge_S, cam_xi;
+  std::vector<int32_t> cam_model, dist_model;
   std::vector<float> obs_uv;
   std::vector<uint8_t> pose_const, edge_robust;
   std::vector<int32_t> cam_of_kf, lm_obs_ptr, obs_kf, imu_i, imu_j, imu_ptr, edge_i, edge_j;
@@ -209,6 +216,7 @@ struct Flat {
     p.imu_noise = imu_noise;
     p.edge_i = edge_i.data(); p.edge_j = edge_j.data(); p.edge_q = edge_q.data(); p.edge_t = edge_t.data();
     p.edge_sqrt_info = edge_S.data(); p.edge_robust = edge_robust.data();
+    if (cam_model.size() == (size_t)p.n_cam) { p.cam_model = cam_model.data(); p.dist_model = dist_model.data(); p.cam_xi = cam_xi.data(); }
     return p;
   }
 };
@@ -268,6 +276,12 @@ void GlobalBundleAdjustment(Context& ctx, MapPtr map, int interations_limit, dou
     if (!Adapter<KF>::camera(*kf, &F.intr[4 * (size_t)k], &F.dist[4 * (size_t)k])) {
       std::printf("FATAL: Unknown projection type.\n");                                            // :112-114
       std::exit(-1);
+    }
+    {
+      int cm = 0, dm = 0; double xi = 0.0;
+      Adapter<KF>::camera_model(*kf, &cm, &dm, &xi);                                               // :186-231
+      F.cam_model.resize(F.pose_const.size(), 0); F.dist_model.resize(F.pose_const.size(), 0); F.cam_xi.resize(F.pose_const.size(), 0.0);
+      F.cam_model[k] = cm; F.dist_model[k] = dm; F.cam_xi[k] = xi;
     }
     if (!visual_only) {                                                                             // :117-144, 367-421
       auto pred = kf->GetPredecessor();

@@ -174,6 +174,26 @@ int cvb_db_append(cvb_ctx* ctx, cvb_db* db, const uint8_t* rows, const int32_t* 
   return CVB_OK;
 }
 
+int cvb_db_remove(cvb_ctx* ctx, cvb_db* db, int kf_index) {
+  if (!ctx || !db) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
+  const int n_seg = (int)db->seg_ptr.size() - 1;
+  CVB_REQUIRE(ctx, kf_index >= 0 && kf_index < n_seg, "cvb_db_remove: keyframe index %d out of range (database holds %d)", kf_index, n_seg);
+  const int64_t a = db->seg_ptr[kf_index], b = db->seg_ptr[kf_index + 1], end = db->seg_ptr.back();
+  const size_t tail = (size_t)(end - b) * db->desc_bytes, len = (size_t)(b - a);
+  if (tail && len) {   // move the tail down through a scratch buffer (source and destination overlap)
+    void* tmp = cvb_ws(ctx, WS_GS2, tail);
+    if (!tmp) return CVB_ERR_CUDA;
+    CVB_CUDA(ctx, cudaMemcpyAsync(tmp, db->d_rows + (size_t)b * db->desc_bytes, tail, cudaMemcpyDeviceToDevice, ctx->stream));
+    CVB_CUDA(ctx, cudaMemcpyAsync(db->d_rows + (size_t)a * db->desc_bytes, tmp, tail, cudaMemcpyDeviceToDevice, ctx->stream));
+    CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  db->seg_ptr.erase(db->seg_ptr.begin() + kf_index + 1);
+  for (size_t i = (size_t)kf_index + 1; i < db->seg_ptr.size(); i++) db->seg_ptr[i] -= (int32_t)len;
+  db->seg_dirty = true;
+  return CVB_OK;
+}
+
 int cvb_db_size(const cvb_db* db, int32_t* n_kf, int64_t* n_rows) {
   if (!db) return CVB_ERR_INVALID;
   if (n_kf) *n_kf = (int32_t)db->seg_ptr.size() - 1;

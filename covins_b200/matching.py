@@ -115,6 +115,10 @@ class DescriptorDatabase:
         assert int(rpk.sum()) == len(rows), "rows_per_kf does not add up to the number of rows"
         self.ctx.check(lib().cvb_db_append(self.ctx.handle, self.handle, _ptr(rows), _ptr(rpk), len(rpk)))
 
+    def remove(self, kf_index: int):
+        """a keyframe leaves the map (culling / erase): later keyframes move down by one index"""
+        self.ctx.check(lib().cvb_db_remove(self.ctx.handle, self.handle, int(kf_index)))
+
     def size(self):
         import ctypes as C
         n_kf, n_rows = C.c_int32(), C.c_int64()

@@ -23,7 +23,7 @@ class BaProblem(C.Structure):
                     "pose", "speedbias", "pose_const", "cam_of_kf", "extr", "intr", "dist", "lm", "lm_obs_ptr", "obs_kf",
                     "obs_uv", "obs_sigma", "obs_skip", "imu_i", "imu_j", "imu_ptr", "imu_dt", "imu_acc", "imu_gyr",
                     "imu_acc0", "imu_gyr0", "imu_noise", "edge_i", "edge_j", "edge_q", "edge_t", "edge_sqrt_info",
-                    "edge_robust")]
+                    "edge_robust", "cam_model", "dist_model", "cam_xi")]
 
 
 class BaOptions(C.Structure):
@@ -69,6 +69,9 @@ class _Flat:
         a["extr"] = _arr(p["extr"], np.float64).reshape(-1, 7)
         a["intr"] = _arr(p.get("intr", np.zeros((len(a["extr"]), 4))), np.float64)
         a["dist"] = _arr(p.get("dist", np.zeros((len(a["extr"]), 4))), np.float64)
+        # GlobalEuclideanReprError<Camera, Distortion> template arguments per calibration (None = pinhole / radtan)
+        a["cam_model"] = _arr(p.get("cam_model"), np.int32); a["dist_model"] = _arr(p.get("dist_model"), np.int32)
+        a["cam_xi"] = _arr(p.get("cam_xi"), np.float64)
         a["lm"] = _arr(p.get("lm", np.zeros((0, 3))), np.float64)
         a["lm_obs_ptr"] = _arr(p.get("lm_obs_ptr", np.zeros(1)), np.int32)
         a["obs_kf"] = _arr(p.get("obs_kf", np.zeros(0)), np.int32)

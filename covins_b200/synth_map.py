@@ -289,6 +289,44 @@ CONFIGS = {
 }
 
 
+def with_camera_model(p: dict, cam_model: int, dist_model: int, dist=None, xi: float = 0.0, seed: int = 0, pix_noise: float = 1.0):
+    """The same map observed through another GlobalEuclideanReprError<Camera, Distortion> instantiation
+    (optimization_be.cpp:186-231): cam_model 0 pinhole / 1 unified(xi), dist_model 0 radtan / 1 equidistant / 2 fisheye (FOV).
+    The inlier observations are re-projected from the ground truth with the new model (+ pixel noise); gross outliers keep
+    their random pixels."""
+    q = dict(p)
+    default = {0: EUROC_DIST, 1: np.array([-0.013, 0.02, -0.012, 0.002]), 2: np.array([0.93, 0.0, 0.0, 0.0])}[dist_model]
+    d = np.asarray(default if dist is None else dist, float)
+    rng = np.random.default_rng(seed)
+    R_ws = quat_to_rot(p["gt_pose"][:, :4]); t_ws = p["gt_pose"][:, 4:]
+    R_sc = quat_to_rot(p["extr"][0][:4]); t_sc = p["extr"][0][4:]
+    obs_lm = np.repeat(np.arange(p["L"]), np.diff(p["lm_obs_ptr"]))
+    k = p["obs_kf"]
+    ps = np.einsum("nji,nj->ni", R_ws[k], p["gt_lm"][obs_lm] - t_ws[k])
+    pc = (ps - t_sc) @ R_sc
+    den = pc[:, 2] + (xi * np.linalg.norm(pc, axis=1) if cam_model == 1 else 0.0)
+    x, y = pc[:, 0] / den, pc[:, 1] / den
+    r2 = x * x + y * y
+    if dist_model == 0:
+        rad = 1 + d[0] * r2 + d[1] * r2 * r2
+        xd = x * rad + 2 * d[2] * x * y + d[3] * (r2 + 2 * x * x); yd = y * rad + d[2] * (r2 + 2 * y * y) + 2 * d[3] * x * y
+    elif dist_model == 1:
+        r = np.sqrt(r2); th = np.arctan(r); t2 = th * th
+        s = np.where(r > 1e-8, th * (1 + d[0] * t2 + d[1] * t2 ** 2 + d[2] * t2 ** 3 + d[3] * t2 ** 4) / np.maximum(r, 1e-12), 1.0)
+        xd, yd = s * x, s * y
+    else:
+        w = d[0]; c = 2 * np.tan(0.5 * w); r = np.sqrt(r2)
+        s = np.where(r2 < 1e-5, c / w, np.arctan(c * r) / (w * np.maximum(r, 1e-12)))
+        xd, yd = s * x, s * y
+    uv = np.stack([p["intr"][0][0] * xd + p["intr"][0][2], p["intr"][0][1] * yd + p["intr"][0][3]], -1) + rng.normal(0, pix_noise, (len(k), 2))
+    keep = p["obs_is_outlier"]
+    uv[keep] = p["obs_uv"][keep]
+    q["obs_uv"] = uv.astype(np.float32)
+    q["dist"] = d[None, :].copy()
+    q["cam_model"] = np.array([cam_model], np.int32); q["dist_model"] = np.array([dist_model], np.int32); q["cam_xi"] = np.array([xi])
+    return q
+
+
 _CACHE_VERSION = "r02a"   # bump when make_map changes
 
 

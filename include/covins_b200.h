@@ -14,9 +14,10 @@
  *   - functions without suffix take HOST buffers and include all H2D/D2H copies (synchronous on
  *     return); `_dev` variants take DEVICE pointers and enqueue on `stream` (a cudaStream_t passed as
  *     void*; NULL = the ctx's own stream) without synchronising.
- *   - a ctx owns one device, one stream, and grow-only device workspaces; it is NOT thread-safe:
- *     use one ctx per host thread (the reference runs one place-recognition thread per agent,
- *     src/covins_backend/handler_be.cpp:52-56, and at most one optimisation per map).
+ *   - a ctx owns one device, one stream, and grow-only device workspaces.  Every entry point makes the ctx's device
+ *     current for the calling thread and holds the ctx's lock for its duration: a ctx may be shared between host threads
+ *     (calls are serialised per ctx); for concurrency use one ctx per host thread (the reference runs one
+ *     place-recognition thread per agent, src/covins_backend/handler_be.cpp:52-56, and at most one optimisation per map).
  *   - no CPU fallback exists: without a CUDA device every compute call fails with CVB_ERR_CUDA.
  */
 #ifndef COVINS_B200_H_
@@ -108,6 +109,10 @@ CVB_API int cvb_db_destroy(cvb_ctx* ctx, cvb_db* db);
 CVB_API int cvb_db_reserve(cvb_ctx* ctx, cvb_db* db, int64_t rows);
 CVB_API int cvb_db_append(cvb_ctx* ctx, cvb_db* db, const uint8_t* rows, const int32_t* rows_per_kf, int n_kf);
 CVB_API int cvb_db_size(const cvb_db* db, int32_t* n_kf, int64_t* n_rows);
+/* A keyframe leaves the map (Keyframe::SetInvalid / culling, keyframe_be.cpp:413-440; Map::EraseKeyframe): its segment is
+ * cut out of the resident descriptor array; the database indices of the keyframes appended after it drop by one (the
+ * order of the remaining keyframes is kept, like erasing from a vector). */
+CVB_API int cvb_db_remove(cvb_ctx* ctx, cvb_db* db, int kf_index);
 CVB_API int cvb_db_match_hamming(cvb_ctx* ctx, cvb_db* db, const uint8_t* q, int nq, float thr, float ratio,
                                  int32_t* n_matches, int32_t* m_kf, int32_t* m_query, int32_t* m_train,
                                  float* m_dist, int cap, int32_t* n_total);
@@ -297,7 +302,7 @@ typedef struct cvb_ba_problem {
   const int32_t* cam_of_kf;   /* [K]     calibration index, NULL = 0 */
   const double* extr;         /* [n_cam][7] T_sc (constant block, optimization_be.cpp:91-92) */
   const double* intr;         /* [n_cam][4] fx, fy, cx, cy (constant) */
-  const double* dist;         /* [n_cam][4] radtan k1, k2, p1, p2 (constant) */
+  const double* dist;         /* [n_cam][4] distortion coefficients (constant); meaning per dist_model, default radtan k1, k2, p1, p2 */
   const double* lm;           /* [L][3]  world position */
   const int32_t* lm_obs_ptr;  /* [L+1]   CSR by landmark */
   const int32_t* obs_kf;      /* [n_obs] keyframe index */
@@ -321,6 +326,11 @@ typedef struct cvb_ba_problem {
   const double* edge_t;         /* [n_edge][3] measured t_12 */
   const double* edge_sqrt_info; /* [n_edge][36] row-major, rotation rows first (optimization_be.cpp:896-897) */
   const uint8_t* edge_robust;   /* [n_edge] 1 = CauchyLoss(cauchy_edge) on this edge; NULL = none */
+  /* camera / distortion model per calibration: the template arguments of GlobalEuclideanReprError<Camera, Distortion>
+   * (optimization_be.cpp:186-231).  NULL = pinhole / radtan for every camera (what ORB-SLAM3 agents send). */
+  const int32_t* cam_model;     /* [n_cam] 0 = aslam::PinholeCamera, 1 = aslam::UnifiedProjectionCamera */
+  const int32_t* dist_model;    /* [n_cam] 0 = RadTan (k1,k2,p1,p2), 1 = Equidistant (k1..k4), 2 = Fisheye / FOV (w) — in `dist` */
+  const double* cam_xi;         /* [n_cam] mirror parameter xi of the unified model (its intrinsics are [xi, fu, fv, cu, cv]) */
 } cvb_ba_problem;
 
 typedef struct cvb_ba_options {

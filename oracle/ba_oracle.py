@@ -82,19 +82,43 @@ def pose_plus(pose, delta):
 
 
 # ------------------------------------------------------------------------------------------------ residuals
-def reproj_residual(pose, lm, extr, intr, dist, uv, sigma):
+def reproj_residual(pose, lm, extr, intr, dist, uv, sigma, cam_model=None, dist_model=None, xi=None):
+    """GlobalEuclideanReprError<Camera, Distortion> [A]: Camera 0 pinhole / 1 unified (xi), Distortion 0 radtan / 1 equidistant
+    / 2 fisheye (FOV) — per observation (tensors) or None = pinhole + radtan (optimization_be.cpp:186-231)."""
     q_ws, t_ws = pose[..., :4], pose[..., 4:]
     p_s = qrot(qconj(q_ws), lm - t_ws)
     p_c = qrot(qconj(extr[..., :4]), p_s - extr[..., 4:])
-    # aslam::ProjectionResult POINT_BEHIND_CAMERA (z < 1e-10): the error term zeroes residual and Jacobians [A]
-    front = p_c[..., 2] > 1e-10
-    zs = torch.where(front, p_c[..., 2], torch.ones_like(p_c[..., 2]))
-    x, y = p_c[..., 0] / zs, p_c[..., 1] / zs
-    k1, k2, p1, p2 = dist.unbind(-1)
+    n = p_c.shape[0]
+    cam = torch.zeros(n, dtype=torch.long) if cam_model is None else cam_model
+    dm = torch.zeros(n, dtype=torch.long) if dist_model is None else dist_model
+    xi = torch.zeros(n) if xi is None else xi
+    X, Y, Z = p_c.unbind(-1)
+    d = p_c.norm(dim=-1)
+    den = torch.where(cam == 1, Z + xi * d, Z)
+    # aslam::ProjectionResult POINT_BEHIND_CAMERA (z < 1e-10) / outside the unified model: the error term zeroes residual
+    # and Jacobians [A]
+    front = den > 1e-10
+    dens = torch.where(front, den, torch.ones_like(den))
+    x, y = X / dens, Y / dens
     r2 = x * x + y * y
+    k1, k2, p1, p2 = dist.unbind(-1)
+    # radtan
     rad = 1 + k1 * r2 + k2 * r2 * r2
-    xd = x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
-    yd = y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    xd0 = x * rad + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    yd0 = y * rad + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    # equidistant (k1..k4)
+    rs = torch.sqrt(torch.where(r2 > 1e-16, r2, torch.ones_like(r2)))
+    th = torch.atan(rs); t2 = th * th
+    thd = th * (1 + k1 * t2 + k2 * t2 * t2 + p1 * t2 ** 3 + p2 * t2 ** 4)
+    s1 = torch.where(r2 > 1e-16, thd / rs, torch.ones_like(rs))
+    # fisheye / FOV (w = k1)
+    w = k1
+    ws = torch.where(w * w < 1e-5, torch.ones_like(w), w)
+    c = 2 * torch.tan(0.5 * ws)
+    rs2 = torch.sqrt(torch.where(r2 >= 1e-5, r2, torch.ones_like(r2)))
+    s2 = torch.where(w * w < 1e-5, torch.ones_like(w), torch.where(r2 < 1e-5, c / ws, torch.atan(c * rs2) / (ws * rs2)))
+    xd = torch.where(dm == 0, xd0, torch.where(dm == 1, s1 * x, s2 * x))
+    yd = torch.where(dm == 0, yd0, torch.where(dm == 1, s1 * y, s2 * y))
     u = intr[..., 0] * xd + intr[..., 2]
     v = intr[..., 1] * yd + intr[..., 3]
     r = torch.stack([(u - uv[..., 0]) / sigma, (v - uv[..., 1]) / sigma], -1)
@@ -235,6 +259,10 @@ class Problem:
             self.o_sigma = torch.tensor(np.asarray(p["obs_sigma"], float)[sel])
             self.o_intr = torch.tensor(np.asarray(p["intr"], float))[cam[self.o_kf]]
             self.o_dist = torch.tensor(np.asarray(p["dist"], float))[cam[self.o_kf]]
+            ncam = len(np.asarray(p["extr"]).reshape(-1, 7))
+            self.o_cam = torch.tensor(np.asarray(p["cam_model"] if p.get("cam_model") is not None else np.zeros(ncam), np.int64))[cam[self.o_kf]]
+            self.o_dm = torch.tensor(np.asarray(p["dist_model"] if p.get("dist_model") is not None else np.zeros(ncam), np.int64))[cam[self.o_kf]]
+            self.o_xi = torch.tensor(np.asarray(p["cam_xi"] if p.get("cam_xi") is not None else np.zeros(ncam), float))[cam[self.o_kf]]
         else:
             self.lm_in = np.zeros(0, bool); self.o_lm = np.zeros(0, np.int64); self.o_kf = np.zeros(0, np.int64)
         # ---- IMU factors ----
@@ -329,7 +357,8 @@ class Problem:
             P, Lm = pose[self.o_kf], lm[self.o_lm]
             E = self.extr_kf[self.o_kf]
             info["reproj"] = add_block(
-                lambda d: reproj_residual(pose_plus(P, d[0]), Lm + d[1], E, self.o_intr, self.o_dist, self.o_uv, self.o_sigma),
+                lambda d: reproj_residual(pose_plus(P, d[0]), Lm + d[1], E, self.o_intr, self.o_dist, self.o_uv, self.o_sigma,
+                                          self.o_cam, self.o_dm, self.o_xi),
                 [P, Lm], [self.col_pose[self.o_kf], self.col_lm[self.o_lm]], [6, 3], self.cauchy_reproj)
         if self.imu is not None:
             Pi, Si, Pj, Sj = pose[self.imu_i], sb[self.imu_i], pose[self.imu_j], sb[self.imu_j]

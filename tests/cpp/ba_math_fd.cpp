@@ -13,18 +13,24 @@ int main(){
   double pose[7]={0.1,-0.2,0.3,0.9,1,2,3}; {double n=sqrt(pose[0]*pose[0]+pose[1]*pose[1]+pose[2]*pose[2]+pose[3]*pose[3]); for(int i=0;i<4;i++)pose[i]/=n;}
   double extr[7]={0.5,-0.5,0.5,0.5,0.02,-0.06,0.01};
   double intr[4]={458.654,457.296,367.215,248.375}, dist[4]={-0.28340811,0.07395907,0.00019359,1.76187114e-05};
-  // find a lm in front
+  // all six GlobalEuclideanReprError<Camera, Distortion> instantiations (optimization_be.cpp:186-231)
+  const double dists[3][4]={{-0.28340811,0.07395907,0.00019359,1.76187114e-05},{-0.013,0.02,-0.012,0.002},{0.93,0,0,0}};
   double lm[3];
-  for(;;){ lm[0]=1+3*rnd(); lm[1]=2+3*rnd(); lm[2]=3+3*rnd(); double r[2],Jp[12],Jl[6]; if(reproj(pose,extr,intr,dist,lm,300,200,2.0,r,Jp,Jl,true)) { if (fabs(r[0])<200&&fabs(r[1])<200) break;} }
-  double r[2],Jp[12],Jl[6]; reproj(pose,extr,intr,dist,lm,300,200,2.0,r,Jp,Jl,true);
+  for(int cam=0;cam<2;cam++) for(int dm=0;dm<3;dm++){
+    CamModel cm{cam,dm,cam?1.2:0.0};
+    memcpy(dist,dists[dm],32);
+    for(;;){ lm[0]=1+3*rnd(); lm[1]=2+3*rnd(); lm[2]=3+3*rnd(); double r[2],Jp[12],Jl[6]; if(reproj(pose,extr,intr,dist,cm,lm,300,200,2.0,r,Jp,Jl,true)) { if (fabs(r[0])<200&&fabs(r[1])<200) break;} }
+    double r[2],Jp[12],Jl[6]; reproj(pose,extr,intr,dist,cm,lm,300,200,2.0,r,Jp,Jl,true);
+    double eps=1e-6, maxe=0;
+    for(int c=0;c<6;c++){ double d[6]={0,0,0,0,0,0}; d[c]=eps; double pp[7],pm[7]; pose_plus(pose,d,pp); d[c]=-eps; pose_plus(pose,d,pm);
+      double rp[2],rm[2]; reproj(pp,extr,intr,dist,cm,lm,300,200,2.0,rp,0,0,false); reproj(pm,extr,intr,dist,cm,lm,300,200,2.0,rm,0,0,false);
+      for(int a=0;a<2;a++){ double fd=(rp[a]-rm[a])/(2*eps); maxe=fmax(maxe,fabs(fd-Jp[6*a+c])); } }
+    for(int c=0;c<3;c++){ double lp[3],lmn[3]; memcpy(lp,lm,24); memcpy(lmn,lm,24); lp[c]+=eps; lmn[c]-=eps; double rp[2],rm[2];
+      reproj(pose,extr,intr,dist,cm,lp,300,200,2.0,rp,0,0,false); reproj(pose,extr,intr,dist,cm,lmn,300,200,2.0,rm,0,0,false);
+      for(int a=0;a<2;a++){ double fd=(rp[a]-rm[a])/(2*eps); maxe=fmax(maxe,fabs(fd-Jl[3*a+c])); } }
+    printf("reproj cam %d dist %d r=(%g,%g) max jac err %g (|J| ~ %g)\n", cam,dm,r[0],r[1],maxe,fabs(Jp[0]));
+  }
   double eps=1e-6, maxe=0;
-  for(int c=0;c<6;c++){ double d[6]={0,0,0,0,0,0}; d[c]=eps; double pp[7],pm[7]; pose_plus(pose,d,pp); d[c]=-eps; pose_plus(pose,d,pm);
-    double rp[2],rm[2]; reproj(pp,extr,intr,dist,lm,300,200,2.0,rp,0,0,false); reproj(pm,extr,intr,dist,lm,300,200,2.0,rm,0,0,false);
-    for(int a=0;a<2;a++){ double fd=(rp[a]-rm[a])/(2*eps); maxe=fmax(maxe,fabs(fd-Jp[6*a+c])); } }
-  for(int c=0;c<3;c++){ double lp[3],lmn[3]; memcpy(lp,lm,24); memcpy(lmn,lm,24); lp[c]+=eps; lmn[c]-=eps; double rp[2],rm[2];
-    reproj(pose,extr,intr,dist,lp,300,200,2.0,rp,0,0,false); reproj(pose,extr,intr,dist,lmn,300,200,2.0,rm,0,0,false);
-    for(int a=0;a<2;a++){ double fd=(rp[a]-rm[a])/(2*eps); maxe=fmax(maxe,fabs(fd-Jl[3*a+c])); } }
-  printf("reproj r=(%g,%g) max jac err %g (|J| ~ %g)\n", r[0],r[1],maxe,fabs(Jp[0]));
   // between
   double pose2[7]={-0.3,0.1,0.2,0.8,2,1,4}; {double n=sqrt(pose2[0]*pose2[0]+pose2[1]*pose2[1]+pose2[2]*pose2[2]+pose2[3]*pose2[3]); for(int i=0;i<4;i++)pose2[i]/=n;}
   double qm[4]={0.05,0.1,-0.1,0.98}; {double n=sqrt(qm[0]*qm[0]+qm[1]*qm[1]+qm[2]*qm[2]+qm[3]*qm[3]); for(int i=0;i<4;i++)qm[i]/=n;}

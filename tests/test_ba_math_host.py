@@ -12,5 +12,6 @@ def test_device_math_jacobians_vs_finite_differences(tmp_path):
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "ba_math_fd.cpp")])
     out = subprocess.check_output([exe], text=True)
     errs = [float(x) for x in re.findall(r"max jac err ([0-9.eE+-]+)", out)]
-    assert len(errs) == 3, out
+    assert len(errs) == 8, out          # 6 camera/distortion instantiations of the reprojection error + between + IMU
+    assert out.count("reproj cam") == 6
     assert max(errs) < 1e-6, out

@@ -237,3 +237,25 @@ def test_gba_c3_matches_cpu_port(ctx):
     ref = bp.solve(p, 4, visual_only=False)
     well = (got["lm_owner"] >= 0) & (np.abs(ref["lm"]).max(1) < 100.0)
     _port_compare(got, ref, p, lm_mask=well, cost_rtol=1e-5)
+
+
+@pytest.mark.parametrize("cam_model,dist_model", [(0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2)])
+def test_all_six_reprojection_instantiations_match_oracle(ctx, cam_model, dist_model):
+    """GlobalEuclideanReprError<{Pinhole, UnifiedProjection}, {RadTan, Equidistant, Fisheye}> (optimization_be.cpp:186-231):
+    analytic CUDA Jacobians vs the autograd oracle, visual-inertial solve on the same map seen through each model"""
+    p = synth_map.with_camera_model(synth_map.make_config("tiny"), cam_model, dist_model, xi=0.9 if cam_model else 0.0, seed=7)
+    got = O.solve(ctx, p, 5, visual_only=False)
+    ref = bo.solve(bo.Problem(p, visual_only=False, loop_loss=1.0), 5)
+    _compare(got, ref, p)
+    assert got["final_cost"] < got["initial_cost"]
+
+
+def test_unknown_camera_model_is_reported(ctx):
+    import covins_b200
+    p = synth_map.with_camera_model(synth_map.make_config("tiny"), 0, 0)
+    p["dist_model"] = np.array([5], np.int32)
+    with pytest.raises(covins_b200.CvbError, match="Unknown distortion type"):
+        O.solve(ctx, p, 1)
+    p["dist_model"] = np.array([0], np.int32); p["cam_model"] = np.array([3], np.int32)
+    with pytest.raises(covins_b200.CvbError, match="Unknown projection type"):
+        O.solve(ctx, p, 1)

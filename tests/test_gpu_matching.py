@@ -224,7 +224,41 @@ def test_descriptor_database_matches_batch_call_and_oracle(ctx):
     db._cap = 3
     nm2, *rest = db.match_hamming(desc[0], 64.0, 0.95)
     assert int(nm2.sum()) == len(rest[0]) > 3
+    # keyframes leave the map (culling, keyframe_be.cpp:413-440): cvb_db_remove cuts the segment out, later indices drop by one
+    keep = list(range(len(lens)))
+    for victim in (3, 0, len(lens) - 3, 1):          # middle, first, (then) last-but-one, the empty one
+        db.remove(victim)
+        keep.pop(victim)
+        t2 = np.concatenate([t[seg[i]:seg[i + 1]] for i in keep]); seg2 = np.concatenate([[0], np.cumsum([lens[i] for i in keep])]).astype(np.int32)
+        assert db.size() == (len(keep), int(seg2[-1]))
+        nm3, k3, q3, t3, d3 = db.match_hamming(desc[0], 40.0, 0.8)
+        mt, md, rn = M.match_candidates_hamming(ctx, desc[0], t2, seg2, 40.0, 0.8)
+        kf, qq = np.nonzero(mt >= 0)
+        assert np.array_equal(nm3, rn) and np.array_equal(k3, kf) and np.array_equal(q3, qq) and np.array_equal(t3, mt[kf, qq])
+    import covins_b200
+    with pytest.raises(covins_b200.CvbError):
+        db.remove(len(keep))
     db.close()
+
+
+def test_l2_host_path_single_long_segment_chunked(ctx):
+    """cvb_knn_l2_batch on ONE long segment takes the chunked tensor-core path; its chunk tables must not
+    alias the quantised descriptors staged by the host wrapper.  ~200k rows, 700 queries, vs the oracle on the first rows
+    and vs the scalar kernel on all of them."""
+    import os
+    s, _ = synth.sift_keyframes(seed=41, n_kf=700, n_feat=300)
+    t = s.reshape(-1, 128)                       # 210k rows, one segment
+    q = s[3][:300].copy(); q = np.concatenate([q, s[10][:300], s[500][:100]])
+    idx, dist = M.knn_match_l2(ctx, q, t, None, k=2)
+    os.environ["COVINS_B200_MATCH_KERNEL"] = "popc"
+    try:
+        idx_s, dist_s = M.knn_match_l2(ctx, q, t, None, k=2)
+    finally:
+        os.environ.pop("COVINS_B200_MATCH_KERNEL", None)
+    assert np.array_equal(idx, idx_s) and np.array_equal(dist, dist_s)
+    ri, rd = ora.knn_l2(q[:8], t, k=2)           # rows 0..2 of q and t were the ones the aliasing bug overwrote
+    assert np.array_equal(idx[0][:8], ri) and np.array_equal(dist[0][:8], rd)
+    assert idx[0][0, 0] == 3 * 300 and dist[0][0, 0] == 0.0
 
 
 @pytest.mark.parametrize("metric", ["hamming", "l2"])

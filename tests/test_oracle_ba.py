@@ -106,3 +106,17 @@ def test_product_pgo_edge_builder_equals_oracle():
         assert np.allclose(got["sqrt_info"], ref["sqrt_info"], rtol=1e-14, atol=0)
         # small quaternion components come out of sqrt(1 + R00 - R11 - R22): rounding of R is amplified to ~1e-12 there
         assert np.allclose(got["q"], ref["q"], rtol=0, atol=5e-11) and np.allclose(got["t"], ref["t"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("cam_model,dist_model", [(0, 1), (0, 2), (1, 0), (1, 1), (1, 2)])
+def test_oracle_camera_models_reduce_cost_to_noise_level(cam_model, dist_model):
+    """the other five GlobalEuclideanReprError instantiations (optimization_be.cpp:186-231) in the autograd oracle: a map
+    observed through the model is solved back to the noise level (inlier residuals ~ 1 px / sigma)"""
+    from covins_b200 import synth_map
+    p = synth_map.with_camera_model(synth_map.make_config("tiny"), cam_model, dist_model, xi=0.9 if cam_model else 0.0, seed=7)
+    pr = bo.Problem(p, visual_only=True, loop_loss=1.0)
+    r = bo.solve(pr, 6)
+    assert r["cost"][-1] < r["cost"][0]
+    norms = bo.corrected_reproj_norms(pr, r["pose"], r["sb"], r["lm"])
+    inl = ~p["obs_is_outlier"][pr.obs_sel]
+    assert np.median(norms[inl]) < 0.5
