@@ -129,6 +129,8 @@ struct Engine {
   int* pflag_raw = nullptr;
   cvb_chol::DistView dv;
   double** d_peer_S = nullptr;
+  std::vector<uint8_t> h_prefill;               // tile mask of S before fill (the distributed plan is rebuilt from it)
+  std::vector<int> h_owner;                     // tile column → owning rank
   std::vector<int> h_off_pose, h_off_sb;
   cvb_chol::TilePlan plan;
   DevArr<double> extr_kf, intr_kf, dist_kf, xi_kf;
@@ -1359,7 +1361,11 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     }
   }
   std::vector<uint8_t> pre_fill(tmask);
-  E.plan.build(nt, tmask, E.world > 1 ? &h_owner : nullptr, E.rank);
+  // the replicated plan (every rank applies every update); cvb_ba_enable_p2p swaps in the owner-filtered one — same tile
+  // structure, same packed layout — once peer access is known to work on every rank
+  E.plan.build(nt, tmask);
+  E.h_prefill = pre_fill;
+  E.h_owner = h_owner;
   E.n_tiles = (size_t)E.plan.n_tiles_L;
   std::vector<int> h_xt_all, h_xt_own;
   for (int j = 0; j < nt; j++)
@@ -2158,6 +2164,13 @@ int cvb_ba_enable_p2p(cvb_ba* h) {
   ENG_CUDA(cudaMalloc(&E.d_peer_S, sizeof(double*) * 16));
   ENG_CUDA(cudaMemcpyAsync(E.d_peer_S, dv.peer_S, sizeof(double*) * 16, cudaMemcpyHostToDevice, E.st));
   ENG_CUDA(cudaStreamSynchronize(E.st));
+  // distributed plan: same structure, pair lists restricted to the tile columns this rank owns
+  {
+    const std::vector<int> groups = E.plan.h_col_group;
+    E.plan.build(E.plan.nt, E.h_prefill, &E.h_owner, E.rank);
+    E.plan.h_col_group = groups;
+    if ((rc = E.plan.upload(E.ctx, E.st))) return rc;
+  }
   E.dv = dv;
   E.p2p = true;
   return CVB_OK;

@@ -225,6 +225,7 @@ struct Flat {
 
 // parameters the reference reads from covins_params (config/config_backend.yaml)
 struct OptParams {
+  double th_outlier_align = 1.3;            // opt.th_outlier_align (config_backend.yaml)
   bool gba_fix_poses_loaded_maps = false;       // opt.gba_fix_poses_loaded_maps (optimization_be.cpp:338)
   bool gba_use_map_loop_constraints = true;     // :539
   double th_gba_outlier_global = 0.92;          // :277
@@ -562,6 +563,71 @@ void PoseGraphOptimization(Context& ctx, MapPtr map, PoseMap corrected_poses, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Optimization::OptimizeRelativePose — optimization_be.hpp:42-44.  Same signature meaning: matches1[i] (indexed by kf1's
+// keypoints) holds the landmark of kf2 matched to kf1's landmark i; T12 is refined in place; rejected entries of matches1
+// are nulled; returns the inlier count, 0 when fewer than 12 remain.  Reference quirks kept on purpose:
+//   * TcwB is built with kf1's extrinsics (:643);
+//   * the purge nulls matches1[r] with r the RESIDUAL index, not vIndex[r] (:815).
+// ---------------------------------------------------------------------------------------------------------------
+template <class KFPtr, class LandmarkVector, class Transform4>
+inline int OptimizeRelativePose(Context& ctx, const KFPtr& kf1, const KFPtr& kf2, LandmarkVector& matches1, Transform4& T12,
+                                double /*th2, unused by the reference*/, const OptParams& P) {
+  using KF = typename std::decay<decltype(*kf1)>::type;
+  cvb_relpose_problem prob{};
+  detail::transform_to_pose7(T12, prob.T12);                                                          // :629-638
+  // TcwA = (T_ws1 * T_sc1)^-1, TcwB = (T_ws2 * T_sc1)^-1  (kf1's extrinsics for both, :642-643)
+  auto mul4 = [](const Transform4& A, const Transform4& B) {
+    Transform4 C = Transform4::Identity();
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { double s = 0; for (int k = 0; k < 4; k++) s += A(r, k) * B(k, c); C(r, c) = s; }
+    return C;
+  };
+  auto inv_rigid = [](const Transform4& T) {
+    Transform4 I = Transform4::Identity();
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) I(r, c) = T(c, r);
+    for (int r = 0; r < 3; r++) I(r, 3) = -(I(r, 0) * T(0, 3) + I(r, 1) * T(1, 3) + I(r, 2) * T(2, 3));
+    return I;
+  };
+  const Transform4 TcwA = inv_rigid(mul4(kf1->GetPoseTws(), kf1->GetStateExtrinsics()));
+  const Transform4 TcwB = inv_rigid(mul4(kf2->GetPoseTws(), kf1->GetStateExtrinsics()));
+  const auto lmsA = kf1->GetLandmarks();
+  std::vector<double> pA, pB, sA, sB;
+  std::vector<float> kA, kB;
+  const int N = (int)matches1.size();
+  for (int i = 0; i < N; i++) {                                                                        // :656-780
+    if (!matches1[i]) continue;
+    auto pMPA = lmsA[i];
+    auto pMPB = matches1[i];
+    const int iB = pMPB->GetFeatureIndex(kf2);
+    if (!pMPA || pMPA->IsInvalid() || pMPB->IsInvalid() || iB < 0) continue;
+    const auto wa = pMPA->GetWorldPos(), wb = pMPB->GetWorldPos();
+    for (int r = 0; r < 3; r++) {
+      pA.push_back(TcwA(r, 0) * wa[0] + TcwA(r, 1) * wa[1] + TcwA(r, 2) * wa[2] + TcwA(r, 3));
+      pB.push_back(TcwB(r, 0) * wb[0] + TcwB(r, 1) * wb[1] + TcwB(r, 2) * wb[2] + TcwB(r, 3));
+    }
+    kA.push_back(kf1->keypoints_distorted_[i][0]); kA.push_back(kf1->keypoints_distorted_[i][1]);
+    kB.push_back(kf2->keypoints_distorted_[iB][0]); kB.push_back(kf2->keypoints_distorted_[iB][1]);
+    sA.push_back((kf1->keypoints_aors_[i][1] + 1) * 2.0); sB.push_back((kf2->keypoints_aors_[iB][1] + 1) * 2.0);
+  }
+  prob.n = (int32_t)sA.size();
+  prob.pA_c = pA.data(); prob.pB_c = pB.data(); prob.kpA = kA.data(); prob.kpB = kB.data(); prob.sigmaA = sA.data(); prob.sigmaB = sB.data();
+  if (!Adapter<KF>::camera(*kf1, prob.intrA, prob.distA) || !Adapter<KF>::camera(*kf2, prob.intrB, prob.distB)) {
+    std::printf("FATAL: Unknown projection type.\n");                                                // :705-707
+    std::exit(-1);
+  }
+  Adapter<KF>::camera_model(*kf1, &prob.cam_model_A, &prob.dist_model_A, &prob.xiA);
+  Adapter<KF>::camera_model(*kf2, &prob.cam_model_B, &prob.dist_model_B, &prob.xiB);
+  double out[7];
+  std::vector<uint8_t> removed(prob.n > 0 ? prob.n : 1, 0);
+  int32_t n_inl = 0;
+  ctx.check(cvb_optimize_relative_pose(ctx.get(), &prob, P.th_outlier_align, out, removed.data(), &n_inl, nullptr), "cvb_optimize_relative_pose");
+  for (int r = 0; r < prob.n; r++)
+    if (removed[r]) matches1[r] = nullptr;                                                            // matches1[i] with i = residual index (:815)
+  if (n_inl == 0) return 0;                                                                            // :821-823, T12 untouched
+  T12 = detail::pose7_to_transform<Transform4>(out);                                                  // :829
+  return n_inl;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Matching blocks
 // ---------------------------------------------------------------------------------------------------------------
 struct Match {   // covins::Match (include/covins/matcher/MatchingAlgorithm.h:56-70)
@@ -628,6 +694,204 @@ inline std::vector<Matches> LandmarkMatchCandidates(Context& ctx, const uint8_t*
   return out;
 }
 
+// The SIFT branch of the same candidate loop (placerec_gen_be.cpp:86-87,99: FlannBasedMatcher::knnMatch on CV_32F 128-d
+// rows; here the exact brute-force 2-NN) + the same filter with the SIFT thresholds (img_match_thres /
+// ratio_thres of the yaml).  descriptors row-major [n][128] float, integer-valued 0..255 as cv::xfeatures2d::SIFT emits.
+inline std::vector<Matches> MatchCandidatesSIFT(Context& ctx, const float* query, int n_query, const std::vector<const float*>& cand_desc,
+                                                const std::vector<int>& cand_rows, const std::vector<bool>& same_client,
+                                                const OptParams& P, std::vector<bool>* discarded) {
+  const int n_seg = (int)cand_desc.size();
+  std::vector<int32_t> seg(n_seg + 1, 0);
+  for (int s = 0; s < n_seg; s++) seg[s + 1] = seg[s] + cand_rows[s];
+  std::vector<float> train((size_t)seg[n_seg] * 128);
+  for (int s = 0; s < n_seg; s++) std::copy(cand_desc[s], cand_desc[s] + (size_t)cand_rows[s] * 128, train.begin() + (size_t)seg[s] * 128);
+  std::vector<int32_t> mt((size_t)n_seg * n_query), nm(n_seg);
+  std::vector<float> md((size_t)n_seg * n_query);
+  ctx.check(cvb_match_l2_batch(ctx.get(), query, n_query, train.data(), seg.data(), n_seg, 128, P.img_match_thres, P.ratio_thres, mt.data(),
+                               md.data(), nm.data()),
+            "cvb_match_l2_batch");
+  std::vector<Matches> out(n_seg);
+  if (discarded) discarded->assign(n_seg, false);
+  for (int s = 0; s < n_seg; s++) {
+    for (int q = 0; q < n_query; q++) {
+      const int32_t t = mt[(size_t)s * n_query + q];
+      if (t >= 0) out[s].push_back(Match{(size_t)q, (size_t)t, md[(size_t)s * n_query + q]});
+    }
+    const int nmatches = (int)out[s].size();
+    if (discarded) {
+      if (same_client[s] && nmatches < P.matches_thres) (*discarded)[s] = true;
+      else if (nmatches < P.matches_thres_merge) (*discarded)[s] = true;
+    }
+  }
+  return out;
+}
+
+// estd2::DenseMatcher-shaped adaptor (include/covins/dense_matcher/DenseMatcher.hpp:49-76): the same constructor
+// arguments and the same templated match(algorithm) call, consuming the reference's MatchingAlgorithm policy interface
+// (include/covins/matcher/MatchingAlgorithm.h:83-152: doSetup / sizeA / sizeB / skipA / skipB / distanceThreshold /
+// reserveMatches / setBestMatch).  The one thing a GPU cannot take through that interface is the virtual distance(a, b)
+// call per pair, so the algorithm additionally exposes its descriptor rows:
+//     const unsigned char* descriptorA(size_t i) const;   // kfPtrA_->GetDescriptor(i)  (keyframe_base.cpp:254-256)
+//     const unsigned char* descriptorB(size_t i) const;
+// (two one-line accessors on LandmarkMatchingAlgorithm, shown in INTEGRATION.md); distance() itself — 256-bit Hamming,
+// FLT_MAX at or above the threshold, LandmarkMatchingAlgorithm.h:103-114 — is what the kernel evaluates.
+// Results arrive through setBestMatch in ascending B order, exactly as DenseMatcher::matchBody emits them
+// (implementation/DenseMatcher.hpp:93-121); ties resolve as with numMatcherThreads = 1.
+class DenseMatcher {
+ public:
+  DenseMatcher(Context& ctx, unsigned char /*numMatcherThreads*/ = 8, unsigned char numBest = 4, bool useDistanceRatioThreshold = false)
+      : ctx_(ctx), num_best_(numBest), use_ratio_(useDistanceRatioThreshold) {}
+  template <class MATCHING_ALGORITHM_T>
+  void match(MATCHING_ALGORITHM_T& algo) {
+    if (use_ratio_) { std::printf("FATAL: DenseMatcher ratio mode is not used by COVINS (placerec_be.cpp:87) and not implemented\n"); std::exit(-1); }
+    algo.doSetup();
+    const int nA = (int)algo.sizeA(), nB = (int)algo.sizeB();
+    std::vector<uint8_t> A((size_t)nA * 32), B((size_t)nB * 32), sA(nA), sB(nB);
+    for (int i = 0; i < nA; i++) { sA[i] = algo.skipA(i) ? 1 : 0; std::copy(algo.descriptorA(i), algo.descriptorA(i) + 32, A.begin() + (size_t)i * 32); }
+    for (int i = 0; i < nB; i++) { sB[i] = algo.skipB(i) ? 1 : 0; std::copy(algo.descriptorB(i), algo.descriptorB(i) + 32, B.begin() + (size_t)i * 32); }
+    const int32_t seg[2] = {0, nB};
+    std::vector<int32_t> oA(nB > 0 ? nB : 1), oB(nB > 0 ? nB : 1);
+    std::vector<float> oD(nB > 0 ? nB : 1);
+    int32_t n = 0;
+    ctx_.check(cvb_landmark_match_batch(ctx_.get(), A.data(), sA.data(), nA, B.data(), sB.data(), seg, 1, algo.distanceThreshold(), num_best_,
+                                        oA.data(), oB.data(), oD.data(), &n),
+               "cvb_landmark_match_batch");
+    algo.reserveMatches((size_t)n);
+    for (int m = 0; m < n; m++) algo.setBestMatch((size_t)oA[m], (size_t)oB[m], (double)oD[m]);
+  }
+
+ private:
+  Context& ctx_;
+  int num_best_;
+  bool use_ratio_;
+};
+
+// What FeatureMatcher::SearchBySE3 reads of a keyframe, with owning storage (cvb_kf_view points into it).
+struct KfViewStorage {
+  std::vector<float> kp, octave;
+  std::vector<uint8_t> desc, lm_valid, lm_desc;
+  std::vector<double> lm_pos, lm_maxdist;
+  std::vector<int32_t> grid_ptr, grid_idx;
+  cvb_kf_view v{};
+  // KeyframeBase::AssignFeaturesToGrid (keyframe_base.cpp:122-143) on the flat arrays
+  void assign_grid(double img_w, double img_h) {
+    const int n = (int)(kp.size() / 2);
+    v.grid_w_inv = 64.0 / img_w; v.grid_h_inv = 48.0 / img_h;
+    std::vector<int> cell(n, -1);
+    grid_ptr.assign(64 * 48 + 1, 0);
+    for (int i = 0; i < n; i++) {
+      const long px = std::lround((double)kp[2 * (size_t)i] * v.grid_w_inv), py = std::lround((double)kp[2 * (size_t)i + 1] * v.grid_h_inv);
+      if (px >= 0 && px < 64 && py >= 0 && py < 48) { cell[i] = (int)(px * 48 + py); grid_ptr[cell[i] + 1]++; }   // out-of-grid cells: UB in the reference
+    }
+    for (int c = 0; c < 64 * 48; c++) grid_ptr[c + 1] += grid_ptr[c];
+    grid_idx.assign(grid_ptr.back(), 0);
+    std::vector<int32_t> fill(grid_ptr.begin(), grid_ptr.end() - 1);
+    for (int i = 0; i < n; i++) if (cell[i] >= 0) grid_idx[fill[cell[i]]++] = i;
+  }
+  const cvb_kf_view* view() {
+    v.n = (int32_t)(kp.size() / 2);
+    v.kp = kp.data(); v.octave = octave.data(); v.desc = desc.data(); v.lm_valid = lm_valid.data(); v.lm_pos = lm_pos.data();
+    v.lm_maxdist = lm_maxdist.data(); v.lm_desc = lm_desc.data(); v.grid_ptr = grid_ptr.data(); v.grid_idx = grid_idx.data();
+    return &v;
+  }
+};
+
+// FeatureMatcher::SearchBySE3(pKF1, pKF2, matches12, T12, th) (feature_matcher_be.cpp:293-498) for a batch of candidates:
+// matches12[p] is updated in place exactly as the reference does (:485-496: matches12[i] = mapPoints2[idx2]); returns the
+// number of matches found per candidate.  KF is touched through the member names the reference class has
+// (keypoints_distorted_, keypoints_aors_, GetDescriptor(i), GetLandmarks(), calibration via Adapter<KF>::K, GetPoseTcw(),
+// img_dim_*_); Landmark through IsInvalid / GetWorldPos / GetMaxDistanceInvariance / GetDescriptorPtr / GetFeatureIndex.
+template <class KFPtr, class LandmarkVector, class Transform4>
+inline std::vector<int> SearchBySE3(Context& ctx, const KFPtr& kf1, const std::vector<KFPtr>& kf2, std::vector<LandmarkVector>& matches12,
+                                    const std::vector<Transform4>& T12, const std::vector<Transform4>& T21, double th,
+                                    int desc_matching_th_low, int num_octaves, double scale_factor) {
+  auto flatten = [](const KFPtr& kf, KfViewStorage& S) {
+    const size_t n = kf->keypoints_distorted_.size();
+    S.kp.resize(2 * n); S.octave.resize(n); S.desc.resize(32 * n); S.lm_valid.assign(n, 0); S.lm_pos.assign(3 * n, 0.0);
+    S.lm_maxdist.assign(n, 1.0); S.lm_desc.assign(32 * n, 0);
+    const auto lms = kf->GetLandmarks();
+    for (size_t i = 0; i < n; i++) {
+      S.kp[2 * i] = kf->keypoints_distorted_[i][0]; S.kp[2 * i + 1] = kf->keypoints_distorted_[i][1];
+      S.octave[i] = kf->keypoints_aors_[i][1];
+      std::copy(kf->GetDescriptor(i), kf->GetDescriptor(i) + 32, S.desc.begin() + 32 * i);
+      if (lms[i] && !lms[i]->IsInvalid()) {
+        S.lm_valid[i] = 1;
+        const auto p = lms[i]->GetWorldPos();
+        for (int c = 0; c < 3; c++) S.lm_pos[3 * i + c] = p[c];
+        S.lm_maxdist[i] = lms[i]->GetMaxDistanceInvariance();
+        std::copy(lms[i]->GetDescriptorPtr(), lms[i]->GetDescriptorPtr() + 32, S.lm_desc.begin() + 32 * i);
+      }
+    }
+    const auto Tcw = kf->GetPoseTcw();
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) S.v.Tcw[4 * r + c] = Tcw(r, c);
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) S.v.K[3 * r + c] = kf->calibration_K(r, c);
+    S.v.img[0] = kf->img_dim_x_min_; S.v.img[1] = kf->img_dim_x_max_; S.v.img[2] = kf->img_dim_y_min_; S.v.img[3] = kf->img_dim_y_max_;
+    S.assign_grid(kf->image_width(), kf->image_height());
+  };
+  const int n_pairs = (int)kf2.size();
+  KfViewStorage S1;
+  flatten(kf1, S1);
+  std::vector<KfViewStorage> S2(n_pairs);
+  std::vector<cvb_kf_view> v2(n_pairs);
+  const size_t n1 = kf1->keypoints_distorted_.size();
+  std::vector<uint8_t> a1((size_t)n_pairs * n1, 0), a2;
+  std::vector<double> t12((size_t)n_pairs * 16), t21((size_t)n_pairs * 16);
+  for (int p = 0; p < n_pairs; p++) {
+    flatten(kf2[p], S2[p]);
+    v2[p] = *S2[p].view();
+    const size_t n2 = kf2[p]->keypoints_distorted_.size(), base = a2.size();
+    a2.resize(base + n2, 0);
+    for (size_t i = 0; i < n1; i++)                                                                // :312-324
+      if (matches12[p][i]) {
+        a1[(size_t)p * n1 + i] = 1;
+        const int idx2 = matches12[p][i]->GetFeatureIndex(kf2[p]);
+        if (idx2 >= 0 && idx2 < (int)n2) a2[base + idx2] = 1;
+      }
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { t12[(size_t)p * 16 + 4 * r + c] = T12[p](r, c); t21[(size_t)p * 16 + 4 * r + c] = T21[p](r, c); }
+  }
+  cvb_search_params prm{th, desc_matching_th_low, num_octaves, scale_factor};
+  std::vector<int32_t> m12((size_t)n_pairs * n1 + 1), nf(n_pairs + 1);
+  ctx.check(cvb_search_by_se3_batch(ctx.get(), S1.view(), v2.data(), n_pairs, t12.data(), t21.data(), a1.data(), a2.data(), &prm, m12.data(),
+                                    nf.data(), nullptr, nullptr),
+            "cvb_search_by_se3_batch");
+  std::vector<int> found(n_pairs);
+  for (int p = 0; p < n_pairs; p++) {
+    const auto lms2 = kf2[p]->GetLandmarks();
+    for (size_t i = 0; i < n1; i++)
+      if (m12[(size_t)p * n1 + i] >= 0) matches12[p][i] = lms2[m12[(size_t)p * n1 + i]];            // :491
+    found[p] = nf[p];
+  }
+  return found;
+}
+
+// RANSAC hypothesis scoring (the countWithinDistance / selectWithinDistance inner loops of opengv::sac::Ransac for
+// Se3Solver::projectiveAlignment, Se3Solver.cpp:59-110, and RelNonCentralPosSolver::computePose, :343-377) — all
+// hypotheses of one RANSAC run in one launch; sampling and the minimal solvers (GP3P / 5-pt / 17-pt) stay with opengv.
+// models: n_hyp x 12 (3x4 row-major).  Returns the inlier count per hypothesis; inlier (optional) n_hyp x n flags.
+inline std::vector<int> ScoreAbsolutePoseHypotheses(Context& ctx, const std::vector<double>& models, const std::vector<double>& points,
+                                                    const std::vector<double>& bearings, const std::vector<double>& sigma_angles,
+                                                    const double cam_offset[3], const double cam_rotation[9], double threshold,
+                                                    std::vector<uint8_t>* inlier = nullptr) {
+  const int n_hyp = (int)(models.size() / 12), n = (int)sigma_angles.size();
+  std::vector<int32_t> cnt(n_hyp > 0 ? n_hyp : 1);
+  if (inlier) inlier->assign((size_t)n_hyp * n, 0);
+  ctx.check(cvb_score_absolute_pose_batch(ctx.get(), models.data(), n_hyp, points.data(), bearings.data(), sigma_angles.data(), n, cam_offset,
+                                          cam_rotation, threshold, nullptr, inlier ? inlier->data() : nullptr, cnt.data()),
+            "cvb_score_absolute_pose_batch");
+  return std::vector<int>(cnt.begin(), cnt.begin() + n_hyp);
+}
+inline std::vector<int> ScoreRelativePoseHypotheses(Context& ctx, const std::vector<double>& models, const std::vector<double>& bearings1,
+                                                    const std::vector<double>& bearings2, const std::vector<double>& sigma1,
+                                                    const std::vector<double>& sigma2, double threshold, std::vector<uint8_t>* inlier = nullptr) {
+  const int n_hyp = (int)(models.size() / 12), n = (int)sigma1.size();
+  std::vector<int32_t> cnt(n_hyp > 0 ? n_hyp : 1);
+  if (inlier) inlier->assign((size_t)n_hyp * n, 0);
+  ctx.check(cvb_score_relative_pose_batch(ctx.get(), models.data(), n_hyp, bearings1.data(), bearings2.data(), sigma1.data(), sigma2.data(), n,
+                                          threshold, nullptr, inlier ? inlier->data() : nullptr, cnt.data()),
+            "cvb_score_relative_pose_batch");
+  return std::vector<int>(cnt.begin(), cnt.begin() + n_hyp);
+}
+
 // Resident-map descriptor database (cvb_db_*): the ORB descriptors of the map's keyframes live in HBM; the candidate
 // loop of PlaceRecognitionG::ComputeSE3 (placerec_gen_be.cpp:60-135) becomes one call per query keyframe.  The database
 // index of a keyframe is its insertion order; keep it next to the keyframe (e.g. std::map<idpair, int>).
@@ -644,6 +908,11 @@ class DescriptorDatabase {
     return n_kf_++;
   }
   int size() const { return n_kf_; }
+  // the keyframe leaves the map (culling, keyframe_be.cpp:413-440 / Map::EraseKeyframe): later indices drop by one
+  void RemoveKeyframe(int db_index) {
+    ctx_.check(cvb_db_remove(ctx_.get(), db_, db_index), "cvb_db_remove");
+    n_kf_--;
+  }
   // knnMatch(k=2) + distance/ratio filter of the query keyframe against EVERY keyframe of the database:
   // result[db index] == the reference's img_matches for that candidate (accepted queries ascending, :102-114)
   std::vector<Matches> MatchAll(const uint8_t* query, int n_query, const OptParams& P) {

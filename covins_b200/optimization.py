@@ -206,8 +206,15 @@ def torch_allreduce():
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
 
+    import os
+    debug = os.environ.get("COVINS_B200_AR_DEBUG")
+    state = {"n": 0}
+
     def fn(user, ptr, count, stream):
         try:
+            if debug:
+                state["n"] += 1
+                print(f"[allreduce rank {dist.get_rank()}] #{state['n']} count={count}", flush=True)
             ext = torch.cuda.ExternalStream(stream)
             with torch.cuda.stream(ext):
                 t = torch.as_tensor(_Ptr(ptr, count), device="cuda")
@@ -349,3 +356,36 @@ def dense_cholesky_solve(ctx: Context, A, b):
     x = np.zeros_like(b); ms = C.c_double()
     ctx.check(lib().cvb_dense_cholesky_solve(ctx.handle, A.ctypes.data, len(b), b.ctypes.data, x.ctypes.data, C.byref(ms)))
     return x, ms.value
+
+
+class RelPoseProblem(C.Structure):
+    _fields_ = [("n", C.c_int32)] + [(k, c_vp) for k in ("pA_c", "pB_c", "kpA", "kpB", "sigmaA", "sigmaB")] + \
+               [("intrA", C.c_double * 4), ("distA", C.c_double * 4), ("intrB", C.c_double * 4), ("distB", C.c_double * 4),
+                ("cam_model_A", C.c_int32), ("dist_model_A", C.c_int32), ("cam_model_B", C.c_int32), ("dist_model_B", C.c_int32),
+                ("xiA", C.c_double), ("xiB", C.c_double), ("T12", C.c_double * 7)]
+
+
+def optimize_relative_pose(ctx: Context, T12, pA_c, pB_c, kpA, kpB, sigmaA, sigmaB, camA: dict, camB: dict, th_outlier_align=1.3):
+    """Optimization::OptimizeRelativePose (optimization_be.cpp:620-831) on flattened residual pairs: → dict(T12 [7], removed [n]
+    bool (by residual index), n_inliers (the reference's return value), iterations (2), cost (history of both solves)).
+    cam*: dict(intr[4], dist[4], cam_model=0, dist_model=0, xi=0)."""
+    a = [np.ascontiguousarray(pA_c, np.float64).reshape(-1, 3), np.ascontiguousarray(pB_c, np.float64).reshape(-1, 3),
+         np.ascontiguousarray(kpA, np.float32).reshape(-1, 2), np.ascontiguousarray(kpB, np.float32).reshape(-1, 2),
+         np.ascontiguousarray(sigmaA, np.float64), np.ascontiguousarray(sigmaB, np.float64)]
+    n = len(a[0])
+    s = RelPoseProblem()
+    s.n = n
+    for k, v in zip(("pA_c", "pB_c", "kpA", "kpB", "sigmaA", "sigmaB"), a):
+        setattr(s, k, v.ctypes.data)
+    for tag, cam in (("A", camA), ("B", camB)):
+        getattr(s, "intr" + tag)[:] = [float(x) for x in np.asarray(cam["intr"]).reshape(4)]
+        getattr(s, "dist" + tag)[:] = [float(x) for x in np.asarray(cam["dist"]).reshape(4)]
+        setattr(s, "cam_model_" + tag, int(cam.get("cam_model", 0))); setattr(s, "dist_model_" + tag, int(cam.get("dist_model", 0)))
+        setattr(s, "xi" + tag, float(cam.get("xi", 0.0)))
+    s.T12[:] = [float(x) for x in np.asarray(T12).reshape(7)]
+    out = np.zeros(7); removed = np.zeros(max(n, 1), np.uint8); ninl = C.c_int32(0); info = np.zeros(19)
+    ctx.check(lib().cvb_optimize_relative_pose(ctx.handle, C.byref(s), float(th_outlier_align), out.ctypes.data, removed.ctypes.data,
+                                               C.byref(ninl), info.ctypes.data))
+    nh = int(info[2])
+    return dict(T12=out, removed=removed[:n].astype(bool), n_inliers=int(ninl.value), iterations=(int(info[0]), int(info[1])),
+                cost=info[3:3 + min(nh, 16)].copy())

@@ -139,3 +139,39 @@ def se3_search_scene(seed: int, n_kp: int = 1000, n_shared: int = 300, pix_noise
     T21 = np.linalg.inv(T12)
     already1 = (rng.random(n_kp) < 0.1).astype(np.uint8); already2 = (rng.random(n_kp) < 0.1).astype(np.uint8)
     return views, T12, T21, already1, already2
+
+
+def relpose_case(seed: int, n: int = 150, outlier_frac: float = 0.1, pix_noise: float = 1.0, cam: dict | None = None):
+    """Residual pairs of Optimization::OptimizeRelativePose (optimization_be.cpp:620-831): the same physical points expressed in
+    camera A (pA_c) and camera B (pB_c = T12^-1 pA_c + 1 cm noise: the two keyframes own different landmark estimates),
+    their observations in both images, octave sigmas, and a perturbed initial T12 = [q, t]."""
+    from .synth_map import EUROC_DIST, EUROC_INTR, rot_to_quat
+    rng = np.random.default_rng(seed)
+    cam = cam or dict(intr=EUROC_INTR, dist=EUROC_DIST, cam_model=0, dist_model=0, xi=0.0)
+    R = _rot(rng.normal(0, 0.2, 3)); t = rng.normal(0, 0.3, 3)
+    pB = rng.uniform(-3, 3, (n, 3)) + np.array([0, 0, 8.0])
+    pA = pB @ R.T + t + rng.normal(0, 0.01, (n, 3))
+
+    def proj(p):
+        d = np.asarray(cam["dist"], float)
+        den = p[:, 2] + (cam.get("xi", 0.0) * np.linalg.norm(p, axis=1) if cam.get("cam_model", 0) == 1 else 0.0)
+        x, y = p[:, 0] / den, p[:, 1] / den
+        r2 = x * x + y * y
+        if cam.get("dist_model", 0) == 0:
+            rad = 1 + d[0] * r2 + d[1] * r2 * r2
+            xd = x * rad + 2 * d[2] * x * y + d[3] * (r2 + 2 * x * x); yd = y * rad + d[2] * (r2 + 2 * y * y) + 2 * d[3] * x * y
+        elif cam["dist_model"] == 1:
+            r = np.sqrt(r2); th = np.arctan(r); t2 = th * th
+            s_ = th * (1 + d[0] * t2 + d[1] * t2 ** 2 + d[2] * t2 ** 3 + d[3] * t2 ** 4) / np.maximum(r, 1e-12)
+            xd, yd = s_ * x, s_ * y
+        else:
+            w = d[0]; c = 2 * np.tan(0.5 * w); r = np.sqrt(r2)
+            s_ = np.arctan(c * r) / (w * np.maximum(r, 1e-12)); xd, yd = s_ * x, s_ * y
+        return np.stack([cam["intr"][0] * xd + cam["intr"][2], cam["intr"][1] * yd + cam["intr"][3]], -1)
+    kpA = proj(pA) + rng.normal(0, pix_noise, (n, 2)); kpB = proj(pB) + rng.normal(0, pix_noise, (n, 2))
+    out = rng.random(n) < outlier_frac
+    kpA[out] += rng.normal(0, 60, (int(out.sum()), 2))
+    sA = (rng.integers(0, 3, n) + 1) * 2.0; sB = (rng.integers(0, 3, n) + 1) * 2.0
+    T0 = np.concatenate([rot_to_quat(R @ _rot(rng.normal(0, 0.03, 3))), t + rng.normal(0, 0.05, 3)])
+    Tgt = np.concatenate([rot_to_quat(R), t])
+    return dict(T12=T0, pA_c=pA, pB_c=pB, kpA=kpA.astype(np.float32), kpB=kpB.astype(np.float32), sigmaA=sA, sigmaB=sB, camA=cam, camB=cam), Tgt, out

@@ -266,6 +266,33 @@ CVB_API int cvb_score_relative_pose_batch(cvb_ctx* ctx, const double* model, int
                                           const double* sigma1, const double* sigma2, int n, double threshold,
                                           double* scores, uint8_t* inlier, int32_t* n_inliers);
 
+/*
+ * Optimization::OptimizeRelativePose(kf1, kf2, matches1, T12, th2) (optimization_be.cpp:620-831): the 6-dof refinement of
+ * the relative pose T12 from the matched landmark pairs, both ceres::Solve calls (5 + 5 iterations, DOGLEG, CauchyLoss(1))
+ * and the outlier purge between them, in one call.  The caller (shim) flattens, per residual pair r (the reference's
+ * vIndex order, :656-780): pA_c = TcwA * P3DAw, pB_c = TcwB * P3DBw with TcwB built from kf1's extrinsics as the reference
+ * does (:643), the two observations and sigmas.  Camera / distortion model as in cvb_ba_problem.
+ * T12 / T12_out: [qx,qy,qz,qw, x,y,z] (the reference's ceresAB).  removed [n] (nullable): 1 = residual pair r purged (:812;
+ * the reference nulls matches1[r] — indexed by the RESIDUAL index, :815 — the shim reproduces that).  *n_inliers = the return
+ * value: numCorrespondences - numBad, or 0 (and T12_out = T12) when fewer than 12 remain (:821-823).
+ * info (nullable, 19 doubles): iterations of the two solves, number of cost entries, cost history (tests).
+ */
+typedef struct cvb_relpose_problem {
+  int32_t n;
+  const double* pA_c;      /* [n][3] */
+  const double* pB_c;      /* [n][3] */
+  const float* kpA;        /* [n][2] kf1->keypoints_distorted_[i] */
+  const float* kpB;        /* [n][2] kf2->keypoints_distorted_[iB] */
+  const double* sigmaA;    /* [n] (octave + 1) * 2 */
+  const double* sigmaB;
+  double intrA[4], distA[4], intrB[4], distB[4];
+  int32_t cam_model_A, dist_model_A, cam_model_B, dist_model_B;
+  double xiA, xiB;
+  double T12[7];
+} cvb_relpose_problem;
+CVB_API int cvb_optimize_relative_pose(cvb_ctx* ctx, const cvb_relpose_problem* p, double th_outlier_align, double* T12_out,
+                                       uint8_t* removed, int32_t* n_inliers, double* info);
+
 /* INT-pipe microbenchmark used for the Hamming roofline denominator (SURVEY.md §8d asks the builder to
  * measure the popc issue peak): runs `iters` dependent-free XOR+POPC+ADD rounds on every SM and
  * returns giga-(32-bit popc)/s in *gpopc_per_s. */

@@ -48,9 +48,21 @@ struct Keyframe {
   std::vector<double> imu_dt, imu_acc, imu_gyr;
   double imu_acc0[3] = {0, 0, 0}, imu_gyr0[3] = {0, 0, 0}, imu_noise[5] = {0, 0, 0, 0, 9.81};
   int n_pose_optimized = 0, n_velbias_optimized = 0;
+  // what FeatureMatcher::SearchBySE3 reads (feature_matcher_be.cpp:293-498)
+  std::vector<std::array<unsigned char, 32>> descriptors_;   // cv::Mat descriptors_ rows
+  double K_[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  Transform T_c_w_ = Transform::Identity();
+  double img_dim_x_min_ = 0, img_dim_x_max_ = 752, img_dim_y_min_ = 0, img_dim_y_max_ = 480;
+  const unsigned char* GetDescriptor(size_t i) const { return descriptors_[i].data(); }   // keyframe_base.cpp:254-256
+  std::vector<LandmarkPtr> GetLandmarks() const { return landmarks_; }
+  Transform GetPoseTcw() const { return T_c_w_; }
+  double calibration_K(int r, int c) const { return K_[3 * r + c]; }                       // calibration_.K(r, c)
+  double image_width() const { return 752.0; }                                              // camera_->imageWidth()
+  double image_height() const { return 480.0; }
 
   bool IsInvalid() const { return invalid; }
   Transform GetPoseTws() const { return T_w_s_; }
+  Transform GetStateExtrinsics() const { return T_s_c_; }
   Transform GetPoseTws_vio() const { return T_w_s_vio_; }
   void SetPoseTws(const Transform& T) { T_w_s_ = T; }
   Vector3 GetStateVelocity() const { return velocity_; }
@@ -84,6 +96,14 @@ struct Landmark {
   std::map<KeyframePtr, size_t> observations_;   // pointer-ordered like the reference (typedefs_base.hpp:187)
   KeyframePtr ref_kf;
   int n_optimized = 0;
+  double max_distance_ = 1.0;
+  std::array<unsigned char, 32> descriptor_{};
+  double GetMaxDistanceInvariance() const { return max_distance_; }
+  const unsigned char* GetDescriptorPtr() const { return descriptor_.data(); }              // Landmark::GetDescriptor().data
+  int GetFeatureIndex(const KeyframePtr& kf) const {
+    auto it = observations_.find(kf);
+    return it == observations_.end() ? -1 : (int)it->second;
+  }
   bool IsInvalid() const { return invalid; }
   std::map<KeyframePtr, size_t> GetObservations() const { return observations_; }
   Vector3 GetWorldPos() const { return pos_w_; }

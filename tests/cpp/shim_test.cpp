@@ -75,6 +75,97 @@ int main(int argc, char** argv) {
     wr(dir, "lmdesc_out", out_lm);
     return 0;
   }
+  if (mode == "relpose") {
+    // Optimization::OptimizeRelativePose through the reference-shaped wrapper: two mock keyframes whose landmarks are the
+    // dumped camera-frame points (identity poses / extrinsics: TcwA = TcwB = I, so pA_c = the world positions)
+    auto pA = rd<double>(dir, "pA_c"); auto pB = rd<double>(dir, "pB_c"); auto kA = rd<float>(dir, "kpA"); auto kB = rd<float>(dir, "kpB");
+    auto sA = rd<double>(dir, "sigmaA"); auto sB = rd<double>(dir, "sigmaB"); auto t12 = rd<double>(dir, "T12"); auto intr = rd<double>(dir, "intr"); auto dist = rd<double>(dir, "dist");
+    const size_t n = sA.size();
+    auto k1 = std::make_shared<Keyframe>(), k2 = std::make_shared<Keyframe>();
+    for (int c = 0; c < 4; c++) { k1->intr[c] = k2->intr[c] = intr[c]; k1->dist[c] = k2->dist[c] = dist[c]; }
+    std::vector<LandmarkPtr> matches1(n + 3);   // three trailing keypoints without a match
+    for (size_t i = 0; i < n + 3; i++) {
+      k1->keypoints_distorted_.push_back({i < n ? kA[2 * i] : 0.f, i < n ? kA[2 * i + 1] : 0.f});
+      k1->keypoints_aors_.push_back({0.f, i < n ? (float)(sA[i] / 2.0 - 1.0) : 0.f, 0.f, 0.f});
+      auto la = std::make_shared<Landmark>();
+      if (i < n) la->pos_w_ = {pA[3 * i], pA[3 * i + 1], pA[3 * i + 2]};
+      k1->landmarks_.push_back(la);
+      if (i >= n) continue;
+      k2->keypoints_distorted_.push_back({kB[2 * i], kB[2 * i + 1]});
+      k2->keypoints_aors_.push_back({0.f, (float)(sB[i] / 2.0 - 1.0), 0.f, 0.f});
+      auto lb = std::make_shared<Landmark>();
+      lb->pos_w_ = {pB[3 * i], pB[3 * i + 1], pB[3 * i + 2]};
+      lb->observations_[k2] = i;
+      k2->landmarks_.push_back(lb);
+      matches1[i] = lb;
+    }
+    Transform T12 = pose7_to_T(t12.data());
+    covins_b200::OptParams P;
+    P.th_outlier_align = rd<double>(dir, "th")[0];
+    const int ninl = covins_b200::OptimizeRelativePose(ctx, k1, k2, matches1, T12, 4.0, P);
+    std::vector<double> out(8 + n + 3);
+    covins_b200::detail::transform_to_pose7(T12, out.data());
+    out[7] = ninl;
+    for (size_t i = 0; i < n + 3; i++) out[8 + i] = matches1[i] ? 1.0 : 0.0;
+    wr(dir, "relpose_out", out);
+    return 0;
+  }
+  if (mode == "search") {
+    // FeatureMatcher::SearchBySE3 through the reference-shaped wrapper on two mock keyframes built from dumped arrays,
+    // and the DenseMatcher-shaped adaptor on a MatchingAlgorithm-style policy object
+    auto mk = [&](const char* pre) {
+      auto kf = std::make_shared<Keyframe>();
+      auto kp = rd<float>(dir, (std::string(pre) + "_kp").c_str()); auto oc = rd<float>(dir, (std::string(pre) + "_octave").c_str());
+      auto de = rd<uint8_t>(dir, (std::string(pre) + "_desc").c_str()); auto lv = rd<uint8_t>(dir, (std::string(pre) + "_lm_valid").c_str());
+      auto lp = rd<double>(dir, (std::string(pre) + "_lm_pos").c_str()); auto lm = rd<double>(dir, (std::string(pre) + "_lm_maxdist").c_str());
+      auto ld = rd<uint8_t>(dir, (std::string(pre) + "_lm_desc").c_str()); auto K = rd<double>(dir, (std::string(pre) + "_K").c_str());
+      auto T = rd<double>(dir, (std::string(pre) + "_Tcw").c_str());
+      const size_t n = oc.size();
+      for (size_t i = 0; i < n; i++) {
+        kf->keypoints_distorted_.push_back({kp[2 * i], kp[2 * i + 1]});
+        kf->keypoints_aors_.push_back({0.f, oc[i], 0.f, 0.f});
+        std::array<unsigned char, 32> d; std::copy(de.begin() + 32 * i, de.begin() + 32 * i + 32, d.begin());
+        kf->descriptors_.push_back(d);
+        LandmarkPtr p;
+        if (lv[i]) {
+          p = std::make_shared<Landmark>();
+          p->pos_w_ = {lp[3 * i], lp[3 * i + 1], lp[3 * i + 2]}; p->max_distance_ = lm[i];
+          std::copy(ld.begin() + 32 * i, ld.begin() + 32 * i + 32, p->descriptor_.begin());
+        }
+        kf->landmarks_.push_back(p);
+      }
+      for (int i = 0; i < 9; i++) kf->K_[i] = K[i];
+      for (int i = 0; i < 16; i++) kf->T_c_w_.m[i] = T[i];
+      return kf;
+    };
+    auto k1 = mk("k1"), k2 = mk("k2");
+    for (size_t i = 0; i < k2->landmarks_.size(); i++) if (k2->landmarks_[i]) k2->landmarks_[i]->observations_[k2] = i;
+    auto t12 = rd<double>(dir, "T12"), t21 = rd<double>(dir, "T21");
+    Transform T12, T21; for (int i = 0; i < 16; i++) { T12.m[i] = t12[i]; T21.m[i] = t21[i]; }
+    std::vector<std::vector<LandmarkPtr>> m12(1, std::vector<LandmarkPtr>(k1->landmarks_.size()));
+    auto found = covins_b200::SearchBySE3(ctx, k1, std::vector<KeyframePtr>{k2}, m12, std::vector<Transform>{T12}, std::vector<Transform>{T21}, 9.5, 50, 1, 2.0);
+    std::vector<int32_t> out; out.push_back(found[0]);
+    for (size_t i = 0; i < m12[0].size(); i++) out.push_back(m12[0][i] ? m12[0][i]->GetFeatureIndex(k2) : -1);
+    wr(dir, "search_out", out);
+    // DenseMatcher-shaped adaptor with a policy object that has the MatchingAlgorithm interface + the two descriptor accessors
+    struct Algo {
+      KeyframePtr a, b; std::vector<int32_t> res;
+      void doSetup() {}
+      size_t sizeA() const { return a->descriptors_.size(); }
+      size_t sizeB() const { return b->descriptors_.size(); }
+      bool skipA(size_t i) const { return !a->landmarks_[i] || a->landmarks_[i]->IsInvalid(); }   // LandmarkMatchingAlgorithm.cpp:76-84
+      bool skipB(size_t i) const { return !b->landmarks_[i] || b->landmarks_[i]->IsInvalid(); }
+      float distanceThreshold() const { return 50.0f; }
+      const unsigned char* descriptorA(size_t i) const { return a->GetDescriptor(i); }
+      const unsigned char* descriptorB(size_t i) const { return b->GetDescriptor(i); }
+      void reserveMatches(size_t) {}
+      void setBestMatch(size_t ia, size_t ib, double d) { res.push_back((int32_t)ia); res.push_back((int32_t)ib); res.push_back((int32_t)d); }
+    } algo{k1, k2, {}};
+    covins_b200::DenseMatcher dm(ctx, 8);
+    dm.match<Algo>(algo);
+    wr(dir, "dense_out", algo.res);
+    return 0;
+  }
   // ---- build the mock map from the flat arrays ----
   auto pose = rd<double>(dir, "pose"); auto sb = rd<double>(dir, "speedbias"); auto extr = rd<double>(dir, "extr");
   auto intr = rd<double>(dir, "intr"); auto dist = rd<double>(dir, "dist"); auto lm = rd<double>(dir, "lm");

@@ -259,3 +259,32 @@ def test_unknown_camera_model_is_reported(ctx):
     p["dist_model"] = np.array([0], np.int32); p["cam_model"] = np.array([3], np.int32)
     with pytest.raises(covins_b200.CvbError, match="Unknown projection type"):
         O.solve(ctx, p, 1)
+
+
+# ---------------------------------------------------------------------------------------------- O3 OptimizeRelativePose
+@pytest.mark.parametrize("case", ["radtan", "equi_unified", "few", "purge"])
+def test_optimize_relative_pose_matches_oracle(ctx, case):
+    """Optimization::OptimizeRelativePose (optimization_be.cpp:620-831): both solves + the purge in one launch vs the
+    autograd restatement — same iteration counts, costs to 1e-9 relative, T12 to 1e-9, same removed set / return value"""
+    from covins_b200 import synth
+    from oracle import relpose_oracle as ro
+    cam = None
+    if case == "equi_unified":
+        cam = dict(intr=synth_map.EUROC_INTR, dist=np.array([-0.013, 0.02, -0.012, 0.002]), cam_model=1, dist_model=1, xi=0.9)
+    kw, gt, out = synth.relpose_case(11, n=15 if case == "few" else 60, outlier_frac=0.4 if case == "few" else 0.1, cam=cam)
+    th = 0.9 if case in ("purge", "few") else 1.3      # 1.3 can never fire on Cauchy(1)-corrected norms (< 1); 0.9 exercises the purge
+    got = O.optimize_relative_pose(ctx, th_outlier_align=th, **kw)
+    ref = ro.optimize_relative_pose(th_outlier_align=th, **kw)
+    assert np.array_equal(got["removed"], ref["removed"]) and got["n_inliers"] == ref["n_inliers"]
+    if case == "few":
+        assert got["n_inliers"] == 0 and np.array_equal(got["T12"], kw["T12"])      # < 12 survivors: return 0, T12 untouched (:821-823)
+        return
+    if case == "purge":
+        assert got["removed"].sum() >= 3
+    else:
+        assert got["removed"].sum() == 0
+    rc = list(ref["r1"]["cost"]) + list(ref["r2"]["cost"])
+    assert got["iterations"] == (ref["r1"]["iterations"], ref["r2"]["iterations"])
+    assert np.allclose(got["cost"], rc, rtol=1e-9)
+    assert np.abs(got["T12"] - ref["T12"]).max() < 1e-9
+    assert np.abs(got["T12"][4:] - gt[4:]).max() < 0.05

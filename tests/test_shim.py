@@ -126,3 +126,49 @@ def test_shim_match_candidates_equals_oracle(tmp_path):
     got_d = out_lm[len(lens):].astype(np.uint8).reshape(len(lens), 32)
     for i in range(len(lens)):
         assert np.array_equal(got_d[i], rd[i] if rb[i] >= 0 else np.full(32, 0xAB, np.uint8))
+
+
+@pytest.mark.gpu
+def test_shim_search_by_se3_and_dense_matcher_adaptor(ctx, tmp_path):
+    """FeatureMatcher::SearchBySE3 and estd2::DenseMatcher::match<ALGO> through the reference-shaped C++ wrappers on mock
+    containers == the flat-array API == the oracle"""
+    from covins_b200 import placerec as PR, synth
+    from oracle import geom as og, knn as ora
+    if not os.path.exists(EXE):
+        build_shim_test()
+    views, T12, T21, a1, a2 = synth.se3_search_scene(21, n_kp=600, n_shared=200)
+    for pre, v in zip(("k1", "k2"), views):
+        for k in ("kp", "octave", "desc", "lm_valid", "lm_pos", "lm_maxdist", "lm_desc", "K", "Tcw"):
+            np.ascontiguousarray(v[k]).tofile(os.path.join(tmp_path, f"{pre}_{k}.bin"))
+    np.ascontiguousarray(T12).tofile(tmp_path / "T12.bin"); np.ascontiguousarray(T21).tofile(tmp_path / "T21.bin")
+    subprocess.check_call([EXE, str(tmp_path), "search"])
+    out = np.fromfile(tmp_path / "search_out.bin", np.int32)
+    mk = lambda v: PR.KfView(v["kp"], v["octave"], v["desc"], v["lm_valid"], v["lm_pos"], v["lm_maxdist"], v["lm_desc"], v["K"], v["Tcw"], v["img_bounds"])
+    k1, k2 = mk(views[0]), mk(views[1])
+    zero1, zero2 = np.zeros(k1.n, np.uint8), np.zeros(k2.n, np.uint8)      # the wrapper starts from empty matches12
+    r12, rnf, _, _ = og.search_by_se3(k1, k2, T12, T21, zero1, zero2)
+    assert out[0] == rnf and np.array_equal(out[1:], r12) and rnf > 5
+    dense = np.fromfile(tmp_path / "dense_out.bin", np.int32).reshape(-1, 3)
+    ra, rb, rd = ora.landmark_match(views[0]["desc"], 1 - views[0]["lm_valid"], views[1]["desc"], 1 - views[1]["lm_valid"], 50.0, 4)
+    assert np.array_equal(dense[:, 0], ra) and np.array_equal(dense[:, 1], rb) and np.array_equal(dense[:, 2], rd.astype(np.int32)) and len(ra) > 20
+
+
+@pytest.mark.gpu
+def test_shim_optimize_relative_pose(ctx, tmp_path):
+    """Optimization::OptimizeRelativePose through the reference-shaped C++ wrapper == the flat-array API (same T12, same
+    return value, matches1 nulled at the purged RESIDUAL indices)"""
+    from covins_b200 import optimization as O, synth
+    if not os.path.exists(EXE):
+        build_shim_test()
+    kw, gt, out = synth.relpose_case(5, n=80)
+    for k in ("pA_c", "pB_c", "kpA", "kpB", "sigmaA", "sigmaB", "T12"):
+        np.ascontiguousarray(kw[k]).tofile(tmp_path / f"{k}.bin")
+    np.asarray(kw["camA"]["intr"], np.float64).tofile(tmp_path / "intr.bin"); np.asarray(kw["camA"]["dist"], np.float64).tofile(tmp_path / "dist.bin")
+    np.array([0.9]).tofile(tmp_path / "th.bin")
+    subprocess.check_call([EXE, str(tmp_path), "relpose"])
+    o = np.fromfile(tmp_path / "relpose_out.bin")
+    ref = O.optimize_relative_pose(ctx, th_outlier_align=0.9, **kw)
+    sign = np.sign(o[:4] @ ref["T12"][:4])
+    assert np.abs(o[:4] * sign - ref["T12"][:4]).max() < 1e-9 and np.abs(o[4:7] - ref["T12"][4:]).max() < 1e-9
+    assert int(o[7]) == ref["n_inliers"] and ref["removed"].sum() >= 3
+    assert np.array_equal(o[8:8 + 80] == 0.0, ref["removed"]) and np.all(o[8 + 80:] == 0.0)
