@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) reduce_final(const double* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 // K4: reprojection linearisation.  mode 0: residual + Jacobian records + cost; 1: cost only; 2: corrected norms
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) lin_obs_kernel(int n_obs, const int* __restrict__ obs_kf, const int* __restrict__ obs_lm,
+__global__ void __launch_bounds__(256, 2) lin_obs_kernel(int n_obs, const int* __restrict__ obs_kf, const int* __restrict__ obs_lm,
                                                       const double* __restrict__ obs_uv, const double* __restrict__ obs_sigma,
                                                       const double* __restrict__ pose, const double* __restrict__ lm,
                                                       const double* __restrict__ extr_kf, const double* __restrict__ intr_kf,
@@ -599,35 +599,47 @@ __global__ void imu_repropagate_kernel(int n_imu, const int* __restrict__ imu_j,
   if (!ok) atomicOr(flag, 2);
 }
 
-// IMU factor: whitened residual (15) and whitened, Jacobi-scaled Jacobian (15x30); mode 1: cost only
+// IMU factor: whitened residual (15) and whitened, Jacobi-scaled Jacobian (15x30); mode 1: cost only.
+// One WARP per factor (ncu r02: the one-thread-per-factor version ran 439 us for 2 k factors at 255 registers with the
+// 450-double Jacobian in local memory): lane c < 30 owns column c of the Jacobian — raw column (ba_math.cuh:
+// imu_raw_column), whitening by the upper-triangular sqrt_info (120 MACs), coalesced store along c; lane 30 whitens the
+// residual.  Every lane recomputes the few shared 3x3 products (~600 flops) instead of exchanging them.
 __global__ void __launch_bounds__(256) lin_imu_kernel(int n_imu, const int* __restrict__ imu_i, const int* __restrict__ imu_j,
                                const ImuPre* __restrict__ pre, const double* __restrict__ pose, const double* __restrict__ sb,
                                const double* __restrict__ scale, const int* __restrict__ off_pose,
                                const int* __restrict__ off_sb, double g, int mode, double* __restrict__ Jout,
                                double* __restrict__ rout, double* __restrict__ partials, int slot) {
   double csum[1] = {0.0};
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n_imu; f += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int f = warp; f < n_imu; f += n_warps) {
     const int i = imu_i[f], j = imu_j[f];
-    double r[15], Jraw[450];
-    imu_raw(pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, pre[f], g, r, mode == 0 ? Jraw : nullptr);
-    const double* W = pre[f].sqrt_info;
-    double rw[15], s = 0;
-    for (int a = 0; a < 15; a++) {
-      double v = 0;
-      for (int m = a; m < 15; m++) v += W[15 * a + m] * r[m];   // upper triangular
-      rw[a] = v;
-      s += v * v;
+    const ImuPre& P = pre[f];
+    const double* W = P.sqrt_info;
+    if (lane == 30 || mode != 0) {
+      // the residual: lane 30 (and, for the cost-only pass, nobody else is needed)
+      if (lane == 30) {
+        double r[15];
+        imu_raw_column(pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, P, g, 0, nullptr, r);
+        double s = 0;
+        for (int a = 0; a < 15; a++) {
+          double v = 0;
+          for (int m = a; m < 15; m++) v += W[15 * a + m] * r[m];   // upper triangular
+          if (mode == 0) rout[15 * (size_t)f + a] = v;
+          s += v * v;
+        }
+        csum[0] += 0.5 * s;
+      }
+      if (mode != 0) continue;
     }
-    csum[0] += 0.5 * s;
-    if (mode != 0) continue;
-    for (int a = 0; a < 15; a++) rout[15 * (size_t)f + a] = rw[a];
-    for (int c = 0; c < 30; c++) {
-      const int kf = c < 15 ? i : j;
-      const double sc = scale[cam_col(off_pose, off_sb, kf, c < 15 ? c : c - 15)];
+    if (lane < 30) {
+      double col[15];
+      imu_raw_column(pose + 7 * i, sb + 9 * i, pose + 7 * j, sb + 9 * j, P, g, lane, col, nullptr);
+      const int kf = lane < 15 ? i : j;
+      const double sc = scale[cam_col(off_pose, off_sb, kf, lane < 15 ? lane : lane - 15)];
       for (int a = 0; a < 15; a++) {
         double v = 0;
-        for (int m = a; m < 15; m++) v += W[15 * a + m] * Jraw[30 * m + c];
-        Jout[(size_t)f * 450 + 30 * a + c] = v * sc;
+        for (int m = a; m < 15; m++) v += W[15 * a + m] * col[m];
+        Jout[(size_t)f * 450 + 30 * a + lane] = v * sc;
       }
     }
   }

@@ -399,4 +399,59 @@ __host__ __device__ inline void imu_raw(const double* pose_i, const double* sb_i
   }
 }
 
+// Column c (0..29) of the raw IMU Jacobian and, optionally, the raw residual — the same quantities as imu_raw(), arranged for
+// one-lane-per-column evaluation (lin_imu_kernel: a warp per factor; every lane recomputes the handful of shared 3x3
+// products, ~600 flops, and owns one column of the 15x30 Jacobian).
+__host__ __device__ inline void imu_raw_column(const double* pose_i, const double* sb_i, const double* pose_j, const double* sb_j,
+                                               const ImuPre& P, double g, int c, double col[15], double* r /*15 or null*/) {
+  const Pose Pi = load_pose(pose_i), Pj = load_pose(pose_j);
+  const M3 Ri = q2R(Pi.q), Rj = q2R(Pj.q);
+  const V3 vi{sb_i[0], sb_i[1], sb_i[2]}, vj{sb_j[0], sb_j[1], sb_j[2]};
+  const V3 dba{sb_i[3] - P.ba[0], sb_i[4] - P.ba[1], sb_i[5] - P.ba[2]};
+  const V3 dbg{sb_i[6] - P.bg[0], sb_i[7] - P.bg[1], sb_i[8] - P.bg[2]};
+  M3 Jpa, Jpg, Jqg, Jva, Jvg;
+  for (int i = 0; i < 9; i++) { Jpa.m[i] = P.dp_dba[i]; Jpg.m[i] = P.dp_dbg[i]; Jqg.m[i] = P.dq_dbg[i]; Jva.m[i] = P.dv_dba[i]; Jvg.m[i] = P.dv_dbg[i]; }
+  const double T = P.T;
+  const V3 gv{0, 0, g};
+  const V3 theta = mul(Jqg, dbg);
+  const Q4 gam{P.gamma[0], P.gamma[1], P.gamma[2], P.gamma[3]};
+  const Q4 g_hat = qmul(gam, qexp(theta));
+  const V3 wp = 0.5 * T * T * gv + Pj.t - Pi.t - T * vi;
+  const V3 wv = T * gv + vj - vi;
+  const Q4 qij = qmul(qconj(Pi.q), Pj.q);
+  const Q4 E = qmul(qconj(g_hat), qij);
+  if (r) {
+    const V3 a_hat = V3{P.alpha[0], P.alpha[1], P.alpha[2]} + mul(Jpa, dba) + mul(Jpg, dbg);
+    const V3 b_hat = V3{P.beta[0], P.beta[1], P.beta[2]} + mul(Jva, dba) + mul(Jvg, dbg);
+    const V3 rp = mulT(Ri, wp) - a_hat, rv = mulT(Ri, wv) - b_hat;
+    r[0] = rp.x; r[1] = rp.y; r[2] = rp.z; r[3] = 2 * E.x; r[4] = 2 * E.y; r[5] = 2 * E.z; r[6] = rv.x; r[7] = rv.y; r[8] = rv.z;
+    for (int k = 0; k < 3; k++) { r[9 + k] = sb_j[3 + k] - sb_i[3 + k]; r[12 + k] = sb_j[6 + k] - sb_i[6 + k]; }
+  }
+  if (!col) return;
+  for (int a = 0; a < 15; a++) col[a] = 0.0;
+  const int cb = c / 3, b = c % 3;
+  const M3 Rit = transpose(Ri);
+  auto put = [&](int row0, const M3& A, double sgn) { for (int a = 0; a < 3; a++) col[row0 + a] = sgn * A.m[3 * a + b]; };
+  switch (cb) {
+    case 0: {   // dtheta_i
+      const M3 GRjT = mul(quat_right_jac(E), transpose(Rj));
+      put(0, mul(Rit, skew(wp)), 1.0); put(3, GRjT, -1.0); put(6, mul(Rit, skew(wv)), 1.0);
+    } break;
+    case 1: put(0, Rit, -1.0); break;                                   // dp_i
+    case 2: put(0, Rit, -T); put(6, Rit, -1.0); break;                  // v_i
+    case 3: put(0, Jpa, -1.0); put(6, Jva, -1.0); col[9 + b] = -1.0; break;   // ba_i
+    case 4: {   // bg_i
+      const Q4 Mq = qmul(qconj(gam), qij);
+      const V3 mth{-theta.x, -theta.y, -theta.z};
+      const M3 dq_bg = mul(mul(quat_right_jac(E), transpose(q2R(Mq))), mul(so3_Jr(mth), Jqg));
+      put(0, Jpg, -1.0); put(3, dq_bg, -1.0); put(6, Jvg, -1.0); col[12 + b] = -1.0;
+    } break;
+    case 5: put(3, mul(quat_right_jac(E), transpose(Rj)), 1.0); break;  // dtheta_j
+    case 6: put(0, Rit, 1.0); break;                                    // dp_j
+    case 7: put(6, Rit, 1.0); break;                                    // v_j
+    case 8: col[9 + b] = 1.0; break;                                    // ba_j
+    default: col[12 + b] = 1.0; break;                                  // bg_j
+  }
+}
+
 }  // namespace bam

@@ -132,8 +132,11 @@ class _Traj:
 
 def make_map(seed: int, n_agents: int, kf_per_agent: int, n_lm: int, mean_track: float = 8.0, outlier_frac: float = 0.05,
              pix_noise: float = 1.0, drift_trans: float = 0.002, drift_yaw_deg: float = 0.02, lm_noise: float = 0.01,
-             with_imu: bool = True, loops_per_pair: int = 3, loops_intra: int = 2):
-    """→ dict of numpy arrays: the flat problem (initial = drifted state) plus ground truth under 'gt_*'."""
+             with_imu: bool = True, loops_per_pair: int = 3, loops_intra: int = 2, candidate_window: int = 0):
+    """→ dict of numpy arrays: the flat problem (initial = drifted state) plus ground truth under 'gt_*'.
+    candidate_window > 0 (stress configs: C5 has 10^6 landmarks x 10^4 keyframes): a landmark's observers are searched only
+    among its anchor's temporal neighbours (+- window) and the same time window of two other agents, instead of among all
+    keyframes."""
     rng = np.random.default_rng(seed)
     K = n_agents * kf_per_agent
     dt_kf, dt_imu = 1.0 / KF_HZ, 1.0 / IMU_HZ
@@ -163,9 +166,51 @@ def make_map(seed: int, n_agents: int, kf_per_agent: int, n_lm: int, mean_track:
     # camera-frame coordinates of every (landmark, KF) pair as ONE GEMM: pcam[c,k,:] = P[c] @ R_wc[k] - p_wc[k] @ R_wc[k]
     Rcat = np.ascontiguousarray(R_wc.transpose(1, 0, 2).reshape(3, 3 * K)).astype(np.float32)      # [3, K*3]
     off = np.einsum("kj,kji->ki", p_wc, R_wc).reshape(1, 3 * K).astype(np.float32)
+    if candidate_window > 0:
+        chunk = 20_000
+        R32, p32 = R_wc.astype(np.float32), p_wc.astype(np.float32)
     for s in range(0, n_lm, chunk):
         P = lm_gt[s:s + chunk].astype(np.float32)                    # [c,3]; float32 is enough for the visibility test
         c = P.shape[0]
+        if candidate_window > 0:
+            # candidate keyframes: the anchor's agent and two other agents, each a time window around the anchor's time
+            a = anchor[s:s + c]
+            w = candidate_window
+            t0 = kf_id[a]
+            others = (agent_of[a][:, None] + rng.integers(1, max(n_agents, 2), (c, 2))) % n_agents
+            ag = np.concatenate([agent_of[a][:, None], others], 1)                                 # [c,3]
+            tt = np.clip(t0[:, None] + np.arange(-w, w + 1)[None, :], 0, kf_per_agent - 1)         # [c,2w+1]
+            cand = (ag[:, :, None] * kf_per_agent + tt[:, None, :]).reshape(c, -1)                  # [c, 3(2w+1)]
+            cand = np.sort(cand, axis=1)
+            dup = np.concatenate([np.zeros((c, 1), bool), cand[:, 1:] == cand[:, :-1]], 1)          # clipped windows repeat indices
+            d = P[:, None, :] - p32[cand]
+            pc_ = np.einsum("cnji,cnj->cni", R32[cand], d)
+            z = pc_[..., 2]
+            vis = (z > 0.5) & (z < 20.0) & ~dup
+            iz = 1.0 / np.where(vis, z, np.float32(1))
+            xn_ = pc_[..., 0] * iz; yn_ = pc_[..., 1] * iz
+            r2 = xn_ * xn_ + yn_ * yn_
+            vis &= r2 < 0.75
+            rad = 1 + np.float32(EUROC_DIST[0]) * r2 + np.float32(EUROC_DIST[1]) * r2 * r2
+            xn_ *= rad; yn_ *= rad
+            vis &= (np.abs(xn_ * np.float32(EUROC_INTR[0]) + np.float32(EUROC_INTR[2] - IMG_W / 2)) < IMG_W / 2 - 8)
+            vis &= (np.abs(yn_ * np.float32(EUROC_INTR[1]) + np.float32(EUROC_INTR[3] - IMG_H / 2)) < IMG_H / 2 - 8)
+            vis |= (cand == a[:, None]) & ~dup
+            rows, cc = np.nonzero(vis)
+            cols = cand[rows, cc]
+            ar = a[rows]
+            key = np.where(agent_of[cols] == agent_of[ar], np.abs(kf_id[cols] - kf_id[ar]).astype(np.float64), 30.0 + rng.uniform(0, 60, len(rows)))
+            key = key + rng.uniform(0, 12, len(rows))
+            key[cols == ar] = -1.0
+            o = np.lexsort((key, rows))
+            rows, cols = rows[o], cols[o]
+            start_of_row = np.searchsorted(rows, np.arange(c))
+            rank_ = np.arange(len(rows)) - start_of_row[rows]
+            keep = rank_ < want[s:s + c][rows]
+            rows, cols = rows[keep], cols[keep]
+            o = np.lexsort((cols, rows))
+            obs_lm.append(s + rows[o]); obs_kf.append(cols[o])
+            continue
         pcam = (P @ Rcat - off).reshape(c, K, 3)
         z = pcam[..., 2]
         vis = (z > 0.5) & (z < 20.0)
@@ -286,6 +331,9 @@ CONFIGS = {
     "C1": dict(n_agents=1, kf_per_agent=200, n_lm=10_000),
     "C2": dict(n_agents=2, kf_per_agent=400, n_lm=40_000),
     "C3": dict(n_agents=5, kf_per_agent=400, n_lm=100_000),
+    # BASELINE.json config 5: 12-agent 10k-KF / 1M-landmark stress map (observers searched in a +-40-keyframe window of three agents)
+    "C5": dict(n_agents=12, kf_per_agent=834, n_lm=1_000_000, candidate_window=40),
+    "C5s": dict(n_agents=12, kf_per_agent=100, n_lm=60_000, candidate_window=40),      # small stand-in with the same generator path (tests)
 }
 
 
@@ -327,7 +375,7 @@ def with_camera_model(p: dict, cam_model: int, dist_model: int, dist=None, xi: f
     return q
 
 
-_CACHE_VERSION = "r02a"   # bump when make_map changes
+_CACHE_VERSION = "r02b"   # bump when make_map changes
 
 
 def make_config(name: str, seed: int | None = None, **kw):

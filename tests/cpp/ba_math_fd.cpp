@@ -53,4 +53,10 @@ int main(){
     double rp[15],rm[15]; imu_raw(pi,si,pj,sj,P,9.81,rp,0); imu_raw(pi2,si2,pj2,sj2,P,9.81,rm,0);
     for(int a=0;a<15;a++){ double fd=(rp[a]-rm[a])/(2*eps); double er=fabs(fd-Jr[30*a+c]); if(er>worst){worst=er;wc=c;wa=a;} } }
   printf("imu max jac err %g at row %d col %d\n",worst,wa,wc);
+  // the column-wise evaluation used by the warp-per-factor kernel must reproduce imu_raw exactly
+  double cmax=0, rr2[15];
+  for(int c=0;c<30;c++){ double col[15]; imu_raw_column(pose,sbi,pose2,sbj,P,9.81,c,col,c==0?rr2:nullptr); for(int a=0;a<15;a++) cmax=fmax(cmax,fabs(col[a]-Jr[30*a+c])); }
+  for(int a=0;a<15;a++) cmax=fmax(cmax,fabs(rr2[a]-rr[a]));
+  printf("imu column-wise vs full: max abs diff %g\n",cmax);
+  if(cmax!=0.0) return 1;
 }
