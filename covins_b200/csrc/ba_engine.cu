@@ -1308,6 +1308,47 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     for (int k = 0; k < K; k++)
       if (comp_size[find(k)] < 2) { E.h_off_pose[k] = cursor; cursor += 6; }
     n_total = cursor;
+  } else if (E.L_in == 0 && p->n_edge > 0 && !getenv("COVINS_B200_PGO_PLAIN_ORDER")) {
+    // Pose graph (PoseGraphOptimization: no landmarks, only between-factors): the keyframes of one agent form a banded chain
+    // (successor + 5 predecessor edges, optimization_be.cpp:947-1021) and the few loop edges couple distant keyframes.  In
+    // plain keyframe order the tile columns are one long dependent chain (94 columns x ~100 us at C3).  Nested dissection
+    // by hand: the endpoints of long-range edges go to a per-chain BORDER segment at the end; what remains are independent
+    // banded chains, each laid out on its own tiles → they are eliminated concurrently as column groups (like the IMU chains
+    // of the visual-inertial problem), then the small border is factored.  A chain's columns only ever touch its own tiles
+    // and its own border segment, so concurrent groups never update the same tile.
+    std::vector<char> border(K, 0);
+    for (int e = 0; e < p->n_edge; e++)
+      if (std::abs(p->edge_i[e] - p->edge_j[e]) > 8) border[p->edge_i[e]] = border[p->edge_j[e]] = 1;
+    std::vector<int> parent(K);
+    std::iota(parent.begin(), parent.end(), 0);
+    std::function<int(int)> find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+    for (int e = 0; e < p->n_edge; e++) {
+      if (std::abs(p->edge_i[e] - p->edge_j[e]) > 8) continue;       // a chain = connected through short-range edges (border keyframes included)
+      const int a = find(p->edge_i[e]), b = find(p->edge_j[e]);
+      if (a != b) parent[std::max(a, b)] = std::min(a, b);
+    }
+    std::vector<int> comp_size(K, 0);
+    for (int k = 0; k < K; k++) comp_size[find(k)]++;
+    std::vector<int> roots;
+    for (int r = 0; r < K; r++)
+      if (find(r) == r && comp_size[r] >= 64) roots.push_back(r);
+    int cursor = 0;
+    for (int r : roots) {                                             // interiors of the big chains: one column group each
+      cursor = ((cursor + TT - 1) / TT) * TT;
+      const int begin = cursor;
+      for (int k = r; k < K; k++)
+        if (find(k) == r && !border[k]) { E.h_off_pose[k] = cursor; cursor += 6; }
+      if (cursor > begin) sb_ranges.emplace_back(begin, cursor);
+    }
+    cursor = ((cursor + TT - 1) / TT) * TT;
+    for (int k = 0; k < K; k++)                                       // small components: main sequence
+      if (comp_size[find(k)] < 64) { E.h_off_pose[k] = cursor; cursor += 6; }
+    for (int r : roots) {                                             // per-chain border segments
+      cursor = ((cursor + TT - 1) / TT) * TT;
+      for (int k = r; k < K; k++)
+        if (find(k) == r && border[k]) { E.h_off_pose[k] = cursor; cursor += 6; }
+    }
+    n_total = cursor;
   } else {
     for (int k = 0; k < K; k++) E.h_off_pose[k] = 6 * k;
     n_total = 6 * K;

@@ -17,6 +17,7 @@
 
 #include <vector>
 
+#include "ba_math.cuh"
 #include "cvb_internal.cuh"
 
 namespace {
@@ -145,6 +146,113 @@ __global__ void __launch_bounds__(256) search_se3_kernel(DevKf k1, const DevPair
   if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&found, cnt);
   __syncthreads();
   if (threadIdx.x == 0) *P.n_found = found;
+}
+
+// ---- FeatureMatcher::SearchByProjection (feature_matcher_be.cpp:168-291) ---------------------------------------------
+// Phase A (all threads of ONE CTA): every candidate landmark is projected with the keyframe's full camera model, gated
+// (image bounds, distance invariance, viewing angle) and its keypoints in the search radius are listed — in the grid's
+// candidate order, with their Hamming distances, octave gate applied (at most kProjCap per landmark).  Phase B (thread 0):
+// the reference's sequential semantics — a keypoint taken by an earlier landmark is skipped, the first strict minimum wins,
+// RemapLandmark bookkeeping — over those short lists.  The order dependence is inherent to the reference (vpMatched is
+// updated while the loop runs); the expensive part (projection, radius search, distances) is what runs in parallel.
+constexpr int kProjCap = 48;
+struct ProjDev {
+  int m;
+  const uint8_t* valid; const double* pos; const double* normal; const double* min_dist; const double* max_dist;
+  const double* max_distance; const uint8_t* desc; const int* feat_idx;
+  double Tcw[16], intr[4], dist[4], xi;
+  int cam, dm;
+  int* cand_idx; int* cand_dist; int* cand_n;      // [m][kProjCap], [m]
+  uint8_t* matched; uint8_t* has_lm; int* lm_cand; int* feat;   // working copies [n], [n], [n], [m]
+  int* action; int* best_idx; int* n_matches; int* overflow;
+};
+
+__global__ void __launch_bounds__(256, 1) search_proj_kernel(DevKf kf, ProjDev P, double th, int th_low, double sf, int num_octaves) {
+  double Ow[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) Ow[r] = -add(add(mul(P.Tcw[r], P.Tcw[3]), mul(P.Tcw[4 + r], P.Tcw[7])), mul(P.Tcw[8 + r], P.Tcw[11]));
+  for (int i = threadIdx.x; i < P.m; i += blockDim.x) {
+    int cnt = -1;   // -1 = gated out
+    do {
+      if (!P.valid[i]) break;
+      const double pw[3] = {P.pos[3 * (size_t)i], P.pos[3 * (size_t)i + 1], P.pos[3 * (size_t)i + 2]};
+      double pc[3];
+      rt_apply(P.Tcw, pw, pc);
+      if (pc[2] < 0.0) break;
+      const bam::CamModel cm{P.cam, P.dm, P.xi};
+      double x, y, xd, yd;
+      if (!bam::cam_normalise(cm, bam::V3{pc[0], pc[1], pc[2]}, &x, &y, nullptr, false)) break;
+      bam::cam_distort(cm, P.dist, x, y, &xd, &yd, nullptr, false);
+      const double u = P.intr[0] * xd + P.intr[2], v = P.intr[1] * yd + P.intr[3];
+      if (!in_image(kf.img, u, v)) break;
+      const double PO[3] = {sub(pw[0], Ow[0]), sub(pw[1], Ow[1]), sub(pw[2], Ow[2])};
+      const double d3 = __dsqrt_rn(add(add(mul(PO[0], PO[0]), mul(PO[1], PO[1])), mul(PO[2], PO[2])));
+      if (d3 < P.min_dist[i] || d3 > P.max_dist[i]) break;
+      if (add(add(mul(PO[0], P.normal[3 * (size_t)i]), mul(PO[1], P.normal[3 * (size_t)i + 1])), mul(PO[2], P.normal[3 * (size_t)i + 2])) < mul(0.5, d3)) break;
+      const int level = predict_scale(P.max_distance[i], d3, sf, num_octaves);
+      double radius = th;
+      for (int l = 0; l < level; l++) radius = mul(radius, sf);   // th * pow(scale_factor, level) for integer level
+      const float tx = (float)u, ty = (float)v;
+      int min_cx = (int)floor(mul(sub((double)tx, radius), kf.grid_w_inv)); if (min_cx < 0) min_cx = 0;
+      if (min_cx >= GRID_COLS) break;
+      int max_cx = (int)ceil(mul(add((double)tx, radius), kf.grid_w_inv)); if (max_cx > GRID_COLS - 1) max_cx = GRID_COLS - 1;
+      if (max_cx < 0) break;
+      int min_cy = (int)floor(mul(sub((double)ty, radius), kf.grid_h_inv)); if (min_cy < 0) min_cy = 0;
+      if (min_cy >= GRID_ROWS) break;
+      int max_cy = (int)ceil(mul(add((double)ty, radius), kf.grid_h_inv)); if (max_cy > GRID_ROWS - 1) max_cy = GRID_ROWS - 1;
+      if (max_cy < 0) break;
+      cnt = 0;
+      const uint8_t* dl = P.desc + 32 * (size_t)i;
+      for (int ix = min_cx; ix <= max_cx; ix++)
+        for (int iy = min_cy; iy <= max_cy; iy++) {
+          const int c = ix * GRID_ROWS + iy;
+          for (int q = kf.grid_ptr[c]; q < kf.grid_ptr[c + 1]; q++) {
+            const int idx = kf.grid_idx[q];
+            const float dx = __fsub_rn(kf.kp[2 * (size_t)idx], tx), dy = __fsub_rn(kf.kp[2 * (size_t)idx + 1], ty);
+            if (!((double)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) <= radius)) continue;
+            const int lvl = (int)kf.octave[idx];
+            if (lvl < level - 1 || lvl > level) continue;
+            if (cnt < kProjCap) { P.cand_idx[(size_t)i * kProjCap + cnt] = idx; P.cand_dist[(size_t)i * kProjCap + cnt] = ham256(dl, kf.desc + 32 * (size_t)idx); }
+            cnt++;
+          }
+        }
+      if (cnt > kProjCap) atomicExch(P.overflow, 1);
+    } while (false);
+    P.cand_n[i] = cnt;
+    P.action[i] = 0; P.best_idx[i] = -1;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  int nm = 0;
+  for (int i = 0; i < P.m; i++) {
+    const int cn = P.cand_n[i] < kProjCap ? P.cand_n[i] : kProjCap;
+    int bd = 256, best = -1;
+    for (int q = 0; q < cn; q++) {
+      const int idx = P.cand_idx[(size_t)i * kProjCap + q];
+      if (P.matched[idx]) continue;                                     // if (vpMatched[idx]) continue (:239)
+      const int d = P.cand_dist[(size_t)i * kProjCap + q];
+      if (d < bd) { bd = d; best = idx; }
+    }
+    if (best < 0 || bd > th_low) continue;                             // bestDist <= desc_matching_th_low_ (:258)
+    P.best_idx[i] = best;
+    const int existing = P.feat[i];
+    if (existing != -1) {                                               // already observed (:260-282)
+      const uint8_t* dl = P.desc + 32 * (size_t)i;
+      bool keep = ham256(dl, kf.desc + 32 * (size_t)existing) < bd;
+      if (P.has_lm[best] && ham256(dl, kf.desc + 32 * (size_t)best) < bd) keep = true;
+      if (keep) { P.action[i] = 3; continue; }
+      const int displaced = P.lm_cand[best];                            // RemapLandmark (keyframe_be.cpp:484-495)
+      const bool had = P.has_lm[best] != 0;
+      P.has_lm[existing] = 0; P.lm_cand[existing] = -1;
+      P.has_lm[best] = 1; P.lm_cand[best] = i; P.feat[i] = best;
+      if (had && displaced >= 0) P.feat[displaced] = -1;                // lm_new->EraseObservation comes LAST (:494): existing == best un-observes lm itself
+      P.action[i] = 2;
+    } else {
+      P.matched[best] = 1;                                              // vpMatched[bestIdx] = pMP (:285)
+      P.action[i] = 1; nm++;
+    }
+  }
+  *P.n_matches = nm;
 }
 
 // ---- V1 scoring: block = (chunk of 256 correspondences, hypothesis) ------------------------------------------------
@@ -400,6 +508,66 @@ int cvb_score_absolute_pose_batch(cvb_ctx* ctx, const double* model, int n_hyp, 
 int cvb_score_relative_pose_batch(cvb_ctx* ctx, const double* model, int n_hyp, const double* f1, const double* f2, const double* sigma1,
                                   const double* sigma2, int n, double threshold, double* scores, uint8_t* inlier, int32_t* n_inliers) {
   return score_common(ctx, true, model, n_hyp, f1, f2, sigma1, sigma2, n, nullptr, nullptr, threshold, scores, inlier, n_inliers);
+}
+
+int cvb_search_by_projection(cvb_ctx* ctx, const cvb_kf_view* kf, const int32_t* kf_lm_cand, const double* Tcw, const double* intr,
+                             const double* dist, int cam_model, int dist_model, double xi, const cvb_proj_landmarks* lms,
+                             const uint8_t* matched, const cvb_search_params* prm, int32_t* action, int32_t* best_idx, int32_t* n_matches) {
+  if (!ctx) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
+  CVB_REQUIRE(ctx, kf && Tcw && intr && dist && lms && prm && n_matches && lms->m >= 0, "search_by_projection: bad arguments");
+  CVB_REQUIRE(ctx, kf->n >= 0 && kf->grid_ptr && (kf->n == 0 || (kf->kp && kf->octave && kf->desc && kf->lm_valid && kf_lm_cand && matched)),
+              "search_by_projection: malformed keyframe view");
+  CVB_REQUIRE(ctx, kf->grid_ptr[0] == 0 && kf->grid_ptr[GRID_COLS * GRID_ROWS] <= kf->n, "search_by_projection: malformed grid");
+  if (cam_model < 0 || cam_model > 1) return cvb_fail(ctx, CVB_ERR_UNSUPPORTED, "Unknown projection type.");
+  if (dist_model < 0 || dist_model > 2) return cvb_fail(ctx, CVB_ERR_UNSUPPORTED, "Unknown distortion type.");
+  const int n = kf->n, m = lms->m;
+  *n_matches = 0;
+  if (m == 0) return CVB_OK;
+  CVB_REQUIRE(ctx, lms->valid && lms->pos && lms->normal && lms->min_dist && lms->max_dist && lms->max_distance && lms->desc && lms->feat_idx &&
+              action && best_idx, "search_by_projection: null landmark arrays");
+  for (int i = 0; i < m; i++) CVB_REQUIRE(ctx, lms->feat_idx[i] >= -1 && lms->feat_idx[i] < n, "search_by_projection: feat_idx out of range");
+  for (int i = 0; i < n; i++) CVB_REQUIRE(ctx, kf_lm_cand[i] >= -1 && kf_lm_cand[i] < m, "search_by_projection: kf_lm_cand out of range");
+  Stager S;
+  const size_t ng = (size_t)kf->grid_ptr[GRID_COLS * GRID_ROWS];
+  const size_t o_kp = S.put(kf->kp, (size_t)n * 8), o_oc = S.put(kf->octave, (size_t)n * 4), o_de = S.put(kf->desc, (size_t)n * 32),
+               o_gp = S.put(kf->grid_ptr, (GRID_COLS * GRID_ROWS + 1) * 4), o_gi = S.put(kf->grid_idx, ng * 4);
+  const size_t o_hl = S.put(kf->lm_valid, (size_t)n), o_lc = S.put(kf_lm_cand, (size_t)n * 4), o_ma = S.put(matched, (size_t)n);
+  const size_t o_va = S.put(lms->valid, (size_t)m), o_po = S.put(lms->pos, (size_t)m * 24), o_no = S.put(lms->normal, (size_t)m * 24),
+               o_mi = S.put(lms->min_dist, (size_t)m * 8), o_mx = S.put(lms->max_dist, (size_t)m * 8), o_md = S.put(lms->max_distance, (size_t)m * 8),
+               o_ld = S.put(lms->desc, (size_t)m * 32), o_fi = S.put(lms->feat_idx, (size_t)m * 4), o_fe = S.put(lms->feat_idx, (size_t)m * 4);
+  const size_t in_bytes = S.h.size();
+  const size_t o_ci = S.reserve((size_t)m * kProjCap * 4), o_cd = S.reserve((size_t)m * kProjCap * 4), o_cn = S.reserve((size_t)m * 4);
+  const size_t o_out = S.reserve(0), o_ac = S.reserve((size_t)m * 4), o_bi = S.reserve((size_t)m * 4), o_nm = S.reserve(8);
+  const size_t total = S.h.size();
+  unsigned char* d = (unsigned char*)cvb_ws(ctx, WS_GS4, total);
+  unsigned char* hpin = (unsigned char*)cvb_pinned(ctx, total);
+  if (!d || !hpin) return CVB_ERR_CUDA;
+  DevKf K{};
+  K.n = n; K.kp = (const float*)(d + o_kp); K.octave = (const float*)(d + o_oc); K.desc = d + o_de; K.grid_ptr = (const int*)(d + o_gp);
+  K.grid_idx = (const int*)(d + o_gi); K.grid_w_inv = kf->grid_w_inv; K.grid_h_inv = kf->grid_h_inv;
+  memcpy(K.img, kf->img, sizeof(K.img));
+  ProjDev P{};
+  P.m = m; P.valid = d + o_va; P.pos = (const double*)(d + o_po); P.normal = (const double*)(d + o_no); P.min_dist = (const double*)(d + o_mi);
+  P.max_dist = (const double*)(d + o_mx); P.max_distance = (const double*)(d + o_md); P.desc = d + o_ld; P.feat_idx = (const int*)(d + o_fi);
+  memcpy(P.Tcw, Tcw, sizeof(P.Tcw)); memcpy(P.intr, intr, 32); memcpy(P.dist, dist, 32);
+  P.xi = xi; P.cam = cam_model; P.dm = dist_model;
+  P.cand_idx = (int*)(d + o_ci); P.cand_dist = (int*)(d + o_cd); P.cand_n = (int*)(d + o_cn);
+  P.matched = d + o_ma; P.has_lm = d + o_hl; P.lm_cand = (int*)(d + o_lc); P.feat = (int*)(d + o_fe);
+  P.action = (int*)(d + o_ac); P.best_idx = (int*)(d + o_bi); P.n_matches = (int*)(d + o_nm); P.overflow = (int*)(d + o_nm) + 1;
+  memcpy(hpin, S.h.data(), in_bytes);
+  cudaStream_t st = ctx->stream;
+  CVB_CUDA(ctx, cudaMemcpyAsync(d, hpin, in_bytes, cudaMemcpyHostToDevice, st));
+  CVB_CUDA(ctx, cudaMemsetAsync(d + o_nm, 0, 8, st));
+  search_proj_kernel<<<1, 256, 0, st>>>(K, P, prm->th, prm->desc_th_low, prm->scale_factor, prm->num_octaves);
+  CVB_CHECK_LAUNCH(ctx);
+  CVB_CUDA(ctx, cudaMemcpyAsync(hpin + o_out, d + o_out, total - o_out, cudaMemcpyDeviceToHost, st));
+  CVB_CUDA(ctx, cudaStreamSynchronize(st));
+  const int* tail = (const int*)(hpin + o_nm);
+  if (tail[1]) return cvb_fail(ctx, CVB_ERR_UNSUPPORTED, "search_by_projection: more than %d keypoints in a search radius", kProjCap);
+  memcpy(action, hpin + o_ac, (size_t)m * 4); memcpy(best_idx, hpin + o_bi, (size_t)m * 4);
+  *n_matches = tail[0];
+  return CVB_OK;
 }
 
 }  // extern "C"

@@ -800,7 +800,9 @@ struct KfViewStorage {
 // matches12[p] is updated in place exactly as the reference does (:485-496: matches12[i] = mapPoints2[idx2]); returns the
 // number of matches found per candidate.  KF is touched through the member names the reference class has
 // (keypoints_distorted_, keypoints_aors_, GetDescriptor(i), GetLandmarks(), calibration via Adapter<KF>::K, GetPoseTcw(),
-// img_dim_*_); Landmark through IsInvalid / GetWorldPos / GetMaxDistanceInvariance / GetDescriptorPtr / GetFeatureIndex.
+// img_dim_*_); Landmark through IsInvalid / GetWorldPos / GetMaxDistance / GetDescriptorPtr / GetFeatureIndex.  GetMaxDistance() is
+// the ONE getter a maintainer adds to LandmarkBase: PredictScale (landmark_base.cpp:120-133) divides the raw max_distance_
+// (protected, landmark_base.hpp:107), and GetMaxDistanceInvariance() returns 1.2 x that (landmark_base.cpp:68-71).
 template <class KFPtr, class LandmarkVector, class Transform4>
 inline std::vector<int> SearchBySE3(Context& ctx, const KFPtr& kf1, const std::vector<KFPtr>& kf2, std::vector<LandmarkVector>& matches12,
                                     const std::vector<Transform4>& T12, const std::vector<Transform4>& T21, double th,
@@ -818,7 +820,7 @@ inline std::vector<int> SearchBySE3(Context& ctx, const KFPtr& kf1, const std::v
         S.lm_valid[i] = 1;
         const auto p = lms[i]->GetWorldPos();
         for (int c = 0; c < 3; c++) S.lm_pos[3 * i + c] = p[c];
-        S.lm_maxdist[i] = lms[i]->GetMaxDistanceInvariance();
+        S.lm_maxdist[i] = lms[i]->GetMaxDistance();
         std::copy(lms[i]->GetDescriptorPtr(), lms[i]->GetDescriptorPtr() + 32, S.lm_desc.begin() + 32 * i);
       }
     }

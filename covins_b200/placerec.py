@@ -86,6 +86,40 @@ def search_by_se3_batch(ctx: Context, kf1: KfView, kf2s, T12, T21, already1, alr
     return m12, nf[:n_pairs]
 
 
+class CProjLandmarks(C.Structure):
+    _fields_ = [("m", C.c_int32)] + [(k, c_vp) for k in ("valid", "pos", "normal", "min_dist", "max_dist", "max_distance", "desc", "feat_idx")]
+
+
+def _proj_args(kf: KfView, kf_lm_cand, Tcw, cam: dict, lms: dict, matched, th, desc_th_low, num_octaves, scale_factor, struct_cls, prm_cls):
+    """flat arguments shared by the product call and the oracle binding (which passes its own struct classes)"""
+    m = len(lms["pos"])
+    a = dict(valid=np.ascontiguousarray(lms["valid"], np.uint8), pos=np.ascontiguousarray(lms["pos"], np.float64).reshape(m, 3),
+             normal=np.ascontiguousarray(lms["normal"], np.float64).reshape(m, 3), min_dist=np.ascontiguousarray(lms["min_dist"], np.float64),
+             max_dist=np.ascontiguousarray(lms["max_dist"], np.float64), max_distance=np.ascontiguousarray(lms["max_distance"], np.float64),
+             desc=np.ascontiguousarray(lms["desc"], np.uint8).reshape(m, 32), feat_idx=np.ascontiguousarray(lms["feat_idx"], np.int32))
+    L = struct_cls(); L.m = m
+    for k, v in a.items():
+        setattr(L, k, v.ctypes.data)
+    keep = [a, np.ascontiguousarray(kf_lm_cand, np.int32), np.ascontiguousarray(Tcw, np.float64).reshape(16),
+            np.ascontiguousarray(cam["intr"], np.float64).reshape(4), np.ascontiguousarray(cam["dist"], np.float64).reshape(4),
+            np.ascontiguousarray(matched, np.uint8)]
+    prm = prm_cls(float(th), int(desc_th_low), int(num_octaves), float(scale_factor))
+    return L, prm, keep, m
+
+
+def search_by_projection(ctx: Context, kf: KfView, kf_lm_cand, Tcw, cam: dict, lms: dict, matched, th=10.0, desc_th_low=50, num_octaves=1,
+                         scale_factor=2.0):
+    """FeatureMatcher::SearchByProjection (feature_matcher_be.cpp:168-291) → (action [m], best_idx [m], n_matches); kf.a['lm_valid'][idx]
+    = pKF->GetLandmark(idx) != nullptr; lms: dict(valid, pos, normal, min_dist, max_dist, max_distance, desc, feat_idx)."""
+    L, prm, keep, m = _proj_args(kf, kf_lm_cand, Tcw, cam, lms, matched, th, desc_th_low, num_octaves, scale_factor, CProjLandmarks, CSearchParams)
+    k = kf.cstruct()
+    action = np.zeros(max(m, 1), np.int32); best = np.full(max(m, 1), -1, np.int32); nm = C.c_int32(0)
+    ctx.check(lib().cvb_search_by_projection(ctx.handle, C.byref(k), keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data, keep[4].ctypes.data,
+                                             int(cam.get("cam_model", 0)), int(cam.get("dist_model", 0)), float(cam.get("xi", 0.0)), C.byref(L),
+                                             keep[5].ctypes.data, C.byref(prm), action.ctypes.data, best.ctypes.data, C.byref(nm)))
+    return action[:m], best[:m], int(nm.value)
+
+
 def _score(ctx, fn, args, n_hyp, n, want_scores, want_inliers):
     sc = np.zeros((n_hyp, n)) if want_scores else None
     inl = np.zeros((n_hyp, n), np.uint8) if want_inliers else None

@@ -175,3 +175,77 @@ def relpose_case(seed: int, n: int = 150, outlier_frac: float = 0.1, pix_noise: 
     T0 = np.concatenate([rot_to_quat(R @ _rot(rng.normal(0, 0.03, 3))), t + rng.normal(0, 0.05, 3)])
     Tgt = np.concatenate([rot_to_quat(R), t])
     return dict(T12=T0, pA_c=pA, pB_c=pB, kpA=kpA.astype(np.float32), kpB=kpB.astype(np.float32), sigmaA=sA, sigmaB=sB, camA=cam, camB=cam), Tgt, out
+
+
+def projection_search_scene(seed: int, n_kp: int = 1000, n_lm: int = 800, cam: dict | None = None, img_w: int = 752, img_h: int = 480):
+    """One keyframe and a list of candidate landmarks ("loop map points") as FeatureMatcher::SearchByProjection sees them
+    (feature_matcher_be.cpp:168-291): a third of the landmarks are already observed by the keyframe (at a keypoint with a WORSE
+    descriptor than another nearby one for some of them → RemapLandmark), some are invalid / behind the camera / seen from
+    behind / out of the distance range, several landmarks compete for the same keypoint."""
+    from .synth_map import EUROC_DIST, EUROC_INTR
+    rng = np.random.default_rng(seed)
+    cam = cam or dict(intr=EUROC_INTR, dist=EUROC_DIST, cam_model=0, dist_model=0, xi=0.0)
+    Tcw = np.eye(4); Tcw[:3, :3] = _rot(rng.normal(0, 0.1, 3)); Tcw[:3, 3] = rng.normal(0, 0.2, 3)
+    Rwc = Tcw[:3, :3].T; Ow = -Rwc @ Tcw[:3, 3]
+    # landmarks in front of the camera (plus a few behind)
+    pc = np.stack([rng.uniform(-4, 4, n_lm), rng.uniform(-2.5, 2.5, n_lm), rng.uniform(3, 12, n_lm)], -1)
+    pc[rng.random(n_lm) < 0.05, 2] *= -1
+    pw = pc @ Rwc.T + Ow                                    # = Rwc pc + Ow
+    d = np.asarray(cam["dist"], float)
+    den = pc[:, 2] + (cam.get("xi", 0.0) * np.linalg.norm(pc, axis=1) if cam.get("cam_model", 0) == 1 else 0.0)
+    x, y = pc[:, 0] / den, pc[:, 1] / den
+    r2 = x * x + y * y
+    if cam.get("dist_model", 0) == 0:
+        rad = 1 + d[0] * r2 + d[1] * r2 * r2
+        xd = x * rad + 2 * d[2] * x * y + d[3] * (r2 + 2 * x * x); yd = y * rad + d[2] * (r2 + 2 * y * y) + 2 * d[3] * x * y
+    else:
+        r = np.sqrt(r2); th = np.arctan(r); t2 = th * th
+        s_ = th * (1 + d[0] * t2 + d[1] * t2 ** 2 + d[2] * t2 ** 3 + d[3] * t2 ** 4) / np.maximum(r, 1e-12)
+        xd, yd = s_ * x, s_ * y
+    uv = np.stack([cam["intr"][0] * xd + cam["intr"][2], cam["intr"][1] * yd + cam["intr"][3]], -1)
+    codes = rng.integers(0, 256, (n_lm, ORB_BYTES), dtype=np.uint8)
+    kp = np.stack([rng.uniform(0, img_w, n_kp), rng.uniform(0, img_h, n_kp)], -1).astype(np.float32)
+    desc = rng.integers(0, 256, (n_kp, ORB_BYTES), dtype=np.uint8)
+    octave = np.zeros(n_kp, np.float32)
+    inimg = np.flatnonzero((pc[:, 2] > 0) & (uv[:, 0] > 5) & (uv[:, 0] < img_w - 5) & (uv[:, 1] > 5) & (uv[:, 1] < img_h - 5))
+    # each visible landmark gets 1-2 keypoints near its projection (a good one and sometimes a decoy with more bit flips); pairs of
+    # landmarks share a projection so that they compete for the same keypoint
+    slots = rng.permutation(n_kp)
+    used = 0
+    good_kp = np.full(n_lm, -1)
+    for j, l in enumerate(inimg[: n_kp // 3]):
+        if j % 7 == 6 and j > 0:
+            uv[l] = uv[inimg[j - 1]]; codes[l] = codes[inimg[j - 1]]                 # competitor of the previous landmark
+            continue
+        k0 = slots[used]; used += 1
+        kp[k0] = uv[l] + rng.normal(0, 1.0, 2); desc[k0] = codes[l] ^ _flip_mask(rng, (ORB_BYTES,)); good_kp[l] = k0
+        if j % 3 == 0:
+            k1 = slots[used]; used += 1
+            kp[k1] = uv[l] + rng.normal(0, 3.0, 2); desc[k1] = codes[l] ^ _flip_mask(rng, (ORB_BYTES,)) ^ _flip_mask(rng, (ORB_BYTES,))
+    valid = (rng.random(n_lm) > 0.05).astype(np.uint8)
+    dist3 = np.linalg.norm(pw - Ow, axis=1)
+    normal = (Ow - pw) / dist3[:, None]                     # facing the camera …
+    flip = rng.random(n_lm) < 0.05; normal[flip] *= -1      # … except a few seen from behind (viewing-angle gate; PO.Pn >= 0.5 d needed)
+    normal = -normal                                        # Pn points from the camera side: PO = p - Ow must align with it
+    max_distance = dist3 * rng.uniform(0.9, 1.15, n_lm)
+    min_dist = 0.8 * max_distance; max_dist = 1.2 * max_distance
+    far = rng.random(n_lm) < 0.05; max_dist[far] = dist3[far] * 0.5            # out of the invariance range
+    # the keyframe already observes a third of the visible landmarks: at a random unrelated keypoint (→ remap candidates) or at
+    # their good keypoint
+    kf_has_lm = np.zeros(n_kp, np.uint8); kf_lm_cand = np.full(n_kp, -1, np.int32); feat_idx = np.full(n_lm, -1, np.int32)
+    for j, l in enumerate(inimg[: n_kp // 3: 3]):
+        k = good_kp[l] if (j % 2 == 0 and good_kp[l] >= 0) else slots[used + j]
+        if kf_has_lm[k]:
+            continue
+        kf_has_lm[k] = 1; kf_lm_cand[k] = l; feat_idx[l] = k
+    extra = slots[-40:]                                     # keypoints holding landmarks that are not in the candidate list
+    extra = extra[kf_has_lm[extra] == 0]; kf_has_lm[extra] = 1
+    matched = np.zeros(n_kp, np.uint8); matched[rng.choice(n_kp, 30, replace=False)] = 1
+    obs_good = [l for l in inimg[: n_kp // 3: 3] if feat_idx[l] >= 0 and feat_idx[l] == good_kp[l]]
+    for l in obs_good[::3]:
+        matched[feat_idx[l]] = 1                            # existing (better) observation is not a search candidate → bDoNotReplace
+    view = dict(kp=kp, octave=octave, desc=desc, lm_valid=kf_has_lm, lm_pos=np.zeros((n_kp, 3)), lm_maxdist=np.ones(n_kp), lm_desc=np.zeros((n_kp, 32), np.uint8),
+                K=np.eye(3), Tcw=Tcw, img_bounds=np.array([0.0, img_w, 0.0, img_h]))
+    lms = dict(valid=valid, pos=pw, normal=normal, min_dist=min_dist, max_dist=max_dist, max_distance=max_distance, desc=codes ^ _flip_mask(rng, (n_lm, ORB_BYTES)),
+               feat_idx=feat_idx)
+    return view, kf_lm_cand, Tcw, cam, lms, matched

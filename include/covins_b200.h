@@ -244,6 +244,32 @@ CVB_API int cvb_search_by_se3_batch(cvb_ctx* ctx, const cvb_kf_view* kf1, const 
                                     int32_t* match2);
 
 /*
+ * Replaces FeatureMatcher::SearchByProjection(pKF, Tcw, vpPoints, vpMatched, th) (feature_matcher_be.cpp:168-291; called at
+ * placerec_be.cpp:194 with the loop map points).  kf: kp / octave / desc / grid / img of pKF, lm_valid[idx] = pKF->GetLandmark(idx)
+ * != nullptr (the other cvb_kf_view fields are not read); kf_lm_cand [n]: index into the candidate list of the landmark that
+ * sits at keypoint idx, -1 if none or not in the list (RemapLandmark bookkeeping, keyframe_be.cpp:484-495); Tcw row-major;
+ * intr/dist + cam_model/dist_model/xi: the camera_->project3 model (as in cvb_ba_problem); matched [n] = vpMatched[idx] != nullptr
+ * on entry.  Per candidate landmark i: action 0 = nothing, 1 = vpMatched[best_idx[i]] = pMP (counted in *n_matches),
+ * 2 = RemapLandmark(pMP, feat_idx[i], best_idx[i]), 3 = already observed and not replaced.  The reference's sequential
+ * semantics (earlier landmarks take keypoints first) are reproduced exactly.
+ */
+typedef struct cvb_proj_landmarks {
+  int32_t m;
+  const uint8_t* valid;        /* [m] !IsInvalid() && not in spAlreadyFound (:177-187) */
+  const double* pos;           /* [m][3] GetWorldPos() */
+  const double* normal;        /* [m][3] GetNormal() */
+  const double* min_dist;      /* [m] GetMinDistanceInvariance() */
+  const double* max_dist;      /* [m] GetMaxDistanceInvariance() */
+  const double* max_distance;  /* [m] max_distance_ (PredictScale) */
+  const uint8_t* desc;         /* [m][32] GetDescriptor() */
+  const int32_t* feat_idx;     /* [m] GetFeatureIndex(pKF) or -1 */
+} cvb_proj_landmarks;
+CVB_API int cvb_search_by_projection(cvb_ctx* ctx, const cvb_kf_view* kf, const int32_t* kf_lm_cand, const double* Tcw, const double* intr,
+                                     const double* dist, int cam_model, int dist_model, double xi, const cvb_proj_landmarks* lms,
+                                     const uint8_t* matched, const cvb_search_params* prm, int32_t* action, int32_t* best_idx,
+                                     int32_t* n_matches);
+
+/*
  * RANSAC hypothesis scoring, batched over hypotheses (the inner loop of opengv's Ransac::computeModel —
  * countWithinDistance / selectWithinDistance over all correspondences — for every hypothesis in one launch; sampling and the
  * minimal solvers stay with the caller, SURVEY §8a V1: "given the same sampled minimal sets, identical scores / inlier masks").

@@ -49,3 +49,19 @@ def score_relative_pose(models, f1, f2, sigma1, sigma2, threshold):
     _k.lib().ora_score_relative_pose(c_vp(m.ctypes.data), H, c_vp(a.ctypes.data), c_vp(b.ctypes.data), c_vp(s1.ctypes.data), c_vp(s2.ctypes.data), n,
                                      C.c_double(threshold), c_vp(sc.ctypes.data), c_vp(inl.ctypes.data), c_vp(cnt.ctypes.data))
     return sc, inl, cnt[:H]
+
+
+class OraProjLandmarks(C.Structure):
+    _fields_ = [("m", C.c_int32)] + [(k, c_vp) for k in ("valid", "pos", "normal", "min_dist", "max_dist", "max_distance", "desc", "feat_idx")]
+
+
+def search_by_projection(kf, kf_lm_cand, Tcw, cam, lms, matched, th=10.0, desc_th_low=50, num_octaves=1, scale_factor=2.0):
+    """→ (action [m], best_idx [m], n_matches); argument meaning as covins_b200.placerec.search_by_projection"""
+    from covins_b200.placerec import _proj_args          # array packing helper only; the struct layouts are declared here
+    L, prm, keep, m = _proj_args(kf, kf_lm_cand, Tcw, cam, lms, matched, th, desc_th_low, num_octaves, scale_factor, OraProjLandmarks, OraSearchParams)
+    k = kf.cstruct(OraKfView)
+    action = np.zeros(max(m, 1), np.int32); best = np.full(max(m, 1), -1, np.int32); nm = C.c_int32(0)
+    _k.lib().ora_search_by_projection(C.byref(k), c_vp(keep[1].ctypes.data), c_vp(keep[2].ctypes.data), c_vp(keep[3].ctypes.data), c_vp(keep[4].ctypes.data),
+                                      int(cam.get("cam_model", 0)), int(cam.get("dist_model", 0)), C.c_double(float(cam.get("xi", 0.0))), C.byref(L),
+                                      c_vp(keep[5].ctypes.data), C.byref(prm), c_vp(action.ctypes.data), c_vp(best.ctypes.data), C.byref(nm))
+    return action[:m], best[:m], int(nm.value)

@@ -195,3 +195,119 @@ API void ora_score_relative_pose(const double* model, int n_hyp, const double* f
     n_inliers[h] = cnt;
   }
 }
+
+/* ---------------------------------------------------------------------------------------------- SearchByProjection
+ * FeatureMatcher::SearchByProjection (feature_matcher_be.cpp:168-291): candidate landmarks are projected into the keyframe
+ * with its full camera model (camera_->project3), gated (image, distance invariance, viewing angle), matched to the best
+ * free keypoint in a radius, and the outcome is applied IN ORDER: a keypoint taken by an earlier landmark (vpMatched) is
+ * skipped by the later ones, RemapLandmark (keyframe_be.cpp:484-495) moves an already-observed landmark to a better
+ * keypoint and erases the observation of the landmark it displaces. */
+typedef struct ora_proj_landmarks {
+  int32_t m;
+  const uint8_t* valid; const double* pos; const double* normal; const double* min_dist; const double* max_dist;
+  const double* max_distance; const uint8_t* desc; const int32_t* feat_idx;
+} ora_proj_landmarks;
+
+static int project3(const double* intr, const double* dist, int cam_model, int dist_model, double xi, const double* pc, double* u, double* v) {
+  double den = pc[2];
+  if (cam_model == 1) den = pc[2] + xi * sqrt(pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2]);
+  if (!(den > 1e-10)) return 0;
+  const double x = pc[0] / den, y = pc[1] / den, r2 = x * x + y * y;
+  double xd, yd;
+  if (dist_model == 0) {
+    const double rad = 1.0 + dist[0] * r2 + dist[1] * r2 * r2;
+    xd = x * rad + 2.0 * dist[2] * x * y + dist[3] * (r2 + 2.0 * x * x);
+    yd = y * rad + dist[2] * (r2 + 2.0 * y * y) + 2.0 * dist[3] * x * y;
+  } else if (dist_model == 1) {
+    const double r = sqrt(r2);
+    double s = 1.0;
+    if (r >= 1e-8) { const double th = atan(r), t2 = th * th; s = th * (1.0 + dist[0] * t2 + dist[1] * t2 * t2 + dist[2] * t2 * t2 * t2 + dist[3] * t2 * t2 * t2 * t2) / r; }
+    xd = s * x; yd = s * y;
+  } else {
+    const double w = dist[0];
+    double s = 1.0;
+    if (w * w >= 1e-5) { const double c = 2.0 * tan(0.5 * w); s = r2 < 1e-5 ? c / w : atan(c * sqrt(r2)) / (w * sqrt(r2)); }
+    xd = s * x; yd = s * y;
+  }
+  *u = intr[0] * xd + intr[2]; *v = intr[1] * yd + intr[3];
+  return 1;
+}
+
+API void ora_search_by_projection(const ora_kf_view* kf, const int32_t* kf_lm_cand_in, const double* Tcw, const double* intr, const double* dist,
+                                  int cam_model, int dist_model, double xi, const ora_proj_landmarks* L, const uint8_t* matched_in,
+                                  const ora_search_params* prm, int32_t* action, int32_t* best_idx, int32_t* n_matches) {
+  const int n = kf->n, m = L->m;
+  uint8_t* matched = (uint8_t*)__builtin_alloca(n > 0 ? n : 1);
+  uint8_t* has_lm = (uint8_t*)__builtin_alloca(n > 0 ? n : 1);
+  int32_t* lm_cand = (int32_t*)__builtin_alloca(sizeof(int32_t) * (n > 0 ? n : 1));
+  int32_t* feat = (int32_t*)__builtin_alloca(sizeof(int32_t) * (m > 0 ? m : 1));
+  for (int i = 0; i < n; i++) { matched[i] = matched_in[i]; has_lm[i] = kf->lm_valid[i]; lm_cand[i] = kf_lm_cand_in[i]; }
+  for (int i = 0; i < m; i++) feat[i] = L->feat_idx[i];
+  /* Ow = -Rcw^T tcw */
+  double Ow[3];
+  for (int r = 0; r < 3; r++) Ow[r] = -((Tcw[r] * Tcw[3] + Tcw[4 + r] * Tcw[7]) + Tcw[8 + r] * Tcw[11]);
+  int nm = 0;
+  for (int i = 0; i < m; i++) {
+    action[i] = 0; best_idx[i] = -1;
+    if (!L->valid[i]) continue;
+    const double* pw = L->pos + 3 * (size_t)i;
+    double pc[3];
+    rt_apply(Tcw, pw, pc);
+    if (pc[2] < 0.0) continue;
+    double u, v;
+    if (!project3(intr, dist, cam_model, dist_model, xi, pc, &u, &v)) continue;
+    if (!in_image(kf, u, v)) continue;
+    const double PO[3] = {pw[0] - Ow[0], pw[1] - Ow[1], pw[2] - Ow[2]};
+    const double d3 = sqrt((PO[0] * PO[0] + PO[1] * PO[1]) + PO[2] * PO[2]);
+    if (d3 < L->min_dist[i] || d3 > L->max_dist[i]) continue;
+    const double* Pn = L->normal + 3 * (size_t)i;
+    if ((PO[0] * Pn[0] + PO[1] * Pn[1]) + PO[2] * Pn[2] < 0.5 * d3) continue;
+    const int level = predict_scale(L->max_distance[i], d3, prm);
+    const double radius = prm->th * pow(prm->scale_factor, (double)level);
+    const float tx = (float)u, ty = (float)v;
+    int min_cx = (int)floor(((double)tx - radius) * kf->grid_w_inv); if (min_cx < 0) min_cx = 0;
+    if (min_cx >= GRID_COLS) continue;
+    int max_cx = (int)ceil(((double)tx + radius) * kf->grid_w_inv); if (max_cx > GRID_COLS - 1) max_cx = GRID_COLS - 1;
+    if (max_cx < 0) continue;
+    int min_cy = (int)floor(((double)ty - radius) * kf->grid_h_inv); if (min_cy < 0) min_cy = 0;
+    if (min_cy >= GRID_ROWS) continue;
+    int max_cy = (int)ceil(((double)ty + radius) * kf->grid_h_inv); if (max_cy > GRID_ROWS - 1) max_cy = GRID_ROWS - 1;
+    if (max_cy < 0) continue;
+    int bd = 256, best = -1;
+    const uint8_t* dl = L->desc + 32 * (size_t)i;
+    for (int ix = min_cx; ix <= max_cx; ix++)
+      for (int iy = min_cy; iy <= max_cy; iy++) {
+        const int c = ix * GRID_ROWS + iy;
+        for (int q = kf->grid_ptr[c]; q < kf->grid_ptr[c + 1]; q++) {
+          const int idx = kf->grid_idx[q];
+          const float dx = kf->kp[2 * (size_t)idx] - tx, dy = kf->kp[2 * (size_t)idx + 1] - ty;
+          if (!((double)sqrtf(dx * dx + dy * dy) <= radius)) continue;
+          if (matched[idx]) continue;                                         /* if (vpMatched[idx]) continue (:239) */
+          const int lvl = (int)kf->octave[idx];
+          if (lvl < level - 1 || lvl > level) continue;
+          const int d = ham256(dl, kf->desc + 32 * (size_t)idx);
+          if (d < bd) { bd = d; best = idx; }
+        }
+      }
+    if (best < 0 || bd > prm->desc_th_low) continue;                          /* bestDist <= desc_matching_th_low_ (:258) */
+    best_idx[i] = best;
+    const int existing = feat[i];
+    if (existing != -1) {                                                     /* already observed (:260-282) */
+      int keep = 0;
+      if (ham256(dl, kf->desc + 32 * (size_t)existing) < bd) keep = 1;
+      if (has_lm[best] && ham256(dl, kf->desc + 32 * (size_t)best) < bd) keep = 1;
+      if (keep) { action[i] = 3; continue; }
+      /* RemapLandmark(pMP, existing, best) (keyframe_be.cpp:484-495) */
+      const int displaced = lm_cand[best];
+      const int had = has_lm[best];
+      has_lm[existing] = 0; lm_cand[existing] = -1;
+      has_lm[best] = 1; lm_cand[best] = i; feat[i] = best;
+      if (had && displaced >= 0) feat[displaced] = -1;                        /* lm_new->EraseObservation(kf) is the LAST statement (:494) */
+      action[i] = 2;
+    } else {
+      matched[best] = 1;                                                      /* vpMatched[bestIdx] = pMP (:285) */
+      action[i] = 1; nm++;
+    }
+  }
+  *n_matches = nm;
+}

@@ -98,7 +98,8 @@ struct Landmark {
   int n_optimized = 0;
   double max_distance_ = 1.0;
   std::array<unsigned char, 32> descriptor_{};
-  double GetMaxDistanceInvariance() const { return max_distance_; }
+  double GetMaxDistanceInvariance() const { return 1.2 * max_distance_; }                    // landmark_base.cpp:68-71
+  double GetMaxDistance() const { return max_distance_; }                                   // the added getter (PredictScale's operand)
   const unsigned char* GetDescriptorPtr() const { return descriptor_.data(); }              // Landmark::GetDescriptor().data
   int GetFeatureIndex(const KeyframePtr& kf) const {
     auto it = observations_.find(kf);
