@@ -310,7 +310,10 @@ def run_ours(args):
     rank, world, local = dist_info()
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        # a rank that dies must end the run (watchdog abort) instead of parking the others for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("COVINS_NCCL_TIMEOUT", "240"))))
     ctx = covins_b200.Context(local)
     dev = torch.device("cuda", local)
     hbm_peak, peak_src = _peaks()

@@ -603,9 +603,17 @@ __global__ void signal_panel_kernel(int* const* __restrict__ peer_flag, int k, c
   }
 }
 // peer: spin on the LOCAL flag (one thread, one CTA: nothing else of this GPU is held up)
-__global__ void wait_panel_kernel(const int* __restrict__ flag, const int* __restrict__ epoch) {
+// A peer that never signals (crashed rank) must not wedge this GPU: after kWaitPanelNs the factorisation is flagged failed.
+constexpr unsigned long long kWaitPanelNs = 20ull * 1000 * 1000 * 1000;
+__global__ void wait_panel_kernel(const int* __restrict__ flag, const int* __restrict__ epoch, int* __restrict__ fail) {
   const int e = *epoch;
-  while (ld_acquire_sys(flag) < e) __nanosleep(200);
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (ld_acquire_sys(flag) < e) {
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > kWaitPanelNs) { atomicExch(fail, 1); return; }
+  }
 }
 
 int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
@@ -692,7 +700,7 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
       }
     } else {
       const int o = plan.h_owner[k];
-      wait_panel_kernel<<<1, 1, 0, s>>>(dv->peer_flag[dv->rank] + k, dv->d_epoch);
+      wait_panel_kernel<<<1, 1, 0, s>>>(dv->peer_flag[dv->rank] + k, dv->d_epoch, d_flag);
       CVB_CHECK_LAUNCH(ctx);
       // the column's tiles are contiguous and sit at the same packed offset on every rank: one NVLink copy each
       CVB_CUDA(ctx, cudaMemcpyAsync(diag, dv->peer_S[o] + (size_t)plan.h_col_base[k] * TT, (size_t)(1 + m) * TT * sizeof(double),

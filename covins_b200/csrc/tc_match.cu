@@ -19,6 +19,7 @@
 // candidate segments.
 #include <float.h>
 #include <limits.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -29,7 +30,9 @@ namespace cvb_tc {
 
 constexpr int TM = 128;       // queries per CTA (UMMA M)
 constexpr int TN = 128;       // train rows per tile (UMMA N)
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;        // shared-memory ring of expanded train tiles
+constexpr int ACC_STAGES = 3;    // TMEM ring of 128-column accumulators: columns [0, 384); the query operand sits at column 384
+constexpr uint32_t A_COL = ACC_STAGES * 128;
 constexpr int NORM_RING = 8;
 constexpr int kInf = 0x3FFFFFFF;   // list sentinel; rows that must never enter carry this as their norm term
 
@@ -40,6 +43,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cvb_smem_addr(bar))
                : "memory");
@@ -54,6 +68,25 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// A operand from tensor memory (row i of the 128 x K block in lane i, four K bytes per 32-bit column): the query block
+// is constant for the CTA's lifetime, and with both operands in shared memory the operand fetch alone (8 KB per 64-cycle
+// instruction) saturates the 128 B/clk shared-memory port that the producers' stores also need.
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// 32 lanes x 8 columns per call: thread t of the warp writes registers r[0..7] to lane (warp % 4) * 32 + t
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -62,6 +95,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 32 lanes x 32 columns, the low 16 bits of two adjacent columns packed into one register (even column low, odd column high)
+__device__ __forceinline__ void tc_ld32_pack16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.pack::16b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -116,21 +160,21 @@ struct TcHamming {
     }
     return pc;
   }
-  // query side: the same permutation with 0/1 bytes, so that accumulator = 128 * popc(a & b) = (2 popc(a & b)) << 6,
-  // which is what the packed 16-bit keys of the epilogue subtract (done once per CTA: plain shifts are fine here)
-  static __device__ __forceinline__ int store_half_q(const uint4 (&v)[kLoads], int half, uint8_t* dst_row0) {
-    const uint32_t w[4] = {v[0].x, v[0].y, v[0].z, v[0].w};
+  // query side (tensor memory, one thread per row): the same K permutation with 0/1 bytes, so that accumulator =
+  // 128 * popc(a & b) = (2 popc(a & b)) << 6, which is what the packed 16-bit keys of the epilogue subtract.  Packed word i
+  // of the row becomes operand bytes [32 i, 32 i + 32) = one K = 32 instruction = 8 TMEM columns.
+  static constexpr int kQWords = 8;   // 32-byte operand groups per row
+  static __device__ __forceinline__ int load_q(const uint8_t* __restrict__ row, uint32_t (&w)[8]) {
+    const uint4 a = ldg_nc(row), b = ldg_nc(row + 16);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
     int pc = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      pc += __popc(w[i]);
-      uint4 lo, hi;
-      lo.x = w[i] & 0x01010101u; lo.y = (w[i] >> 1) & 0x01010101u; lo.z = (w[i] >> 2) & 0x01010101u; lo.w = (w[i] >> 3) & 0x01010101u;
-      hi.x = (w[i] >> 4) & 0x01010101u; hi.y = (w[i] >> 5) & 0x01010101u; hi.z = (w[i] >> 6) & 0x01010101u; hi.w = (w[i] >> 7) & 0x01010101u;
-      *reinterpret_cast<uint4*>(dst_row0 + (8 * half + 2 * i) * 128) = lo;
-      *reinterpret_cast<uint4*>(dst_row0 + (8 * half + 2 * i + 1) * 128) = hi;
-    }
+    for (int i = 0; i < 8; i++) pc += __popc(w[i]);
     return pc;
+  }
+  static __device__ __forceinline__ void expand_q(const uint32_t (&w)[8], int i, uint32_t (&r)[8]) {
+#pragma unroll
+    for (int b = 0; b < 8; b++) r[b] = (w[i] >> b) & 0x01010101u;
   }
 };
 struct TcL2 {
@@ -152,8 +196,20 @@ struct TcL2 {
     }
     return (int)n2;
   }
-  static __device__ __forceinline__ int store_half_q(const uint4 (&v)[kLoads], int half, uint8_t* dst_row0) {
-    return store_half(v, half, dst_row0);
+  static constexpr int kQWords = 4;   // 128 operand bytes per row = 4 groups of 32
+  static __device__ __forceinline__ int load_q(const uint8_t* __restrict__ row, uint32_t (&w)[32]) {
+    unsigned n2 = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const uint4 v = ldg_nc(row + 16 * c);
+      w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+      n2 = __dp4a(v.x, v.x, n2); n2 = __dp4a(v.y, v.y, n2); n2 = __dp4a(v.z, v.z, n2); n2 = __dp4a(v.w, v.w, n2);
+    }
+    return (int)n2;
+  }
+  static __device__ __forceinline__ void expand_q(const uint32_t (&w)[32], int i, uint32_t (&r)[8]) {
+#pragma unroll
+    for (int b = 0; b < 8; b++) r[b] = w[8 * i + b];
   }
 };
 
@@ -197,7 +253,7 @@ constexpr int NUM_THREADS = (MMA_WARP + 1) * 32;
 
 template <class M, int K>
 constexpr size_t smem_bytes() {
-  return (size_t)TM * M::kKBytes + (size_t)STAGES * TN * M::kKBytes + (size_t)NORM_RING * TN * sizeof(int) +
+  return (size_t)STAGES * TN * M::kKBytes + (size_t)NORM_RING * TN * sizeof(int) +
          (size_t)2 * TM * GROUPS * K * 2 * sizeof(int) + 64 * sizeof(uint64_t);
 }
 
@@ -211,19 +267,26 @@ __device__ __forceinline__ uint32_t row_offset(int r) {
 // is what OpenCV compares.  kInfKey is larger than any real key of either kind.
 constexpr int kInfKey = 0x7F000000;
 
+// development trace (COVINS_B200_TC_DEBUG bit 16): clock64 stamps of CTA 0's first tiles, per role
+constexpr int TRACE_TILES = 48;
+__device__ long long g_tc_trace[3][TRACE_TILES][4];
+#define TC_STAMP(role, n, slot)                                                                                 \
+  do {                                                                                                          \
+    if ((p.dbg & 16) && blockIdx.x == 0 && (n) < TRACE_TILES) g_tc_trace[role][n][slot] = clock64();            \
+  } while (0)
+
 template <class M, int K>
 __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int KB = M::kKBytes;
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + (size_t)TM * KB;
+  uint8_t* sB = smem;
   int* sNorm = reinterpret_cast<int*>(sB + (size_t)STAGES * TN * KB);
   int* sList = sNorm + NORM_RING * TN;                       // [2][TM][GROUPS][K][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sList + 2 * TM * GROUPS * K * 2);
-  uint64_t* full = bars;                 // [STAGES] producers → MMA (count 128)
+  uint64_t* full = bars;                 // [STAGES] producers → MMA (one arrival per producer warp)
   uint64_t* empty = bars + STAGES;       // [STAGES] MMA completion → producers (tcgen05.commit)
-  uint64_t* tfull = bars + 2 * STAGES;   // [STAGES] MMA completion → epilogue (tcgen05.commit)
-  uint64_t* tempty = bars + 3 * STAGES;  // [STAGES] epilogue → MMA (count EPI_THREADS)
+  uint64_t* tfull = bars + 2 * STAGES;   // [ACC_STAGES] MMA completion → epilogue (tcgen05.commit)
+  uint64_t* tempty = bars + 3 * STAGES;  // [ACC_STAGES] epilogue → MMA (one arrival per epilogue warp)
   __shared__ uint32_t tmem_base_s;
   __shared__ int sQNorm[TM];
 
@@ -234,10 +297,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
   // ---- one-time setup: barriers, TMEM, the query operand ----
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
-      cvb_mbar_init(&full[s], PROD_THREADS);
+      cvb_mbar_init(&full[s], PROD_THREADS / 32);     // one arrival per producer warp
       cvb_mbar_init(&empty[s], 1);
       cvb_mbar_init(&tfull[s], 1);
-      cvb_mbar_init(&tempty[s], EPI_THREADS);
+      cvb_mbar_init(&tempty[s], EPI_THREADS / 32);    // one arrival per epilogue warp
     }
     cvb_fence_mbar_init();
   }
@@ -245,26 +308,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(cvb_smem_addr(&tmem_base_s)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid < 2 * TM) {
-    const int r = (tid & 7) | ((tid >> 4) << 3), half = (tid >> 3) & 1;   // quarter-warp = 8 rows of one half: conflict-free STS.128
-    const int q = qb * TM + r;
-    uint8_t* dst = sA + row_offset<KB>(r);
-    int nrm = 0;
-    if (q < p.nq) {
-      uint4 v[M::kLoads];
-      M::load_half(p.q + (size_t)q * M::kRowBytes, half, v);
-      nrm = M::store_half_q(v, half, dst);
-    } else {
-      for (int c = 0; c < KB / 32; c++) *reinterpret_cast<uint4*>(dst + (half * (KB / 32) + c) * 128) = make_uint4(0, 0, 0, 0);
-    }
-    nrm += __shfl_xor_sync(0xffffffffu, nrm, 8);
-    if (half == 0) sQNorm[r] = nrm;
-  }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (tid < TM) {
+    // the query block → tensor memory: thread = row = TMEM lane (warps 0-3 own lanes 32 w .. 32 w + 31), 8 columns
+    // (= one K = 32 instruction's worth) per tcgen05.st
+    const int q = qb * TM + tid;
+    uint32_t w[M::kIsL2 ? 32 : 8];
+    int nrm = 0;
+    if (q < p.nq) {
+      nrm = M::load_q(p.q + (size_t)q * M::kRowBytes, w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < (M::kIsL2 ? 32 : 8); i++) w[i] = 0;
+    }
+    sQNorm[tid] = nrm;
+    const uint32_t a_taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + A_COL;
+#pragma unroll
+    for (int i = 0; i < KB / 32; i++) {
+      uint32_t r[8];
+      M::expand_q(w, i, r);
+      tc_st8(a_taddr + 8 * i, r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   if (warp >= PROD_WARP0 && warp < MMA_WARP) {
     // =================================== producers ===================================
@@ -311,7 +383,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
         for (int c = 0; c < M::kLoads; c++) cur[c] = pf[u][c];
         issue_load(pf[u]);   // refill this register slot with the tile PF steps ahead
         const int s = n % STAGES;
+        if (pt == 0) TC_STAMP(0, n, 0);
         if (n >= STAGES) cvb_mbar_wait(&empty[s], ((n / STAGES) - 1) & 1);
+        if (pt == 0) TC_STAMP(0, n, 1);
         uint8_t* dst = sB + (size_t)s * TN * KB + row_offset<KB>(prow);
         const bool rv = it.r0 + prow < it.len;
         int part = 0;
@@ -329,40 +403,49 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
           reinterpret_cast<uint16_t*>(sNorm)[(n % NORM_RING) * TN + prow] =
               rv ? (uint16_t)(((part + 256) << 6) | (prow & 31)) : (uint16_t)0xFFFFu;
         }
+        // every lane makes its own stores visible to the async proxy; ONE arrival per warp (hundreds of same-address
+        // mbarrier arrivals per tile serialise in shared memory and cost more than the tile's MMAs)
+        if (pt == 0) TC_STAMP(0, n, 2);
         fence_proxy_async();
-        mbar_arrive(&full[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (pt == 0) TC_STAMP(0, n, 3);
         it.advance();
         n++;
       }
     }
   } else if (warp == MMA_WARP) {
     // =================================== MMA issuer ===================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc();
-      const uint32_t a_addr = cvb_smem_addr(sA);
-      int n = 0;
-      for (int seg = seg0; seg < seg1; seg++) {
-        const int len = p.seg_ptr[seg + 1] - p.seg_ptr[seg];
-        for (int r0 = 0; r0 < len; r0 += TN, n++) {
-          const int s = n % STAGES;
-          const uint32_t ph = (n / STAGES) & 1;
-          cvb_mbar_wait(&full[s], ph);
-          if (n >= STAGES) cvb_mbar_wait(&tempty[s], ((n / STAGES) - 1) & 1);
-          tc_fence_after();
-          const uint32_t b_addr = cvb_smem_addr(sB + (size_t)s * TN * KB);
-          const uint32_t d_tmem = tmem_base + (uint32_t)s * TN;
+    // The WHOLE warp walks the tile sequence with warp-uniform values and one elected lane issues: under a divergent
+    // `if (lane == 0)` the compiler cannot keep the descriptors in uniform registers and wraps every tcgen05.mma in an
+    // ELECT / R2UR.BROADCAST waterfall loop (~150 cycles per instruction against the 64-cycle tensor floor).
+    const uint32_t idesc = make_idesc();
+    const uint32_t a_tmem = tmem_base + A_COL;
+    const uint32_t b_addr0 = cvb_smem_addr(sB);
+    int n = 0;
+    for (int seg = seg0; seg < seg1; seg++) {
+      const int len = __shfl_sync(0xffffffffu, p.seg_ptr[seg + 1] - p.seg_ptr[seg], 0);
+      for (int r0 = 0; r0 < len; r0 += TN, n++) {
+        const int s = n % STAGES, ts = n % ACC_STAGES;
+        if (lane == 0) TC_STAMP(1, n, 0);
+        cvb_mbar_wait(&full[s], (n / STAGES) & 1);
+        if (lane == 0) TC_STAMP(1, n, 1);
+        if (n >= ACC_STAGES) cvb_mbar_wait(&tempty[ts], ((n / ACC_STAGES) - 1) & 1);
+        if (lane == 0) TC_STAMP(1, n, 2);
+        tc_fence_after();
+        const uint64_t b_desc0 = make_desc(b_addr0 + (uint32_t)s * (TN * KB), 128, KB * 8);
+        const uint32_t d_tmem = tmem_base + (uint32_t)ts * TN;
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < KB / 32; k++) {
-            const uint64_t ad = make_desc(a_addr + k * 256, 128, KB * 8);
-            const uint64_t bd = make_desc(b_addr + k * 256, 128, KB * 8);
-            tc_mma_i8(d_tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
-          }
-          tc_commit(&empty[s]);   // shared-memory slot reusable once these MMAs have read it
-          tc_commit(&tfull[s]);   // accumulator ready
+          for (int k = 0; k < KB / 32; k++)   // K chunk k: 256 B further in shared memory (+16 in the address field), 8 columns in TMEM
+            tc_mma_i8_ts(d_tmem, a_tmem + 8 * k, b_desc0 + (uint64_t)(k * 16), idesc, k > 0 ? 1u : 0u);
+          tc_commit(&empty[s]);    // shared-memory slot reusable once these MMAs have read it
+          tc_commit(&tfull[ts]);   // accumulator ready
         }
+        if (lane == 0) TC_STAMP(1, n, 3);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // =================================== epilogue (warps 0..15) ===================================
     const int grp = warp >> 2;                  // column group
@@ -377,12 +460,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
 #pragma unroll
       for (int c = 0; c < K; c++) { wk[c] = M::kIsL2 ? kInfKey : INT_MAX; wi[c] = -1; wd2[c] = kInf; }
       for (int r0 = 0; r0 < len; r0 += TN, n++) {
-        const int s = n % STAGES;
-        cvb_mbar_wait(&tfull[s], (n / STAGES) & 1);
+        const int s = n % ACC_STAGES;
+        if (tid == 0) TC_STAMP(2, n, 0);
+        cvb_mbar_wait(&tfull[s], (n / ACC_STAGES) & 1);
+        if (tid == 0) TC_STAMP(2, n, 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)s * TN + grp * 32;
         uint32_t acc[32];
-        tc_ld32(taddr, acc);
+        // Hamming: the accumulator 128 * popc(q & t) <= 32768 fits 16 bits, so two adjacent columns are read as ONE packed
+        // register (LDTM.x16.PACK16BIT: even column low, odd column high) — exactly the layout of the packed 16-bit keys
+        const bool pack16 = !M::kIsL2 && !(p.dbg & 8);   // dbg 8: the unpacked read (development comparison)
+        if (p.dbg & 4) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) acc[i] = 0;      // experiment: no TMEM read at all (results invalid)
+        } else if (pack16) {
+          tc_ld32_pack16(taddr, acc);
+        } else {
+          tc_ld32(taddr, acc);
+        }
         if (valid && !(p.dbg & 1)) {
           if (!M::kIsL2) {
             // Two columns per instruction: 16-bit keys ((popc(t) - 2 popc(q & t) + 256) << 6 | column) packed pairwise
@@ -401,7 +496,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
 #pragma unroll
               for (int j = 0; j < 4; j++) {
                 const int i = 8 * i4 + 2 * j;   // columns i (low half) and i + 1 (high half)
-                unsigned x = nv[j] + acc[i] * 0xFFFFFFFFu + acc[i + 1] * 0xFFFF0000u;
+                unsigned x = pack16 ? nv[j] - acc[4 * i4 + j] : nv[j] + acc[i] * 0xFFFFFFFFu + acc[i + 1] * 0xFFFF0000u;
 #pragma unroll
                 for (int c = 0; c < K; c++) {
                   const unsigned lo = __vminu2(pk[c], x);
@@ -450,8 +545,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
             }
           }
         }
+        if (tid == 0) TC_STAMP(2, n, 2);
         tc_fence_before();
-        mbar_arrive(&tempty[s]);   // accumulator and norms consumed: the MMA warp may overwrite this TMEM stage
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[s]);
+        if (tid == 0) TC_STAMP(2, n, 3);   // accumulator and norms consumed: the MMA warp may overwrite this TMEM stage
       }
       // ---- segment finished: combine the 4 column-group lists of each query (k smallest by (key, idx)) ----
       int* lst = sList + (size_t)(segc & 1) * TM * GROUPS * K * 2;
@@ -541,6 +639,21 @@ int launch_tc(cvb_ctx* ctx, const TcParams& p, cudaStream_t st) {
   }
   tc_scan_kernel<M, K><<<p.nqb * p.parts, NUM_THREADS, smem, st>>>(p);
   CVB_CHECK_LAUNCH(ctx);
+  if (p.dbg & 16) {
+    static long long h[3][TRACE_TILES][4];
+    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    CVB_CUDA(ctx, cudaMemcpyFromSymbol(h, g_tc_trace, sizeof(h)));
+    const long long t0 = h[0][0][0];
+    fprintf(stderr, "tile | producer: wait_begin got_slot stored arrived | mma: begin full_ok tempty_ok issued | epilogue: begin tfull_ok done arrived\n");
+    for (int n = 0; n < TRACE_TILES; n++) {
+      fprintf(stderr, "%3d |", n);
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 4; c++) fprintf(stderr, " %7lld", h[r][n][c] - t0);
+        fprintf(stderr, " |");
+      }
+      fprintf(stderr, "\n");
+    }
+  }
   return CVB_OK;
 }
 

@@ -146,8 +146,9 @@ def test_shim_search_by_se3_and_dense_matcher_adaptor(ctx, tmp_path):
     mk = lambda v: PR.KfView(v["kp"], v["octave"], v["desc"], v["lm_valid"], v["lm_pos"], v["lm_maxdist"], v["lm_desc"], v["K"], v["Tcw"], v["img_bounds"])
     k1, k2 = mk(views[0]), mk(views[1])
     zero1, zero2 = np.zeros(k1.n, np.uint8), np.zeros(k2.n, np.uint8)      # the wrapper starts from empty matches12
-    r12, rnf, _, _ = og.search_by_se3(k1, k2, T12, T21, zero1, zero2)
-    assert out[0] == rnf and np.array_equal(out[1:], r12) and rnf > 5
+    r12, rnf, rm1, rm2 = og.search_by_se3(k1, k2, T12, T21, zero1, zero2)
+    # (the reference's agreement rule match2[i] == i, :485-496, lets almost nothing through: nf is tiny by construction)
+    assert out[0] == rnf and np.array_equal(out[1:], r12) and (rm1 >= 0).sum() > 40 and (rm2 >= 0).sum() > 40
     dense = np.fromfile(tmp_path / "dense_out.bin", np.int32).reshape(-1, 3)
     ra, rb, rd = ora.landmark_match(views[0]["desc"], 1 - views[0]["lm_valid"], views[1]["desc"], 1 - views[1]["lm_valid"], 50.0, 4)
     assert np.array_equal(dense[:, 0], ra) and np.array_equal(dense[:, 1], rb) and np.array_equal(dense[:, 2], rd.astype(np.int32)) and len(ra) > 20
