@@ -22,18 +22,23 @@ struct cvb_ctx {
   int64_t launches = 0;
   std::string err;
   // grow-only device workspaces (named slots so independent stages never alias)
-  cvb_buf ws[24];
+  cvb_buf ws[26];
   // pinned host staging
   void* h_pin = nullptr;
   size_t h_pin_cap = 0;
   void* ba = nullptr;  // BA state (owned by ba_*.cu)
+  // resident operand tiles of a train set (set by the map database around its matching call, see tc_match.cu): when the
+  // matcher is handed the packed rows `xt_for`, their pre-expanded tiles are at `xt` / `xt_seg_tile`
+  const uint8_t* xt_for = nullptr;
+  const uint8_t* xt = nullptr;
+  const int32_t* xt_seg_tile = nullptr;
   // every extern "C" entry point holds this lock for its duration (cvb_device_guard): a ctx may be shared between host
   // threads — calls on one ctx are serialised, concurrency comes from one ctx per thread
   mutable std::recursive_mutex mtx;
 };
 
 enum { WS_Q = 0, WS_T, WS_SEG, WS_OUT0, WS_OUT1, WS_OUT2, WS_PART_I, WS_PART_D, WS_LIST_I, WS_LIST_D, WS_SKIPA,
-       WS_SKIPB, WS_TMP0, WS_TMP1, WS_FLAG, WS_MISC, WS_CHUNK_PS, WS_CHUNK_OFF, WS_GS0, WS_GS1, WS_GS2, WS_GS3, WS_GS4, WS_GS5 };
+       WS_SKIPB, WS_TMP0, WS_TMP1, WS_FLAG, WS_MISC, WS_CHUNK_PS, WS_CHUNK_OFF, WS_GS0, WS_GS1, WS_GS2, WS_GS3, WS_GS4, WS_GS5, WS_XT, WS_XT_TILE };
 
 int cvb_fail(cvb_ctx* ctx, int code, const char* fmt, ...);
 void* cvb_ws(cvb_ctx* ctx, int slot, size_t bytes);          // returns nullptr on failure (ctx->err set)

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "cvb_internal.cuh"
+#include "tc_match.cuh"
 
 struct cvb_db {
   int desc_bytes = 32;
@@ -19,6 +20,12 @@ struct cvb_db {
   int32_t* d_seg = nullptr;
   size_t cap_seg = 0;
   bool seg_dirty = true;
+  // the tensor-core matcher's operand tiles of every keyframe (tc_match.cu, "pre-expanded operand tiles"): written once
+  // at append time, 128-row tiles, seg_tile[s] = first tile of keyframe s
+  uint8_t* d_xt = nullptr;
+  size_t cap_tiles = 0;
+  std::vector<int32_t> seg_tile{0};
+  int32_t* d_seg_tile = nullptr;
   // per-query scratch (grow-only)
   cvb_buf q, mt, md, nm, off, out_seg, out_q, out_t, out_d;
 };
@@ -36,6 +43,40 @@ int grow(cvb_ctx* ctx, cvb_buf& b, size_t bytes) {
   const size_t want = std::max<size_t>(256, bytes + bytes / 4);
   CVB_CUDA(ctx, cudaMalloc(&b.p, want));
   b.cap = want;
+  return CVB_OK;
+}
+
+// device copies of the segment tables
+int refresh_seg(cvb_ctx* ctx, cvb_db* db) {
+  if (!db->seg_dirty) return CVB_OK;
+  cudaStream_t st = ctx->stream;
+  if (db->cap_seg < db->seg_ptr.size()) {
+    CVB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (db->d_seg) CVB_CUDA(ctx, cudaFree(db->d_seg));
+    if (db->d_seg_tile) CVB_CUDA(ctx, cudaFree(db->d_seg_tile));
+    db->d_seg = db->d_seg_tile = nullptr;
+    db->cap_seg = db->seg_ptr.size() * 3 / 2 + 16;
+    CVB_CUDA(ctx, cudaMalloc(&db->d_seg, db->cap_seg * sizeof(int32_t)));
+    CVB_CUDA(ctx, cudaMalloc(&db->d_seg_tile, db->cap_seg * sizeof(int32_t)));
+  }
+  CVB_CUDA(ctx, cudaMemcpyAsync(db->d_seg, db->seg_ptr.data(), db->seg_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CVB_CUDA(ctx, cudaMemcpyAsync(db->d_seg_tile, db->seg_tile.data(), db->seg_tile.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CVB_CUDA(ctx, cudaStreamSynchronize(st));
+  db->seg_dirty = false;
+  return CVB_OK;
+}
+
+int reserve_tiles(cvb_ctx* ctx, cvb_db* db, size_t tiles, size_t used_tiles) {
+  if (tiles <= db->cap_tiles) return CVB_OK;
+  const size_t want = std::max(tiles, db->cap_tiles * 3 / 2), tb = cvb_tc::tile_bytes();
+  uint8_t* p = nullptr;
+  CVB_CUDA(ctx, cudaMalloc(&p, want * tb));
+  const size_t used = used_tiles * tb;
+  if (used) CVB_CUDA(ctx, cudaMemcpyAsync(p, db->d_xt, used, cudaMemcpyDeviceToDevice, ctx->stream));
+  CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (db->d_xt) CVB_CUDA(ctx, cudaFree(db->d_xt));
+  db->d_xt = p;
+  db->cap_tiles = want;
   return CVB_OK;
 }
 
@@ -127,6 +168,8 @@ int cvb_db_destroy(cvb_ctx* ctx, cvb_db* db) {
   if (ctx) cudaStreamSynchronize(ctx->stream);
   if (db->d_rows) cudaFree(db->d_rows);
   if (db->d_seg) cudaFree(db->d_seg);
+  if (db->d_seg_tile) cudaFree(db->d_seg_tile);
+  if (db->d_xt) cudaFree(db->d_xt);
   for (cvb_buf* b : {&db->q, &db->mt, &db->md, &db->nm, &db->off, &db->out_seg, &db->out_q, &db->out_t, &db->out_d})
     if (b->p) cudaFree(b->p);
   delete db;
@@ -169,8 +212,20 @@ int cvb_db_append(cvb_ctx* ctx, cvb_db* db, const uint8_t* rows, const int32_t* 
                                   cudaMemcpyHostToDevice, ctx->stream));
     CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `rows` may be freed by the caller on return
   }
-  for (int i = 0; i < n_kf; ++i) db->seg_ptr.push_back(db->seg_ptr.back() + rows_per_kf[i]);
+  const int seg_old = (int)db->seg_ptr.size() - 1, tile_old = db->seg_tile.back();
+  for (int i = 0; i < n_kf; ++i) {
+    db->seg_ptr.push_back(db->seg_ptr.back() + rows_per_kf[i]);
+    db->seg_tile.push_back(db->seg_tile.back() + (rows_per_kf[i] + 127) / 128);
+  }
   db->seg_dirty = true;
+  // the new keyframes' operand tiles (HBM-bound, once per keyframe; every later query reads them through the TMA engine)
+  int rc = reserve_tiles(ctx, db, (size_t)db->seg_tile.back(), (size_t)tile_old);
+  if (rc) return rc;
+  if ((rc = refresh_seg(ctx, db))) return rc;
+  rc = cvb_tc::expand_tiles(ctx, db->d_rows, db->d_seg, db->d_seg_tile, seg_old, seg_old + n_kf, tile_old,
+                            db->seg_tile.back() - tile_old, db->d_xt, ctx->stream);
+  if (rc) return rc;
+  CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return CVB_OK;
 }
 
@@ -188,6 +243,20 @@ int cvb_db_remove(cvb_ctx* ctx, cvb_db* db, int kf_index) {
     CVB_CUDA(ctx, cudaMemcpyAsync(db->d_rows + (size_t)a * db->desc_bytes, tmp, tail, cudaMemcpyDeviceToDevice, ctx->stream));
     CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
+  {   // the same for the operand tiles
+    const size_t tb = cvb_tc::tile_bytes();
+    const int ta = db->seg_tile[kf_index], tbn = db->seg_tile[kf_index + 1], tend = db->seg_tile.back();
+    const size_t ttail = (size_t)(tend - tbn) * tb;
+    if (ttail && tbn > ta) {
+      void* tmp = cvb_ws(ctx, WS_GS2, ttail);
+      if (!tmp) return CVB_ERR_CUDA;
+      CVB_CUDA(ctx, cudaMemcpyAsync(tmp, db->d_xt + (size_t)tbn * tb, ttail, cudaMemcpyDeviceToDevice, ctx->stream));
+      CVB_CUDA(ctx, cudaMemcpyAsync(db->d_xt + (size_t)ta * tb, tmp, ttail, cudaMemcpyDeviceToDevice, ctx->stream));
+      CVB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    db->seg_tile.erase(db->seg_tile.begin() + kf_index + 1);
+    for (size_t i = (size_t)kf_index + 1; i < db->seg_tile.size(); i++) db->seg_tile[i] -= (int32_t)(tbn - ta);
+  }
   db->seg_ptr.erase(db->seg_ptr.begin() + kf_index + 1);
   for (size_t i = (size_t)kf_index + 1; i < db->seg_ptr.size(); i++) db->seg_ptr[i] -= (int32_t)len;
   db->seg_dirty = true;
@@ -199,6 +268,22 @@ int cvb_db_size(const cvb_db* db, int32_t* n_kf, int64_t* n_rows) {
   if (n_kf) *n_kf = (int32_t)db->seg_ptr.size() - 1;
   if (n_rows) *n_rows = db->seg_ptr.back();
   return CVB_OK;
+}
+
+int cvb_db_match_hamming_dev(cvb_ctx* ctx, cvb_db* db, const uint8_t* d_q, int nq, float thr, float ratio,
+                             int32_t* d_match_train, float* d_match_dist, int32_t* d_n_matches, void* stream) {
+  if (!ctx || !db) return CVB_ERR_INVALID;
+  CVB_GUARD(ctx);
+  const int n_seg = (int)db->seg_ptr.size() - 1;
+  CVB_REQUIRE(ctx, nq >= 0 && (nq == 0 || d_q) && (n_seg == 0 || d_n_matches), "cvb_db_match_hamming_dev: bad arguments");
+  if (n_seg == 0) return CVB_OK;
+  int rc = refresh_seg(ctx, db);
+  if (rc) return rc;
+  ctx->xt_for = db->d_rows; ctx->xt = db->d_xt; ctx->xt_seg_tile = db->d_seg_tile;
+  rc = cvb_match_hamming_batch_dev(ctx, d_q, nq, db->d_rows, db->d_seg, db->seg_ptr.data(), n_seg, thr, ratio, d_match_train,
+                                   d_match_dist, d_n_matches, stream);
+  ctx->xt_for = nullptr; ctx->xt = nullptr; ctx->xt_seg_tile = nullptr;
+  return rc;
 }
 
 int cvb_db_match_hamming(cvb_ctx* ctx, cvb_db* db, const uint8_t* q, int nq, float thr, float ratio,
@@ -217,18 +302,7 @@ int cvb_db_match_hamming(cvb_ctx* ctx, cvb_db* db, const uint8_t* q, int nq, flo
   }
   cudaStream_t st = ctx->stream;
   int rc;
-  if (db->seg_dirty) {
-    if (db->cap_seg < db->seg_ptr.size()) {
-      CVB_CUDA(ctx, cudaStreamSynchronize(st));
-      if (db->d_seg) CVB_CUDA(ctx, cudaFree(db->d_seg));
-      db->cap_seg = db->seg_ptr.size() * 3 / 2 + 16;
-      CVB_CUDA(ctx, cudaMalloc(&db->d_seg, db->cap_seg * sizeof(int32_t)));
-    }
-    CVB_CUDA(ctx, cudaMemcpyAsync(db->d_seg, db->seg_ptr.data(), db->seg_ptr.size() * sizeof(int32_t),
-                                  cudaMemcpyHostToDevice, st));
-    CVB_CUDA(ctx, cudaStreamSynchronize(st));
-    db->seg_dirty = false;
-  }
+  if ((rc = refresh_seg(ctx, db))) return rc;
   const size_t on = (size_t)n_seg * nq;
   if ((rc = grow(ctx, db->q, (size_t)nq * 32))) return rc;
   if ((rc = grow(ctx, db->mt, on * 4))) return rc;
@@ -247,8 +321,10 @@ int cvb_db_match_hamming(cvb_ctx* ctx, cvb_db* db, const uint8_t* q, int nq, flo
   if (!pin) return CVB_ERR_CUDA;
   memcpy(pin, q, (size_t)nq * 32);
   CVB_CUDA(ctx, cudaMemcpyAsync(db->q.p, pin, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
+  ctx->xt_for = db->d_rows; ctx->xt = db->d_xt; ctx->xt_seg_tile = db->d_seg_tile;   // resident operand tiles of these rows
   rc = cvb_match_hamming_batch_dev(ctx, (const uint8_t*)db->q.p, nq, db->d_rows, db->d_seg, db->seg_ptr.data(), n_seg,
                                    thr, ratio, (int32_t*)db->mt.p, (float*)db->md.p, (int32_t*)db->nm.p, nullptr);
+  ctx->xt_for = nullptr; ctx->xt = nullptr; ctx->xt_seg_tile = nullptr;
   if (rc) return rc;
   db_offsets_kernel<<<1, 1024, 0, st>>>((const int32_t*)db->nm.p, n_seg, (int32_t*)db->off.p);
   CVB_CHECK_LAUNCH(ctx);

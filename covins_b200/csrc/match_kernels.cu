@@ -699,6 +699,8 @@ int knn_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, const 
     tp.q = d_q; tp.nq = nq; tp.t = d_t; tp.seg_ptr = d_seg_ptr; tp.n_seg = n_seg;
     tp.out_idx = d_idx; tp.out_dist = d_dist; tp.filter = filter ? 1 : 0; tp.thr = thr; tp.ratio = ratio;
     tp.match_train = d_match_train; tp.match_dist = d_match_dist; tp.n_matches = d_n_matches;
+    tp.h_seg = h_seg_ptr;
+    if (ctx->xt_for == d_t && ctx->xt) { tp.xt = ctx->xt; tp.seg_tile = ctx->xt_seg_tile; }
     return cvb_tc::launch(ctx, tp, M::kIsL2 ? 1 : 0, k, st);
   }
   {
@@ -733,6 +735,7 @@ int knn_dev(cvb_ctx* ctx, const uint8_t* d_q, int nq, const uint8_t* d_t, const 
       cvb_tc::TcParams tp{};
       tp.q = d_q; tp.nq = nq; tp.t = d_t; tp.seg_ptr = d_ps; tp.n_seg = n_ps;
       tp.out_idx = part_i; tp.out_dist = part_d; tp.filter = 0;
+      tp.h_seg = h_ps.data();
       if ((rc = cvb_tc::launch(ctx, tp, M::kIsL2 ? 1 : 0, k, st))) return rc;
       int32_t empty_key = INT_MAX;
       if (M::kIsL2) {

@@ -23,6 +23,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "cvb_internal.cuh"
 #include "tc_match.cuh"
 
@@ -106,6 +108,23 @@ __device__ __forceinline__ void tc_ld32_pack16(uint32_t taddr, uint32_t (&r)[32]
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 32 lanes x 128 columns as 64 packed registers
+__device__ __forceinline__ void tc_ld64_pack16(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.pack::16b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+        "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+        "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+        "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -629,6 +648,351 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) tc_scan_kernel(const TcParams 
   }
 }
 
+
+// ===================================================================================================================
+// Hamming k-NN on PRE-EXPANDED operand tiles.
+//
+// The kernel above spends its issue slots on ALU work: producers turn every packed bit into a byte (>= 64 logic
+// operations per row and tile) and the epilogue rebuilds the distance from the accumulator and a per-column term read
+// from shared memory.  Both disappear when the operand the tensor core reads is stored once and reused by every query:
+//
+//   * cvb_tc::expand_tiles writes, per keyframe, ceil(rows / 128) tiles of 128 rows x 288 operand bytes in exactly the
+//     shared-memory image tcgen05.mma wants (K-major, no swizzle, 8-row groups of 2304 B): 256 data bytes (0x80 = -128
+//     as s8 for a set bit) + a 32-byte KEY slice.  A tile is 36 KB and contiguous, so the producer is ONE thread issuing
+//     cp.async.bulk copies (TMA engine) — no register path, no expansion in the matching kernel.  The map database
+//     (map_db.cu) keeps these tiles resident next to the packed rows; 9 bytes of HBM per descriptor byte, read at
+//     ~2 TB/s by a kernel that is bound by the tensor pipe, not by HBM.
+//   * the key slice folds the whole distance into the GEMM: with query bytes 0/2 (u8) and
+//         A key bytes = [1, 128, 128, 128, c4, c5, c6, 0...]   c4 + c5 + c6 = 2 popc(q)      (per query row)
+//         B key bytes = [col, p1, p2, p3, 64, 64, 64, 0...]    p1 + p2 + p3 = popc(t)        (per train row)
+//     the s32 accumulator is  (popc(q) + popc(t) - 2 popc(q & t)) << 7 | col  =  Hamming << 7 | row-in-tile: the sort key
+//     itself, <= 32895, so the epilogue reads it as packed 16-bit pairs (LDTM.PACK16BIT) and runs nothing but the
+//     packed min/max network.  Rows past a keyframe's end carry B key bytes [127,127,127,127,0...] → key 48895, which
+//     never enters a list.
+//   * three segment STREAMS: epilogue group g (4 warps = the 128 TMEM lanes) owns accumulator g and every third
+//     keyframe of the CTA's range; the MMA warp and the producer interleave the three streams' tiles.  A (query,
+//     keyframe) list therefore lives in ONE thread's registers from the first tile to the output — no cross-group
+//     merge, no shared-memory lists, no CTA barrier per keyframe — and three tiles are in different phases at any time.
+namespace xt {
+constexpr int KX = 288;                       // operand bytes per row
+constexpr int NSLICE = KX / 32;               // 9 instructions of K = 32 per tile
+constexpr int TILE_BYTES = TN * KX;           // 36864
+constexpr int XSTAGES = 5;                    // shared-memory ring (180 KB)
+constexpr int NGRP = 3;                       // streams = epilogue groups = accumulators
+constexpr int EPI_WARPS = 4 * NGRP;
+constexpr int TMA_WARP = EPI_WARPS;
+constexpr int MMA_WARP_X = EPI_WARPS + 1;
+constexpr int XTHREADS = (MMA_WARP_X + 1) * 32;
+constexpr uint32_t XA_COL = NGRP * 128;       // query operand: TMEM columns [384, 456)
+constexpr int kKeyInvalid = 32896;            // keys >= this are "no row"
+constexpr size_t kSmemBytes = (size_t)XSTAGES * TILE_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t xrow_off(int r) { return (uint32_t)(r >> 3) * (KX * 8) + (uint32_t)(r & 7) * 16; }
+
+// ---- one-time expansion (also the append path of the map database) ----
+__global__ void __launch_bounds__(256) expand_tiles_kernel(const uint8_t* __restrict__ t, const int32_t* __restrict__ seg_ptr,
+                                                           const int32_t* __restrict__ seg_tile, int seg_lo, int seg_hi,
+                                                           int tile_lo, uint8_t* __restrict__ out) {
+  const int tile = tile_lo + blockIdx.x;
+  int lo = seg_lo, hi = seg_hi - 1;             // the last segment whose first tile is <= tile (skips empty segments)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (seg_tile[mid] <= tile) lo = mid; else hi = mid - 1;
+  }
+  const int s_begin = seg_ptr[lo], len = seg_ptr[lo + 1] - s_begin, r0 = (tile - seg_tile[lo]) * TN;
+  const int pt = threadIdx.x, prow = (pt & 7) | ((pt >> 4) << 3), half = (pt >> 3) & 1;
+  const bool rv = r0 + prow < len;
+  uint8_t* dst = out + (size_t)tile * TILE_BYTES + xrow_off(prow);
+  int part = 0;
+  if (rv) {
+    uint4 v[1];
+    TcHamming::load_half(t + (size_t)(s_begin + r0 + prow) * 32, half, v);
+    part = TcHamming::store_half(v, half, dst);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(dst + (8 * half + c) * 128) = make_uint4(0, 0, 0, 0);
+  }
+  part += __shfl_xor_sync(0xffffffffu, part, 8);
+  if (half == 0) {
+    uint4 key = make_uint4(0x7F7F7F7Fu, 0, 0, 0);
+    if (rv) {
+      const int p1 = min(part, 127), p2 = min(part - p1, 127), p3 = part - p1 - p2;
+      key.x = (uint32_t)prow | ((uint32_t)p1 << 8) | ((uint32_t)p2 << 16) | ((uint32_t)p3 << 24);
+      key.y = 0x00404040u;
+    }
+    *reinterpret_cast<uint4*>(dst + 16 * 128) = key;
+  } else {
+    *reinterpret_cast<uint4*>(dst + 17 * 128) = make_uint4(0, 0, 0, 0);
+  }
+}
+
+// the interleaved tile sequence of a CTA: stream g walks keyframes seg0 + g, seg0 + g + NGRP, ... ; round-robin over the
+// streams that still have tiles.  Producer, MMA warp and (per stream) the epilogue groups generate the same sequence.
+struct Streams {
+  int seg[NGRP], t[NGRP], nt[NGRP], tile0[NGRP];
+  int seg1;
+  const int32_t* seg_tile;
+  __device__ void load(int g) {          // position stream g on its next non-empty keyframe (or past the end)
+    while (seg[g] < seg1) {
+      tile0[g] = seg_tile[seg[g]];
+      nt[g] = seg_tile[seg[g] + 1] - tile0[g];
+      if (nt[g] > 0) break;
+      seg[g] += NGRP;
+    }
+    t[g] = 0;
+  }
+  __device__ void init(int seg0, int seg1_, const int32_t* st) {
+    seg1 = seg1_; seg_tile = st;
+#pragma unroll
+    for (int g = 0; g < NGRP; g++) { seg[g] = seg0 + g; nt[g] = 0; tile0[g] = 0; load(g); }
+  }
+  __device__ bool active(int g) const { return seg[g] < seg1; }
+  __device__ bool any() const { return seg[0] < seg1 || seg[1] < seg1 || seg[2] < seg1; }
+  __device__ void advance(int g) {
+    if (++t[g] >= nt[g]) { seg[g] += NGRP; load(g); }
+  }
+};
+
+template <int K>
+__global__ void __launch_bounds__(XTHREADS, 1) tc_xt_kernel(const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sB = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)XSTAGES * TILE_BYTES);
+  uint64_t* full = bars;                  // [XSTAGES] TMA bytes landed (expect_tx)
+  uint64_t* empty = bars + XSTAGES;       // [XSTAGES] MMAs that read the stage completed (tcgen05.commit)
+  uint64_t* tfull = bars + 2 * XSTAGES;   // [NGRP] accumulator g complete (tcgen05.commit)
+  uint64_t* tempty = tfull + NGRP;        // [NGRP] accumulator g read back by its 4 warps
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qb = blockIdx.x % p.nqb, part = blockIdx.x / p.nqb;
+  const int seg0 = (int)((long)part * p.n_seg / p.parts), seg1 = (int)((long)(part + 1) * p.n_seg / p.parts);
+
+  if (tid == 0) {
+    for (int s = 0; s < XSTAGES; s++) { cvb_mbar_init(&full[s], 1); cvb_mbar_init(&empty[s], 1); }
+    for (int g = 0; g < NGRP; g++) { cvb_mbar_init(&tfull[g], 1); cvb_mbar_init(&tempty[g], 4); }
+    cvb_fence_mbar_init();
+  }
+  if (warp == MMA_WARP_X) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(cvb_smem_addr(&tmem_base_s)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  if (tid < TM) {
+    // query block → tensor memory (thread = row = lane): data bytes 0/2, then the key slice
+    const int q = qb * TM + tid;
+    uint32_t w[8];
+    int pq = 0;
+    if (q < p.nq) {
+      pq = TcHamming::load_q(p.q + (size_t)q * 32, w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) w[i] = 0;
+    }
+    const uint32_t a_taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + XA_COL;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      uint32_t r[8];
+#pragma unroll
+      for (int b = 0; b < 8; b++) r[b] = ((w[i] >> b) & 0x01010101u) * 2u;
+      tc_st8(a_taddr + 8 * i, r);
+    }
+    {
+      const int c4 = min(2 * pq, 255), c5 = min(2 * pq - c4, 255), c6 = 2 * pq - c4 - c5;
+      uint32_t r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (q < p.nq) { r[0] = 0x80808001u; r[1] = (uint32_t)c4 | ((uint32_t)c5 << 8) | ((uint32_t)c6 << 16); }
+      tc_st8(a_taddr + 64, r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == TMA_WARP) {
+    // =================================== producer: one thread, bulk copies ===================================
+    if (lane == 0) {
+      Streams S;
+      S.init(seg0, seg1, p.seg_tile);
+      int n = 0;
+      while (S.any()) {
+#pragma unroll
+        for (int g = 0; g < NGRP; g++) {
+          if (!S.active(g)) continue;
+          const int s = n % XSTAGES;
+          if (n >= XSTAGES) cvb_mbar_wait(&empty[s], ((n / XSTAGES) - 1) & 1);
+          cvb_mbar_expect_tx(&full[s], TILE_BYTES);
+          const uint8_t* src = p.xt + (size_t)(S.tile0[g] + S.t[g]) * TILE_BYTES;
+          uint8_t* dst = sB + (size_t)s * TILE_BYTES;
+#pragma unroll
+          for (int c = 0; c < 4; c++) cvb_bulk_g2s(dst + c * (TILE_BYTES / 4), src + c * (TILE_BYTES / 4), TILE_BYTES / 4, &full[s]);
+          S.advance(g);
+          n++;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP_X) {
+    // =================================== MMA issuer (warp-uniform, one elected lane) ===================================
+    // instruction descriptor: D = s32, A = u8, B = s8, both K-major, N = 128, M = 128
+    const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t a_tmem = tmem_base + XA_COL;
+    const uint32_t b_addr0 = cvb_smem_addr(sB);
+    Streams S;
+    S.init(seg0, seg1, p.seg_tile);
+    int n = 0, j[NGRP] = {0, 0, 0};
+    while (S.any()) {
+#pragma unroll
+      for (int g = 0; g < NGRP; g++) {
+        if (!S.active(g)) continue;
+        const int s = n % XSTAGES;
+        cvb_mbar_wait(&full[s], (n / XSTAGES) & 1);
+        if (j[g] >= 1) cvb_mbar_wait(&tempty[g], (j[g] - 1) & 1);
+        tc_fence_after();
+        const uint64_t b_desc0 = make_desc(b_addr0 + (uint32_t)s * TILE_BYTES, 128, KX * 8);
+        const uint32_t d_tmem = tmem_base + (uint32_t)g * TN;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < NSLICE; k++)
+            tc_mma_i8_ts(d_tmem, a_tmem + 8 * k, b_desc0 + (uint64_t)(k * 16), idesc, k > 0 ? 1u : 0u);
+          tc_commit(&empty[s]);
+          tc_commit(&tfull[g]);
+        }
+        __syncwarp();
+        S.advance(g);
+        j[g]++;
+        n++;
+      }
+    }
+  } else {
+    // =================================== epilogue group g: every NGRP-th keyframe, start to finish ===================================
+    const int g = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const int q = qb * TM + row;
+    const bool valid = q < p.nq;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g * TN;
+    int jt = 0;
+    for (int seg = seg0 + g; seg < seg1; seg += NGRP) {
+      const int nt = p.seg_tile[seg + 1] - p.seg_tile[seg];
+      int wk[K];   // (distance << kIdxBits) + row within the keyframe, ascending
+#pragma unroll
+      for (int c = 0; c < K; c++) wk[c] = INT_MAX;
+      for (int t = 0; t < nt; t++, jt++) {
+        cvb_mbar_wait(&tfull[g], jt & 1);
+        tc_fence_after();
+        uint32_t acc[64];
+        tc_ld64_pack16(taddr, acc);            // 128 columns: register i = columns 2 i (low half) and 2 i + 1 (high half)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[g]);   // accumulator in registers: the MMA warp may start this stream's next tile
+        if (valid && !(p.dbg & 1)) {
+          unsigned pk[K];
+#pragma unroll
+          for (int c = 0; c < K; c++) pk[c] = 0xFFFFFFFFu;
+#pragma unroll
+          for (int i = 0; i < 64; i++) {
+            unsigned x = acc[i];
+#pragma unroll
+            for (int c = 0; c < K; c++) {
+              const unsigned lo = __vminu2(pk[c], x);
+              x = __vmaxu2(pk[c], x);
+              pk[c] = lo;
+            }
+          }
+          // later tiles hold larger row indices: a candidate enters only with a strictly smaller distance than the k-th entry
+          const unsigned best16 = min(pk[0] & 0xFFFFu, pk[0] >> 16);
+          const int worst_d = wk[K - 1] == INT_MAX ? 1024 : (wk[K - 1] >> kIdxBits);
+          if ((int)(best16 >> 7) < worst_d) {
+#pragma unroll
+            for (int c = 0; c < K; c++)
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const unsigned k16 = h ? (pk[c] >> 16) : (pk[c] & 0xFFFFu);
+                int x = k16 >= (unsigned)kKeyInvalid ? INT_MAX : (int)(((k16 >> 7) << kIdxBits) + (unsigned)(t * TN) + (k16 & 127u));
+#pragma unroll
+                for (int cc = 0; cc < K; cc++) {
+                  const int lo = min(wk[cc], x);
+                  x = max(wk[cc], x);
+                  wk[cc] = lo;
+                }
+              }
+          }
+        }
+      }
+      // ---- keyframe finished: this thread holds the complete list of (query row, keyframe) ----
+      int wi[K];
+      float fd[K];
+#pragma unroll
+      for (int c = 0; c < K; c++) {
+        wi[c] = wk[c] == INT_MAX ? -1 : (wk[c] & ((1 << kIdxBits) - 1));
+        wk[c] = wk[c] == INT_MAX ? INT_MAX : (wk[c] >> kIdxBits);
+        fd[c] = (float)wk[c];
+      }
+      if (p.filter) {
+        bool ok = false;
+        if (K >= 2 && valid) {
+          const float dm = fd[0], dn = fd[K >= 2 ? 1 : 0];
+          ok = wi[0] >= 0 && wi[K >= 2 ? 1 : 0] >= 0 && dm <= p.thr && dm < __fmul_rn(p.ratio, dn);
+          const size_t o = (size_t)seg * p.nq + q;
+          p.match_train[o] = ok ? wi[0] : -1;
+          p.match_dist[o] = ok ? dm : FLT_MAX;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0 && b) atomicAdd(&p.n_matches[seg], __popc(b));
+      } else if (valid) {
+        const size_t o = ((size_t)seg * p.nq + q) * K;
+#pragma unroll
+        for (int c = 0; c < K; c++) {
+          p.out_idx[o + c] = wi[c];
+          reinterpret_cast<int32_t*>(p.out_dist)[o + c] = wi[c] >= 0 ? wk[c] : INT_MAX;
+        }
+      }
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP_X) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+template <int K>
+int launch_xt(cvb_ctx* ctx, const TcParams& p, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    CVB_CUDA(ctx, cudaFuncSetAttribute(tc_xt_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    attr = true;
+  }
+  tc_xt_kernel<K><<<p.nqb * p.parts, XTHREADS, kSmemBytes, st>>>(p);
+  CVB_CHECK_LAUNCH(ctx);
+  return CVB_OK;
+}
+}  // namespace xt
+
+int64_t tiles_of(const int32_t* h_seg, int n_seg, std::vector<int32_t>* seg_tile) {
+  int64_t total = 0;
+  if (seg_tile) seg_tile->assign((size_t)n_seg + 1, 0);
+  for (int s = 0; s < n_seg; s++) {
+    total += (h_seg[s + 1] - h_seg[s] + TN - 1) / TN;
+    if (seg_tile) (*seg_tile)[s + 1] = (int32_t)total;
+  }
+  return total;
+}
+size_t tile_bytes() { return xt::TILE_BYTES; }
+
+int expand_tiles(cvb_ctx* ctx, const uint8_t* d_rows, const int32_t* d_seg_ptr, const int32_t* d_seg_tile, int seg_lo, int seg_hi,
+                 int tile_lo, int n_tiles, uint8_t* d_xt, cudaStream_t st) {
+  if (n_tiles <= 0) return CVB_OK;
+  xt::expand_tiles_kernel<<<n_tiles, 256, 0, st>>>(d_rows, d_seg_ptr, d_seg_tile, seg_lo, seg_hi, tile_lo, d_xt);
+  CVB_CHECK_LAUNCH(ctx);
+  return CVB_OK;
+}
+
 template <class M, int K>
 int launch_tc(cvb_ctx* ctx, const TcParams& p, cudaStream_t st) {
   static bool attr = false;
@@ -676,6 +1040,29 @@ int launch(cvb_ctx* ctx, TcParams p, int metric, int k, cudaStream_t st) {
   {
     const char* d = getenv("COVINS_B200_TC_DEBUG");
     p.dbg = d ? atoi(d) : 0;
+  }
+  if (metric == 0 && !(getenv("COVINS_B200_TC_XT") && !strcmp(getenv("COVINS_B200_TC_XT"), "0"))) {
+    if (!p.xt) {
+      // no resident tile store for this train set (raw-pointer API): expand it into the workspace first (HBM-bound pre-pass)
+      CVB_REQUIRE(ctx, p.h_seg != nullptr, "tensor-core Hamming path needs the host copy of the segment table");
+      std::vector<int32_t> h_tile;
+      const int64_t n_tiles = tiles_of(p.h_seg, p.n_seg, &h_tile);
+      int32_t* d_tile = (int32_t*)cvb_ws(ctx, WS_XT_TILE, sizeof(int32_t) * ((size_t)p.n_seg + 1));
+      uint8_t* d_xt = (uint8_t*)cvb_ws(ctx, WS_XT, (size_t)n_tiles * xt::TILE_BYTES);
+      if (!d_tile || !d_xt) return CVB_ERR_CUDA;
+      CVB_CUDA(ctx, cudaMemcpyAsync(d_tile, h_tile.data(), sizeof(int32_t) * ((size_t)p.n_seg + 1), cudaMemcpyHostToDevice, st));
+      CVB_CUDA(ctx, cudaStreamSynchronize(st));   // h_tile goes out of scope
+      const int rc = expand_tiles(ctx, p.t, p.seg_ptr, d_tile, 0, p.n_seg, 0, (int)n_tiles, d_xt, st);
+      if (rc) return rc;
+      p.xt = d_xt;
+      p.seg_tile = d_tile;
+    }
+    switch (k) {
+      case 1: return xt::launch_xt<1>(ctx, p, st);
+      case 2: return xt::launch_xt<2>(ctx, p, st);
+      case 3: return xt::launch_xt<3>(ctx, p, st);
+      default: return xt::launch_xt<4>(ctx, p, st);
+    }
   }
 #define TC_CASE(MM, KK) return launch_tc<MM, KK>(ctx, p, st)
   if (metric == 0) {

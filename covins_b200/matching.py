@@ -143,6 +143,19 @@ class DescriptorDatabase:
                 return (nm,) + tuple(o[:tot.value] for o in out)
             self._cap = int(tot.value * 1.25) + 16
 
+    def match_hamming_dev(self, q, thr: float = 40.0, ratio: float = 0.8):
+        """device request: q = CUDA torch tensor u8 [nq, 32] → (match_train [n_kf, nq] i32, match_dist [n_kf, nq] f32,
+        n_matches [n_kf] i32) as CUDA tensors; no copies (cvb_db_match_hamming_dev)."""
+        import torch
+        n_kf, _ = self.size()
+        nq = q.shape[0]
+        mt = torch.empty((n_kf, nq), dtype=torch.int32, device=q.device)
+        md = torch.empty((n_kf, nq), dtype=torch.float32, device=q.device)
+        nm = torch.empty((n_kf,), dtype=torch.int32, device=q.device)
+        self.ctx.check(lib().cvb_db_match_hamming_dev(self.ctx.handle, self.handle, _ptr(q), nq, thr, ratio, _ptr(mt), _ptr(md), _ptr(nm),
+                                                      _torch_stream()))
+        return mt, md, nm
+
     def close(self):
         if self.handle:
             lib().cvb_db_destroy(self.ctx.handle, self.handle)

@@ -116,6 +116,11 @@ CVB_API int cvb_db_remove(cvb_ctx* ctx, cvb_db* db, int kf_index);
 CVB_API int cvb_db_match_hamming(cvb_ctx* ctx, cvb_db* db, const uint8_t* q, int nq, float thr, float ratio,
                                  int32_t* n_matches, int32_t* m_kf, int32_t* m_query, int32_t* m_train,
                                  float* m_dist, int cap, int32_t* n_total);
+/* device variant of the same request (query already in HBM, dense device outputs as cvb_match_hamming_batch_dev:
+ * d_match_train/d_match_dist [n_kf][nq], d_n_matches [n_kf]; no copies, asynchronous on `stream`).  The database's
+ * keyframes are matched from their resident tensor-core operand tiles (written once by cvb_db_append). */
+CVB_API int cvb_db_match_hamming_dev(cvb_ctx* ctx, cvb_db* db, const uint8_t* d_q, int nq, float thr, float ratio,
+                                     int32_t* d_match_train, float* d_match_dist, int32_t* d_n_matches, void* stream);
 
 /*
  * Replaces the SIFT branch, cv::FlannBasedMatcher()::knnMatch(query, train, out, 2)

@@ -137,3 +137,39 @@ def test_tc_single_long_segment_chunked_equals_scalar(ctx, monkeypatch, metric, 
     if metric == "hamming":
         ri, rd = ora.knn_hamming(q[:64], t, k)
         assert np.array_equal(i1[0, :64].cpu().numpy(), ri) and np.array_equal(d1[0, :64].cpu().numpy(), rd)
+
+
+def test_tc_database_resident_tiles_vs_oracle(ctx, tc):
+    """The map database keeps the tensor-core operand tiles of its keyframes (written at append time): host and device requests,
+    appends in several calls, ragged / empty keyframes and removals must all give the oracle's accepted matches."""
+    import torch
+    desc, _ = synth.orb_keyframes(seed=12, n_kf=16, n_feat=700, n_lm=1200, window=1200)
+    lens = [700, 0, 1, 129, 700, 256, 128, 127, 700, 17, 700, 699, 64, 700, 385]
+    t = np.concatenate([desc[i + 1][:l] for i, l in enumerate(lens)])
+    seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    db = M.DescriptorDatabase(ctx)
+    for a, b in ((0, 1), (1, 6), (6, 15)):
+        db.append(t[seg[a]:seg[b]], lens[a:b])
+    keep = list(range(len(lens)))
+
+    def check():
+        t2 = np.concatenate([t[seg[i]:seg[i + 1]] for i in keep]); seg2 = np.concatenate([[0], np.cumsum([lens[i] for i in keep])]).astype(np.int32)
+        for q in (desc[0], desc[0][:77]):
+            ri, rd = ora.knn_hamming_batch(q, t2, seg2, k=2)
+            omt, omd, onm = ora.ratio_filter(ri, rd.astype(np.float32), 45.0, 0.85)
+            nm, m_kf, m_q, m_t, m_d = db.match_hamming(q, 45.0, 0.85)
+            kf, qq = np.nonzero(omt >= 0)
+            assert np.array_equal(nm, onm) and np.array_equal(m_kf, kf) and np.array_equal(m_q, qq)
+            assert np.array_equal(m_t, omt[kf, qq]) and np.array_equal(m_d, omd[kf, qq])
+            mt, md, dn = db.match_hamming_dev(torch.from_numpy(q).cuda(), 45.0, 0.85)
+            assert np.array_equal(mt.cpu().numpy(), omt) and np.array_equal(dn.cpu().numpy(), onm)
+            assert np.array_equal(md.cpu().numpy()[omt >= 0], omd[omt >= 0])
+
+    check()
+    for victim in (4, 0, len(lens) - 3, 0):
+        db.remove(victim); keep.pop(victim)
+        check()
+    db.append(desc[15][:300], [300]); lens.append(300); t = np.concatenate([t, desc[15][:300]]); seg = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    keep.append(len(lens) - 1)
+    check()
+    db.close()

@@ -22,6 +22,22 @@ for dbg, what in ((0, "full kernel"), (1, "no selection in the epilogue"), (2, "
     e1.record(); torch.cuda.synchronize()
     print(f"dbg={dbg} {what:45s} {e0.elapsed_time(e1)/10:.3f} ms")
 
+# the resident-tile path: database appended once, device requests (kernel only, no expansion pre-pass)
+os.environ["COVINS_B200_TC_DEBUG"] = "0"
+db = M.DescriptorDatabase(ctx, reserve_rows=n_kf * nf)
+db.append(t.cpu().numpy(), [nf] * n_kf)
+for dbg, what in ((0, "resident tiles: full kernel"), (1, "resident tiles: no selection in the epilogue")):
+    os.environ["COVINS_B200_TC_DEBUG"] = str(dbg)
+    for _ in range(3): db.match_hamming_dev(q)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10): db.match_hamming_dev(q)
+    e1.record(); torch.cuda.synchronize()
+    print(f"dbg={dbg} {what:45s} {e0.elapsed_time(e1)/10:.3f} ms")
+os.environ["COVINS_B200_TC_DEBUG"] = "0"
+db.close()
+
 # parity of the packed-read variant against the plain one on data with true matches
 desc, _ = synth.orb_keyframes(5, 64, 1000)
 tt = torch.from_numpy(desc.reshape(-1, 32)).to(dev); qq = tt[:1000].clone()
