@@ -219,6 +219,8 @@ struct Engine {
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     for (auto& e : la_ev) if (e) cudaEventDestroy(e);
     if (fs.bulk) cudaStreamDestroy(fs.bulk);
+    if (fs.fast) cudaStreamDestroy(fs.fast);
+    if (fs.fork_fast) cudaEventDestroy(fs.fork_fast);
     for (int g = 0; g < fs.n_group; g++) { if (fs.group[g]) cudaStreamDestroy(fs.group[g]); if (fs.join[g]) cudaEventDestroy(fs.join[g]); }
     if (fs.fork) cudaEventDestroy(fs.fork);
     lap("events, streams");
@@ -1401,10 +1403,11 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   for (size_t g = 0; g < sb_ranges.size(); g++)
     for (int t = sb_ranges[g].first / TT; t <= (sb_ranges[g].second - 1) / TT; t++) col_group[t] = (int)g;
   // ownership of the tile columns (world > 1): an IMU chain's speed-bias columns — a pure latency chain — stay on one
-  // rank, the remaining (pose) columns go round the ranks in blocks of COVINS_B200_DIST_BLOCK columns (default 1)
+  // rank, the remaining (pose) columns go round the ranks in blocks of COVINS_B200_DIST_BLOCK columns (default 6: every
+  // change of owner puts a flag + a 128 KB NVLink copy on the critical chain, measured ~40 us; profiles/r02_block_sweep_4gpu.txt)
   std::vector<int> h_owner;
   if (E.world > 1) {
-    int blk = 1;
+    int blk = 6;
     if (const char* e = getenv("COVINS_B200_DIST_BLOCK")) blk = std::max(1, atoi(e));
     h_owner.assign(nt, 0);
     int seq = 0;
@@ -1609,10 +1612,10 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
   const size_t s_doubles = E.n_tiles * cvb_chol::T * cvb_chol::T, linv_doubles = (size_t)E.n_c_pad * cvb_chol::T;
   if (E.world > 1) {
     if (cudaMalloc(&E.S_raw, s_doubles * 8) != cudaSuccess || cudaMalloc(&E.linv_raw, linv_doubles * 8) != cudaSuccess ||
-        cudaMalloc(&E.pflag_raw, sizeof(int) * (size_t)E.plan.nt) != cudaSuccess)
+        cudaMalloc(&E.pflag_raw, sizeof(int) * 2 * (size_t)E.plan.nt) != cudaSuccess)
       return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (reduced camera system, %zu bytes)", s_doubles * 8);
     ENG_CUDA(cudaMemsetAsync(E.linv_raw, 0, linv_doubles * 8, E.st));
-    ENG_CUDA(cudaMemsetAsync(E.pflag_raw, 0, sizeof(int) * (size_t)E.plan.nt, E.st));
+    ENG_CUDA(cudaMemsetAsync(E.pflag_raw, 0, sizeof(int) * 2 * (size_t)E.plan.nt, E.st));
     E.S.p = E.S_raw; E.S.n = s_doubles; E.linv.p = E.linv_raw; E.linv.n = linv_doubles;
   } else {
     if (E.S.alloc(s_doubles)) return cvb_fail(E.ctx, CVB_ERR_CUDA, "cudaMalloc failed (reduced camera system, %zu bytes)", s_doubles * 8);
@@ -1627,9 +1630,13 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     int lo = 0, hi = 0;   // lo = numerically greatest = lowest priority
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     ENG_CUDA(cudaStreamCreateWithPriority(&E.fs.bulk, cudaStreamNonBlocking, lo));
-    E.la_ev.assign((size_t)2 * E.plan.nt, nullptr);
+    E.la_ev.assign((size_t)5 * E.plan.nt, nullptr);
     for (auto& e : E.la_ev) ENG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     E.fs.ev = E.la_ev.data();
+    if (!getenv("COVINS_B200_NO_CHAIN_STREAM")) {
+      ENG_CUDA(cudaStreamCreateWithPriority(&E.fs.fast, cudaStreamNonBlocking, hi));
+      ENG_CUDA(cudaEventCreateWithFlags(&E.fs.fork_fast, cudaEventDisableTiming));
+    }
     E.fs.n_group = 8;
     for (int g = 0; g < 8; g++) {
       ENG_CUDA(cudaStreamCreateWithPriority(&E.fs.group[g], cudaStreamNonBlocking, hi));

@@ -659,6 +659,15 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
   int last_bulk = -1;
   bool forked = false;
   std::vector<char> used(n_gs > 0 ? n_gs : 1, 0);
+  // Critical-chain stream (fs->fast, highest priority).  Step k+1's diagonal tile needs from step k only ONE tile of the
+  // panel, L(k+1,k), and ONE update, S(k+1,k+1) -= L(k+1,k) L(k+1,k)^T.  So the chain
+  //     potrf(k) -> solve tile (k+1,k) -> update tile (k+1,k+1) -> potrf(k+1) -> ...
+  // runs on its own stream while the rest of panel k (main stream) and the rest of its updates (main: tile column k+1,
+  // bulk stream: everything else) proceed beside it.  Distributed, the hand-over to the next column's owner moves one
+  // 128 KB tile (flag A) instead of waiting for the whole panel (flag B).
+  cudaStream_t sf = (la && fs->fast) ? fs->fast : nullptr;
+  bool sf_live = false;          // sf has been forked off the main stream
+  int prev_chain = -1;           // previous column handled by the chain (its evA is what step C waits for)
   for (int k = 0; k < nt; k++) {
     const int grp = n_gs > 0 ? plan.h_col_group[k] : -1;
     cudaStream_t s = st;
@@ -686,6 +695,105 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
     double* diag = S + (size_t)plan.h_col_base[k] * TT;
     double* linv_k = linv + (size_t)k * TT;
     const bool mine = !dist || plan.h_owner[k] == dv->rank;
+    const int p0 = plan.h_pair_ptr[k], np = plan.h_pair_ptr[k + 1] - p0;
+    if (sf && grp < 0) {
+      // ------------------------------------ chain column ------------------------------------
+      cudaEvent_t evPanel = ev[5 * k], evBulk = ev[5 * k + 1], evP = ev[5 * k + 2], evD = ev[5 * k + 3], evA = ev[5 * k + 4];
+      if (!sf_live) {              // everything before this column (column groups, plain columns) is on the main stream
+        CVB_CUDA(ctx, cudaEventRecord(fs->fork_fast, st));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(sf, fs->fork_fast, 0));
+        sf_live = true;
+      }
+      const bool has_next = m > 0 && plan.h_row_idx[plan.h_col_ptr[k]] == k + 1;
+      const bool mine_n = has_next && (!dist || plan.h_owner[k + 1] == dv->rank);
+      // does the pair list start with the diagonal pair (k+1, k+1)?  (owner-filtered lists hold it only when column k+1 is ours)
+      const int na = plan.h_pair_split[k];
+      const bool diag_pair = has_next && na > 0 && plan.h_pair_i[p0] == k + 1 && plan.h_pair_j[p0] == k + 1;
+      // A. tile (k,k) is final: column k-1's contribution came with the chain, the bulk updates of the columns <= k-2 were
+      //    waited for by the previous chain step (below) — nothing to wait for here
+      if (mine) {
+        potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, sf>>>(diag, (size_t)T, 0, linv_k, d_flag, nullptr, 0);
+        CVB_CHECK_LAUNCH(ctx);
+      }
+      CVB_CUDA(ctx, cudaEventRecord(evP, sf));
+      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 1], sf);
+      // C. tile (k+1,k): final once column k-1's updates of tile column k are done (evA of the previous chain column)
+      if (has_next) {
+        if (prev_chain >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(sf, ev[5 * prev_chain + 4], 0));
+        if (mine) {
+          trsm_kernel<<<2, TRSM_THREADS, kTrsmSmem, sf>>>(diag + TT, linv_k);
+          CVB_CHECK_LAUNCH(ctx);
+          if (dist) {
+            signal_panel_kernel<<<1, 32, 0, sf>>>(dv->d_peer_flag, k, dv->d_epoch, dv->world, dv->rank);          // flag A
+            CVB_CHECK_LAUNCH(ctx);
+          }
+        } else if (mine_n) {
+          wait_panel_kernel<<<1, 1, 0, sf>>>(dv->peer_flag[dv->rank] + k, dv->d_epoch, d_flag);
+          CVB_CHECK_LAUNCH(ctx);
+          CVB_CUDA(ctx, cudaMemcpyAsync(diag + TT, dv->peer_S[plan.h_owner[k]] + ((size_t)plan.h_col_base[k] + 1) * TT, TT * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, sf));
+        }
+      }
+      // the bulk update of the previous column also writes tile (k+1,k+1) (and everything the next chain step reads): it has
+      // to be complete before the diagonal pair is applied / before potrf(k+1) — the depth-1 lookahead rule
+      if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(sf, ev[5 * last_bulk + 1], 0));
+      if (diag_pair) {
+        syrk_kernel<<<4, SYRK_THREADS, kSyrkSmem, sf>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
+        CVB_CHECK_LAUNCH(ctx);
+      }
+      CVB_CUDA(ctx, cudaEventRecord(evD, sf));
+      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 2], sf);
+      // D. the rest of the panel on the main stream
+      const bool early_tile = has_next && (mine || mine_n);     // tile (k+1,k) was produced / fetched by the chain
+      if (mine) {
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st, evP, 0));
+        const int first = has_next ? 1 : 0;
+        if (m - first > 0) {
+          trsm_kernel<<<2 * (m - first), TRSM_THREADS, kTrsmSmem, st>>>(diag + (size_t)(1 + first) * TT, linv_k);
+          CVB_CHECK_LAUNCH(ctx);
+        }
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st, evD, 0));
+        if (dist) {
+          signal_panel_kernel<<<1, 32, 0, st>>>(dv->d_peer_flag, nt + k, dv->d_epoch, dv->world, dv->rank);       // flag B
+          CVB_CHECK_LAUNCH(ctx);
+        }
+      } else {
+        const int o = plan.h_owner[k];
+        wait_panel_kernel<<<1, 1, 0, st>>>(dv->peer_flag[dv->rank] + nt + k, dv->d_epoch, d_flag);
+        CVB_CHECK_LAUNCH(ctx);
+        const double* src = dv->peer_S[o] + (size_t)plan.h_col_base[k] * TT;
+        if (early_tile) {   // the chain owns tile (k+1,k): copy around it
+          CVB_CUDA(ctx, cudaMemcpyAsync(diag, src, TT * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          if (m > 1) CVB_CUDA(ctx, cudaMemcpyAsync(diag + 2 * (size_t)TT, src + 2 * (size_t)TT, (size_t)(m - 1) * TT * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        } else {
+          CVB_CUDA(ctx, cudaMemcpyAsync(diag, src, (size_t)(1 + m) * TT * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+        CVB_CUDA(ctx, cudaMemcpyAsync(linv_k, dv->peer_linv[o] + (size_t)k * TT, TT * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st, evD, 0));
+      }
+      // E. tile column k+1 (minus the diagonal pair), then "panel k available" for the bulk stream
+      if (m > 0) {
+        CVB_CUDA(ctx, cudaEventRecord(evPanel, st));
+        if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[5 * last_bulk + 1], 0));
+        const int a0 = diag_pair ? 1 : 0;
+        if (na - a0 > 0) {
+          syrk_kernel<<<4 * (na - a0), SYRK_THREADS, kSyrkSmem, st>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0 + a0, plan.d_pair_j + p0 + a0);
+          CVB_CHECK_LAUNCH(ctx);
+        }
+        if (tr) cudaEventRecord(tev[(size_t)k * 5 + 3], st);
+        if (np - na > 0) {
+          CVB_CUDA(ctx, cudaStreamWaitEvent(st2, evPanel, 0));
+          syrk_kernel<<<4 * (np - na), SYRK_THREADS, kSyrkSmem, st2>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0 + na, plan.d_pair_j + p0 + na);
+          CVB_CHECK_LAUNCH(ctx);
+          CVB_CUDA(ctx, cudaEventRecord(evBulk, st2));
+          if (tr) cudaEventRecord(tev[(size_t)k * 5 + 4], st2);
+          last_bulk = k;
+        }
+      }
+      CVB_CUDA(ctx, cudaEventRecord(evA, st));
+      prev_chain = k;
+      continue;
+    }
     if (mine) {
       potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, s>>>(diag, (size_t)T, 0, linv_k, d_flag, nullptr, 0);
       CVB_CHECK_LAUNCH(ctx);
@@ -695,12 +803,12 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
         CVB_CHECK_LAUNCH(ctx);
       }
       if (dist) {
-        signal_panel_kernel<<<1, 32, 0, s>>>(dv->d_peer_flag, k, dv->d_epoch, dv->world, dv->rank);
+        signal_panel_kernel<<<1, 32, 0, s>>>(dv->d_peer_flag, nt + k, dv->d_epoch, dv->world, dv->rank);
         CVB_CHECK_LAUNCH(ctx);
       }
     } else {
       const int o = plan.h_owner[k];
-      wait_panel_kernel<<<1, 1, 0, s>>>(dv->peer_flag[dv->rank] + k, dv->d_epoch, d_flag);
+      wait_panel_kernel<<<1, 1, 0, s>>>(dv->peer_flag[dv->rank] + nt + k, dv->d_epoch, d_flag);
       CVB_CHECK_LAUNCH(ctx);
       // the column's tiles are contiguous and sit at the same packed offset on every rank: one NVLink copy each
       CVB_CUDA(ctx, cudaMemcpyAsync(diag, dv->peer_S[o] + (size_t)plan.h_col_base[k] * TT, (size_t)(1 + m) * TT * sizeof(double),
@@ -711,10 +819,10 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
     if (m > 0) {
       if (tr) cudaEventRecord(tev[(size_t)k * 5 + 2], s);
       const bool la_k = la && grp < 0;
-      const int p0 = plan.h_pair_ptr[k], np = plan.h_pair_ptr[k + 1] - p0, na = la_k ? plan.h_pair_split[k] : np;
+      const int na = la_k ? plan.h_pair_split[k] : np;
       if (la_k) {
-        CVB_CUDA(ctx, cudaEventRecord(ev[2 * k], s));
-        if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(s, ev[2 * last_bulk + 1], 0));
+        CVB_CUDA(ctx, cudaEventRecord(ev[5 * k], s));
+        if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(s, ev[5 * last_bulk + 1], 0));
       }
       if (na > 0) {
         syrk_kernel<<<4 * na, SYRK_THREADS, kSyrkSmem, s>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
@@ -722,15 +830,19 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
       }
       if (tr) cudaEventRecord(tev[(size_t)k * 5 + 3], s);
       if (la_k && np - na > 0) {
-        CVB_CUDA(ctx, cudaStreamWaitEvent(st2, ev[2 * k], 0));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st2, ev[5 * k], 0));
         syrk_kernel<<<4 * (np - na), SYRK_THREADS, kSyrkSmem, st2>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0 + na,
                                                                      plan.d_pair_j + p0 + na);
         CVB_CHECK_LAUNCH(ctx);
-        CVB_CUDA(ctx, cudaEventRecord(ev[2 * k + 1], st2));
+        CVB_CUDA(ctx, cudaEventRecord(ev[5 * k + 1], st2));
         if (tr) cudaEventRecord(tev[(size_t)k * 5 + 4], st2);
         last_bulk = k;
       }
     }
+  }
+  if (sf_live) {   // join the chain stream
+    CVB_CUDA(ctx, cudaEventRecord(fs->fork_fast, sf));
+    CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->fork_fast, 0));
   }
   if (forked)
     for (int g = 0; g < n_gs; g++)
@@ -738,7 +850,7 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
         CVB_CUDA(ctx, cudaEventRecord(fs->join[g], fs->group[g]));
         CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->join[g], 0));
       }
-  if (la && last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[2 * last_bulk + 1], 0));   // join
+  if (la && last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[5 * last_bulk + 1], 0));   // join
   if (tr) {
     cudaStreamSynchronize(st);
     FILE* f = fopen(trace_path, "w");

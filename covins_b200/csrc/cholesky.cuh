@@ -38,7 +38,9 @@ struct TilePlan {
 // Extra streams/events of a factorisation (all events with timing disabled); nullptr → everything on one stream.
 struct FactorStreams {
   cudaStream_t bulk = nullptr;       // low-priority stream of the bulk trailing updates (depth-1 lookahead)
-  cudaEvent_t* ev = nullptr;         // 2 * nt events
+  cudaStream_t fast = nullptr;       // highest-priority stream of the critical chain (diagonal tile -> first panel tile -> next diagonal tile)
+  cudaEvent_t fork_fast = nullptr;
+  cudaEvent_t* ev = nullptr;         // 5 * nt events: panel available, bulk done, diagonal tile done, chain step done, tile column k+1 updated
   cudaStream_t group[8] = {};        // streams of the independent column groups
   int n_group = 0;
   cudaEvent_t fork = nullptr, join[8] = {};
@@ -51,7 +53,7 @@ struct DistView {
   int rank = 0, world = 1;
   double* peer_S[16] = {};       // packed tile arrays of all ranks (own entry = local pointer)
   double* peer_linv[16] = {};
-  int* peer_flag[16] = {};       // [nt] per rank
+  int* peer_flag[16] = {};       // [2 nt] per rank: [k] = first panel tile of column k ready (chain), [nt + k] = whole panel ready
   int* d_epoch = nullptr;        // local factorisation counter (device)
   int** d_peer_flag = nullptr;   // device copy of peer_flag[]
 };

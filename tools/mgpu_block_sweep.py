@@ -14,8 +14,13 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=d
 ctx = covins_b200.Context(local)
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
 p = synth_map.make_config(cfg)
-for blk in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1,2,3,4,6,8".split(","))]:
+for spec in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1,2,3,4,6,8".split(",")):
+    nochain = spec.endswith("nc")            # "6nc" = block 6 without the critical-chain stream
+    blk = int(spec[:-2] if nochain else spec)
     os.environ["COVINS_B200_DIST_BLOCK"] = str(blk)
+    os.environ.pop("COVINS_B200_NO_CHAIN_STREAM", None)
+    if nochain:
+        os.environ["COVINS_B200_NO_CHAIN_STREAM"] = "1"
     s = O.BaSolver(ctx, p, rank=rank, world=world, allreduce=O.torch_allreduce(), p2p=True)
     s.iterate(2); ctx.sync(); dist.barrier()
     s.restart(); s.timing(reset=True); ctx.sync(); dist.barrier()
@@ -25,7 +30,7 @@ for blk in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "1
     r = s.result(); tm = s.timing(); s.close()
     it = max(r["iterations"], 1)
     if rank == 0:
-        print(f"{cfg} world={world} p2p={'on' if s.p2p else 'off'} block={blk}: {1e3 * dt / max(n, 1):.2f} ms/it (factor {tm['factor_ms']/it:.2f}, "
+        print(f"{cfg} world={world} p2p={'on' if s.p2p else 'off'} block={spec}: {1e3 * dt / max(n, 1):.2f} ms/it (factor {tm['factor_ms']/it:.2f}, "
               f"blocks+schur+exchange {tm['build_schur_ms']/it:.2f}, solve {tm['solve_ms']/it:.2f}) final cost {r['final_cost']:.6f}", flush=True)
     dist.barrier()
 dist.destroy_process_group()
