@@ -220,6 +220,7 @@ struct Engine {
     for (auto& e : la_ev) if (e) cudaEventDestroy(e);
     if (fs.bulk) cudaStreamDestroy(fs.bulk);
     if (fs.fast) cudaStreamDestroy(fs.fast);
+    for (int g = 0; g < 8; g++) { if (fs.group_aux[g]) cudaStreamDestroy(fs.group_aux[g]); if (fs.join_aux[g]) cudaEventDestroy(fs.join_aux[g]); }
     if (fs.fork_fast) cudaEventDestroy(fs.fork_fast);
     for (int g = 0; g < fs.n_group; g++) { if (fs.group[g]) cudaStreamDestroy(fs.group[g]); if (fs.join[g]) cudaEventDestroy(fs.join[g]); }
     if (fs.fork) cudaEventDestroy(fs.fork);
@@ -1633,9 +1634,16 @@ int engine_setup(Engine& E, const cvb_ba_problem* p, const cvb_ba_options* o) {
     E.la_ev.assign((size_t)5 * E.plan.nt, nullptr);
     for (auto& e : E.la_ev) ENG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     E.fs.ev = E.la_ev.data();
-    if (!getenv("COVINS_B200_NO_CHAIN_STREAM")) {
+    // the critical-chain streams (cholesky.cu: "chain column"); COVINS_B200_CHAIN_STREAM=0 → the plain depth-1 lookahead
+    const char* cs = getenv("COVINS_B200_CHAIN_STREAM");
+    if (!getenv("COVINS_B200_NO_CHAIN_STREAM") && !(cs && !atoi(cs))) {
       ENG_CUDA(cudaStreamCreateWithPriority(&E.fs.fast, cudaStreamNonBlocking, hi));
       ENG_CUDA(cudaEventCreateWithFlags(&E.fs.fork_fast, cudaEventDisableTiming));
+      if (!getenv("COVINS_B200_NO_GROUP_CHAIN"))
+        for (int g = 0; g < 8; g++) {
+          ENG_CUDA(cudaStreamCreateWithPriority(&E.fs.group_aux[g], cudaStreamNonBlocking, hi));
+          ENG_CUDA(cudaEventCreateWithFlags(&E.fs.join_aux[g], cudaEventDisableTiming));
+        }
     }
     E.fs.n_group = 8;
     for (int g = 0; g < 8; g++) {

@@ -126,6 +126,49 @@ __global__ void __launch_bounds__(TRSM_THREADS, 2) trsm_kernel(double* __restric
     }
 }
 
+// The two small products of the critical chain (see factor(): "chain column"), one 128x128 tile each:
+//   MODE 0:  C = P Q^T            (solve of the first panel tile: P = C = S(k+1,k) in place, Q = L(k,k)^-1)
+//   MODE 1:  C -= P Q^T, j <= i   (update of the next diagonal tile: P = Q = L(k+1,k), C = S(k+1,k+1))
+// The throughput kernels above give a tile to 2-4 CTAs (8.7 us of DMMA each); on the chain only latency counts, so the tile
+// is spread over 64 CTAs x 2 rows: a CTA stages Q (128 KB, L2-resident, 8-byte cp.async, row stride 129 doubles) and its own
+// two rows of P, then every thread owns one output column (plain FP64 FMAs: 2 x 128 per thread).  ~3 us per launch.
+constexpr int CHAIN_ROWS = 2;
+constexpr int CHAIN_LDQ = T + 1;
+constexpr size_t kChainSmem = ((size_t)T * CHAIN_LDQ + (size_t)CHAIN_ROWS * T) * sizeof(double);
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(cvb_smem_addr(smem)), "l"(gmem) : "memory");
+}
+template <int MODE>
+__global__ void __launch_bounds__(T, 1) chain_gemm_kernel(double* __restrict__ C, const double* P, const double* Q) {
+  extern __shared__ __align__(16) double smem_d[];
+  double* Qs = smem_d;                          // [T][CHAIN_LDQ]
+  double* Ps = smem_d + (size_t)T * CHAIN_LDQ;  // [CHAIN_ROWS][T]
+  const int j = threadIdx.x, i0 = blockIdx.x * CHAIN_ROWS;
+#pragma unroll 16
+  for (int r = 0; r < T; r++) cp_async8(Qs + (size_t)r * CHAIN_LDQ + j, Q + (size_t)r * T + j);
+#pragma unroll
+  for (int r = 0; r < CHAIN_ROWS; r++) cp_async8(Ps + r * T + j, P + (size_t)(i0 + r) * T + j);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  double acc[CHAIN_ROWS];
+#pragma unroll
+  for (int r = 0; r < CHAIN_ROWS; r++) acc[r] = 0.0;
+  const double* qrow = Qs + (size_t)j * CHAIN_LDQ;
+#pragma unroll 8
+  for (int c = 0; c < T; c++) {
+    const double qv = qrow[c];
+#pragma unroll
+    for (int r = 0; r < CHAIN_ROWS; r++) acc[r] = fma(Ps[r * T + c], qv, acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < CHAIN_ROWS; r++) {
+    double* dst = C + (size_t)(i0 + r) * T + j;
+    if (MODE == 0) *dst = acc[r];
+    else if (j <= i0 + r) *dst -= acc[r];
+  }
+}
+
 // A(i,j) -= A(i,k) A(j,k)^T for the tile pairs (i >= j) of column k's non-zero rows: pi[]/pj[] enumerate them.
 // Four CTAs per pair, one 64x64 quadrant each (consecutive CTAs share the pair's operands in L2); the quadrant above
 // the diagonal of a diagonal tile is skipped.
@@ -623,6 +666,8 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
     CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
     CVB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     CVB_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
+    CVB_CUDA(ctx, cudaFuncSetAttribute(chain_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
+    CVB_CUDA(ctx, cudaFuncSetAttribute(chain_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
     attr = true;
   }
   const int nt = plan.nt;
@@ -668,6 +713,24 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
   cudaStream_t sf = (la && fs->fast) ? fs->fast : nullptr;
   bool sf_live = false;          // sf has been forked off the main stream
   int prev_chain = -1;           // previous column handled by the chain (its evA is what step C waits for)
+  // The column groups (IMU chains) are pure chains: the same split with the group's stream as the chain stream and a second
+  // stream per group for the rest of the panel and all of its (small) updates.
+  const bool grp_chain = sf != nullptr && n_gs > 0 && fs->group_aux[0] != nullptr;
+  int prev_chain_g[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+  int rc_join = 0;
+  auto join_groups = [&]() -> int {
+    for (int g = 0; g < n_gs; g++)
+      if (used[g]) {
+        if (grp_chain) {
+          CVB_CUDA(ctx, cudaEventRecord(fs->join_aux[g], fs->group_aux[g]));
+          CVB_CUDA(ctx, cudaStreamWaitEvent(fs->group[g], fs->join_aux[g], 0));
+        }
+        CVB_CUDA(ctx, cudaEventRecord(fs->join[g], fs->group[g]));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->join[g], 0));
+        used[g] = 0;
+      }
+    return CVB_OK;
+  };
   for (int k = 0; k < nt; k++) {
     const int grp = n_gs > 0 ? plan.h_col_group[k] : -1;
     cudaStream_t s = st;
@@ -679,15 +742,11 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
       s = fs->group[grp % n_gs];
       if (!used[grp % n_gs]) {
         CVB_CUDA(ctx, cudaStreamWaitEvent(s, fs->fork, 0));
+        if (grp_chain) CVB_CUDA(ctx, cudaStreamWaitEvent(fs->group_aux[grp % n_gs], fs->fork, 0));
         used[grp % n_gs] = 1;
       }
     } else if (forked) {   // first column after the grouped ones: join
-      for (int g = 0; g < n_gs; g++)
-        if (used[g]) {
-          CVB_CUDA(ctx, cudaEventRecord(fs->join[g], fs->group[g]));
-          CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->join[g], 0));
-          used[g] = 0;
-        }
+      if ((rc_join = join_groups())) return rc_join;
       forked = false;
     }
     if (tr) cudaEventRecord(tev[(size_t)k * 5 + 0], s);
@@ -696,91 +755,97 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
     double* linv_k = linv + (size_t)k * TT;
     const bool mine = !dist || plan.h_owner[k] == dv->rank;
     const int p0 = plan.h_pair_ptr[k], np = plan.h_pair_ptr[k + 1] - p0;
-    if (sf && grp < 0) {
+    if (sf && (grp < 0 || grp_chain)) {
       // ------------------------------------ chain column ------------------------------------
       cudaEvent_t evPanel = ev[5 * k], evBulk = ev[5 * k + 1], evP = ev[5 * k + 2], evD = ev[5 * k + 3], evA = ev[5 * k + 4];
-      if (!sf_live) {              // everything before this column (column groups, plain columns) is on the main stream
+      const bool is_grp = grp >= 0;
+      const int gi = is_grp ? grp % n_gs : 0;
+      if (!is_grp && !sf_live) {   // everything before this column (column groups, plain columns) is on the main stream
         CVB_CUDA(ctx, cudaEventRecord(fs->fork_fast, st));
         CVB_CUDA(ctx, cudaStreamWaitEvent(sf, fs->fork_fast, 0));
         sf_live = true;
       }
+      cudaStream_t cs = is_grp ? fs->group[gi] : sf;        // chain stream of this column
+      cudaStream_t ws = is_grp ? fs->group_aux[gi] : st;    // its work stream (rest of the panel, tile column k+1)
+      int& pc = is_grp ? prev_chain_g[gi] : prev_chain;     // previous chain column of this sequence
+      const int lb = is_grp ? -1 : last_bulk;               // column groups have no bulk stream: all their updates are small
       const bool has_next = m > 0 && plan.h_row_idx[plan.h_col_ptr[k]] == k + 1;
       const bool mine_n = has_next && (!dist || plan.h_owner[k + 1] == dv->rank);
       // does the pair list start with the diagonal pair (k+1, k+1)?  (owner-filtered lists hold it only when column k+1 is ours)
-      const int na = plan.h_pair_split[k];
-      const bool diag_pair = has_next && na > 0 && plan.h_pair_i[p0] == k + 1 && plan.h_pair_j[p0] == k + 1;
+      const int na = is_grp ? np : plan.h_pair_split[k];
+      const bool diag_pair = has_next && np > 0 && plan.h_pair_i[p0] == k + 1 && plan.h_pair_j[p0] == k + 1;
       // A. tile (k,k) is final: column k-1's contribution came with the chain, the bulk updates of the columns <= k-2 were
       //    waited for by the previous chain step (below) — nothing to wait for here
       if (mine) {
-        potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, sf>>>(diag, (size_t)T, 0, linv_k, d_flag, nullptr, 0);
+        potrf_inv_kernel<<<1, POTRF_THREADS, kPotrfSmem, cs>>>(diag, (size_t)T, 0, linv_k, d_flag, nullptr, 0);
         CVB_CHECK_LAUNCH(ctx);
       }
-      CVB_CUDA(ctx, cudaEventRecord(evP, sf));
-      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 1], sf);
+      CVB_CUDA(ctx, cudaEventRecord(evP, cs));
+      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 1], cs);
       // C. tile (k+1,k): final once column k-1's updates of tile column k are done (evA of the previous chain column)
       if (has_next) {
-        if (prev_chain >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(sf, ev[5 * prev_chain + 4], 0));
+        if (pc >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(cs, ev[5 * pc + 4], 0));
         if (mine) {
-          trsm_kernel<<<2, TRSM_THREADS, kTrsmSmem, sf>>>(diag + TT, linv_k);
+          chain_gemm_kernel<0><<<T / CHAIN_ROWS, T, kChainSmem, cs>>>(diag + TT, diag + TT, linv_k);
           CVB_CHECK_LAUNCH(ctx);
-          if (dist) {
-            signal_panel_kernel<<<1, 32, 0, sf>>>(dv->d_peer_flag, k, dv->d_epoch, dv->world, dv->rank);          // flag A
+          if (dist && !is_grp) {     // (a column group stays on one rank: nobody waits for its flag A)
+            signal_panel_kernel<<<1, 32, 0, cs>>>(dv->d_peer_flag, k, dv->d_epoch, dv->world, dv->rank);          // flag A
             CVB_CHECK_LAUNCH(ctx);
           }
         } else if (mine_n) {
-          wait_panel_kernel<<<1, 1, 0, sf>>>(dv->peer_flag[dv->rank] + k, dv->d_epoch, d_flag);
+          wait_panel_kernel<<<1, 1, 0, cs>>>(dv->peer_flag[dv->rank] + k, dv->d_epoch, d_flag);
           CVB_CHECK_LAUNCH(ctx);
           CVB_CUDA(ctx, cudaMemcpyAsync(diag + TT, dv->peer_S[plan.h_owner[k]] + ((size_t)plan.h_col_base[k] + 1) * TT, TT * sizeof(double),
-                                        cudaMemcpyDeviceToDevice, sf));
+                                        cudaMemcpyDeviceToDevice, cs));
         }
       }
       // the bulk update of the previous column also writes tile (k+1,k+1) (and everything the next chain step reads): it has
       // to be complete before the diagonal pair is applied / before potrf(k+1) — the depth-1 lookahead rule
-      if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(sf, ev[5 * last_bulk + 1], 0));
+      if (lb >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(cs, ev[5 * lb + 1], 0));
       if (diag_pair) {
-        syrk_kernel<<<4, SYRK_THREADS, kSyrkSmem, sf>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0, plan.d_pair_j + p0);
+        chain_gemm_kernel<1><<<T / CHAIN_ROWS, T, kChainSmem, cs>>>(S + (size_t)plan.h_col_base[k + 1] * TT, diag + TT, diag + TT);
         CVB_CHECK_LAUNCH(ctx);
       }
-      CVB_CUDA(ctx, cudaEventRecord(evD, sf));
-      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 2], sf);
-      // D. the rest of the panel on the main stream
+      CVB_CUDA(ctx, cudaEventRecord(evD, cs));
+      if (tr) cudaEventRecord(tev[(size_t)k * 5 + 2], cs);
+      // D. the rest of the panel on the work stream
       const bool early_tile = has_next && (mine || mine_n);     // tile (k+1,k) was produced / fetched by the chain
       if (mine) {
-        CVB_CUDA(ctx, cudaStreamWaitEvent(st, evP, 0));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(ws, evP, 0));
         const int first = has_next ? 1 : 0;
         if (m - first > 0) {
-          trsm_kernel<<<2 * (m - first), TRSM_THREADS, kTrsmSmem, st>>>(diag + (size_t)(1 + first) * TT, linv_k);
+          trsm_kernel<<<2 * (m - first), TRSM_THREADS, kTrsmSmem, ws>>>(diag + (size_t)(1 + first) * TT, linv_k);
           CVB_CHECK_LAUNCH(ctx);
         }
-        CVB_CUDA(ctx, cudaStreamWaitEvent(st, evD, 0));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(ws, evD, 0));
         if (dist) {
-          signal_panel_kernel<<<1, 32, 0, st>>>(dv->d_peer_flag, nt + k, dv->d_epoch, dv->world, dv->rank);       // flag B
+          signal_panel_kernel<<<1, 32, 0, ws>>>(dv->d_peer_flag, nt + k, dv->d_epoch, dv->world, dv->rank);       // flag B
           CVB_CHECK_LAUNCH(ctx);
         }
       } else {
         const int o = plan.h_owner[k];
-        wait_panel_kernel<<<1, 1, 0, st>>>(dv->peer_flag[dv->rank] + nt + k, dv->d_epoch, d_flag);
+        wait_panel_kernel<<<1, 1, 0, ws>>>(dv->peer_flag[dv->rank] + nt + k, dv->d_epoch, d_flag);
         CVB_CHECK_LAUNCH(ctx);
         const double* src = dv->peer_S[o] + (size_t)plan.h_col_base[k] * TT;
         if (early_tile) {   // the chain owns tile (k+1,k): copy around it
-          CVB_CUDA(ctx, cudaMemcpyAsync(diag, src, TT * sizeof(double), cudaMemcpyDeviceToDevice, st));
-          if (m > 1) CVB_CUDA(ctx, cudaMemcpyAsync(diag + 2 * (size_t)TT, src + 2 * (size_t)TT, (size_t)(m - 1) * TT * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          CVB_CUDA(ctx, cudaMemcpyAsync(diag, src, TT * sizeof(double), cudaMemcpyDeviceToDevice, ws));
+          if (m > 1) CVB_CUDA(ctx, cudaMemcpyAsync(diag + 2 * (size_t)TT, src + 2 * (size_t)TT, (size_t)(m - 1) * TT * sizeof(double), cudaMemcpyDeviceToDevice, ws));
         } else {
-          CVB_CUDA(ctx, cudaMemcpyAsync(diag, src, (size_t)(1 + m) * TT * sizeof(double), cudaMemcpyDeviceToDevice, st));
+          CVB_CUDA(ctx, cudaMemcpyAsync(diag, src, (size_t)(1 + m) * TT * sizeof(double), cudaMemcpyDeviceToDevice, ws));
         }
-        CVB_CUDA(ctx, cudaMemcpyAsync(linv_k, dv->peer_linv[o] + (size_t)k * TT, TT * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        CVB_CUDA(ctx, cudaStreamWaitEvent(st, evD, 0));
+        CVB_CUDA(ctx, cudaMemcpyAsync(linv_k, dv->peer_linv[o] + (size_t)k * TT, TT * sizeof(double), cudaMemcpyDeviceToDevice, ws));
+        CVB_CUDA(ctx, cudaStreamWaitEvent(ws, evD, 0));
       }
       // E. tile column k+1 (minus the diagonal pair), then "panel k available" for the bulk stream
       if (m > 0) {
-        CVB_CUDA(ctx, cudaEventRecord(evPanel, st));
-        if (last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[5 * last_bulk + 1], 0));
+        CVB_CUDA(ctx, cudaEventRecord(evPanel, ws));
+        if (lb >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(ws, ev[5 * lb + 1], 0));
         const int a0 = diag_pair ? 1 : 0;
         if (na - a0 > 0) {
-          syrk_kernel<<<4 * (na - a0), SYRK_THREADS, kSyrkSmem, st>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0 + a0, plan.d_pair_j + p0 + a0);
+          syrk_kernel<<<4 * (na - a0), SYRK_THREADS, kSyrkSmem, ws>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0 + a0, plan.d_pair_j + p0 + a0);
           CVB_CHECK_LAUNCH(ctx);
         }
-        if (tr) cudaEventRecord(tev[(size_t)k * 5 + 3], st);
+        if (tr) cudaEventRecord(tev[(size_t)k * 5 + 3], ws);
         if (np - na > 0) {
           CVB_CUDA(ctx, cudaStreamWaitEvent(st2, evPanel, 0));
           syrk_kernel<<<4 * (np - na), SYRK_THREADS, kSyrkSmem, st2>>>(S, plan.d_tile_of, nt, k, plan.d_pair_i + p0 + na, plan.d_pair_j + p0 + na);
@@ -790,8 +855,8 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
           last_bulk = k;
         }
       }
-      CVB_CUDA(ctx, cudaEventRecord(evA, st));
-      prev_chain = k;
+      CVB_CUDA(ctx, cudaEventRecord(evA, ws));
+      pc = k;
       continue;
     }
     if (mine) {
@@ -844,12 +909,7 @@ int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& p
     CVB_CUDA(ctx, cudaEventRecord(fs->fork_fast, sf));
     CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->fork_fast, 0));
   }
-  if (forked)
-    for (int g = 0; g < n_gs; g++)
-      if (used[g]) {
-        CVB_CUDA(ctx, cudaEventRecord(fs->join[g], fs->group[g]));
-        CVB_CUDA(ctx, cudaStreamWaitEvent(st, fs->join[g], 0));
-      }
+  if (forked && (rc_join = join_groups())) return rc_join;
   if (la && last_bulk >= 0) CVB_CUDA(ctx, cudaStreamWaitEvent(st, ev[5 * last_bulk + 1], 0));   // join
   if (tr) {
     cudaStreamSynchronize(st);

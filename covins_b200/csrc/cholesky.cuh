@@ -41,7 +41,9 @@ struct FactorStreams {
   cudaStream_t fast = nullptr;       // highest-priority stream of the critical chain (diagonal tile -> first panel tile -> next diagonal tile)
   cudaEvent_t fork_fast = nullptr;
   cudaEvent_t* ev = nullptr;         // 5 * nt events: panel available, bulk done, diagonal tile done, chain step done, tile column k+1 updated
-  cudaStream_t group[8] = {};        // streams of the independent column groups
+  cudaStream_t group[8] = {};        // streams of the independent column groups (their chain streams)
+  cudaStream_t group_aux[8] = {};    // second stream per group: rest of the panel + updates, beside the group's chain
+  cudaEvent_t join_aux[8] = {};
   int n_group = 0;
   cudaEvent_t fork = nullptr, join[8] = {};
 };
