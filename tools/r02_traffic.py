@@ -4,7 +4,8 @@ to a capture, not pasted).  Usage: python tools/r02_traffic.py"""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CAPS = {"syrk_kernel": ["gpurun_out/r02_prof_syrk.ncu-rep", "gpurun_out/prof_syrk_final.ncu-rep"],
-        "tc_scan_kernel_hamming": ["gpurun_out/r02_prof_tc.ncu-rep", "gpurun_out/prof_tc_final.ncu-rep"]}
+        "tc_scan_kernel_hamming": ["gpurun_out/r02_prof_tc.ncu-rep", "gpurun_out/prof_tc_final.ncu-rep"],
+        "tc_xt_kernel": ["gpurun_out/r02_prof_tc_xt.ncu-rep"]}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
 for key, cands in CAPS.items():
