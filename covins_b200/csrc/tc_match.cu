@@ -685,6 +685,8 @@ constexpr int MMA_WARP_X = EPI_WARPS + 1;
 constexpr int XTHREADS = (MMA_WARP_X + 1) * 32;
 constexpr uint32_t XA_COL = NGRP * 128;       // query operand: TMEM columns [384, 456)
 constexpr int kKeyInvalid = 32896;            // keys >= this are "no row"
+constexpr int kPaceWindow = 96;               // tiles a CTA may run ahead of the slowest CTA of its keyframe range (3.4 MB)
+constexpr long kPaceMinTiles = 1536;          // pacing only when a CTA walks more tiles than this
 constexpr size_t kSmemBytes = (size_t)XSTAGES * TILE_BYTES + 1024;
 
 __device__ __forceinline__ uint32_t xrow_off(int r) { return (uint32_t)(r >> 3) * (KX * 8) + (uint32_t)(r & 7) * 16; }
@@ -823,6 +825,22 @@ __global__ void __launch_bounds__(XTHREADS, 1) tc_xt_kernel(const TcParams p) {
         for (int g = 0; g < NGRP; g++) {
           if (!S.active(g)) continue;
           const int s = n % XSTAGES;
+          if (p.progress != nullptr && (n & 15) == 0 && n > 0) {
+            // Pacing (large maps only): the nqb CTAs that walk the same keyframe range read every tile once from HBM and
+            // nqb - 1 times from L2 — as long as they stay within an L2's worth of each other.  Over thousands of tiles they
+            // drift apart (C5: 4448 tiles per CTA → 8x the HBM traffic, 4.8x the time); the producer therefore publishes its
+            // position every 16 tiles and waits while it is more than kPaceWindow tiles ahead of the slowest CTA of its group.
+            // (All CTAs are resident — grid <= SM count, one CTA per SM — so the wait cannot deadlock.)
+            volatile int* grp_prog = p.progress + (size_t)part * p.nqb;
+            grp_prog[qb] = n;
+            __threadfence();
+            for (;;) {
+              int mn = INT_MAX;
+              for (int i = 0; i < p.nqb; i++) mn = min(mn, grp_prog[i]);
+              if (mn + kPaceWindow >= n) break;
+              __nanosleep(500);
+            }
+          }
           if (n >= XSTAGES) cvb_mbar_wait(&empty[s], ((n / XSTAGES) - 1) & 1);
           cvb_mbar_expect_tx(&full[s], TILE_BYTES);
           const uint8_t* src = p.xt + (size_t)(S.tile0[g] + S.t[g]) * TILE_BYTES;
@@ -832,6 +850,10 @@ __global__ void __launch_bounds__(XTHREADS, 1) tc_xt_kernel(const TcParams p) {
           S.advance(g);
           n++;
         }
+      }
+      if (p.progress != nullptr) {   // done: never hold the others back
+        reinterpret_cast<volatile int*>(p.progress)[(size_t)part * p.nqb + qb] = INT_MAX;
+        __threadfence();
       }
     }
     __syncwarp();
@@ -962,7 +984,16 @@ __global__ void __launch_bounds__(XTHREADS, 1) tc_xt_kernel(const TcParams p) {
 }
 
 template <int K>
-int launch_xt(cvb_ctx* ctx, const TcParams& p, cudaStream_t st) {
+int launch_xt(cvb_ctx* ctx, TcParams p, long total_tiles, cudaStream_t st) {
+  p.progress = nullptr;
+  // opt-in (COVINS_B200_TC_PACING=1): at C5 size the standalone request runs at full speed without it (1.77 ms, 5.6 Tpairs/s) and 6 %
+  // slower with it; it is kept for the case the CTAs of a keyframe range do drift out of each other's L2 window
+  const char* pace = getenv("COVINS_B200_TC_PACING");
+  if (p.nqb > 1 && total_tiles / p.parts > kPaceMinTiles && pace && atoi(pace)) {
+    p.progress = (int*)cvb_ws(ctx, WS_XT_PROGRESS, sizeof(int) * (size_t)p.nqb * p.parts);
+    if (!p.progress) return CVB_ERR_CUDA;
+    CVB_CUDA(ctx, cudaMemsetAsync(p.progress, 0, sizeof(int) * (size_t)p.nqb * p.parts, st));
+  }
   static bool attr = false;
   if (!attr) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(tc_xt_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
@@ -1057,11 +1088,12 @@ int launch(cvb_ctx* ctx, TcParams p, int metric, int k, cudaStream_t st) {
       p.xt = d_xt;
       p.seg_tile = d_tile;
     }
+    const long total_tiles = (long)tiles_of(p.h_seg, p.n_seg, nullptr);
     switch (k) {
-      case 1: return xt::launch_xt<1>(ctx, p, st);
-      case 2: return xt::launch_xt<2>(ctx, p, st);
-      case 3: return xt::launch_xt<3>(ctx, p, st);
-      default: return xt::launch_xt<4>(ctx, p, st);
+      case 1: return xt::launch_xt<1>(ctx, p, total_tiles, st);
+      case 2: return xt::launch_xt<2>(ctx, p, total_tiles, st);
+      case 3: return xt::launch_xt<3>(ctx, p, total_tiles, st);
+      default: return xt::launch_xt<4>(ctx, p, total_tiles, st);
     }
   }
 #define TC_CASE(MM, KK) return launch_tc<MM, KK>(ctx, p, st)

@@ -30,6 +30,7 @@ struct TcParams {
   const uint8_t* xt;
   const int32_t* seg_tile;
   const int32_t* h_seg;
+  int* progress;            // filled by launch(): per (part, query block) tile counter of the pacing scheme, or nullptr
   int dbg;   // development switches (COVINS_B200_TC_DEBUG): 1 = epilogue skips the selection, 2 = producers skip the expansion
 };
 

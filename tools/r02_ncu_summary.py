@@ -38,7 +38,6 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio"]
 sec = 2
 for rep, title in (("r02_prof_tc_xt", "`cvb_tc::xt::tc_xt_kernel<2>` (K1; C3 request: 1000 queries x 2000 KF x 1000 rows = 2 Gpairs per launch; `tools/tc_profile.py`)"),
-                   ("r02_prof_syrk", "`cvb_chol::syrk_kernel` (K8 trailing update, one bulk launch of the C3 factorisation; `tools/ba_one_iter.py`)"),
                    ("r02_prof_chain", "`cvb_chol::chain_gemm_kernel` (K8 critical chain: solve of the first panel tile / update of the next diagonal tile)")):
     f = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(f):
