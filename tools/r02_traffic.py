@@ -3,7 +3,7 @@ and writes profiles/r02_traffic.json, which bench.py reads for `roofline.traffic
 to a capture, not pasted).  Usage: python tools/r02_traffic.py"""
 import csv, io, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CAPS = {"syrk_kernel": ["gpurun_out/prof_syrk_final.ncu-rep"]   # a BULK launch (the round-2 capture r02_prof_syrk hit a 12 us chain-phase launch),
+CAPS = {"syrk_kernel": ["gpurun_out/prof_syrk_final.ncu-rep"],   # a BULK launch (the round-2 capture r02_prof_syrk hit a 12 us chain-phase launch)
         "tc_scan_kernel_hamming": ["gpurun_out/r02_prof_tc.ncu-rep", "gpurun_out/prof_tc_final.ncu-rep"],
         "tc_xt_kernel": ["gpurun_out/r02_prof_tc_xt.ncu-rep"]}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
