@@ -661,14 +661,13 @@ __global__ void wait_panel_kernel(const int* __restrict__ flag, const int* __res
 
 int factor(cvb_ctx* ctx, double* S, double* linv, int* d_flag, const TilePlan& plan, cudaStream_t st,
            const FactorStreams* fs, const DistView* dv) {
-  static bool attr = false;
-  if (!attr) {
+  static cvb_once_per_device once;
+  if (once.first(ctx->device)) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
     CVB_CUDA(ctx, cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSyrkSmem));
     CVB_CUDA(ctx, cudaFuncSetAttribute(potrf_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPotrfSmem));
     CVB_CUDA(ctx, cudaFuncSetAttribute(chain_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
     CVB_CUDA(ctx, cudaFuncSetAttribute(chain_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kChainSmem));
-    attr = true;
   }
   const int nt = plan.nt;
   const bool dist = dv != nullptr && dv->world > 1 && !plan.h_owner.empty();

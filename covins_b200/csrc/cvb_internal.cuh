@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -39,6 +40,17 @@ struct cvb_ctx {
 
 enum { WS_Q = 0, WS_T, WS_SEG, WS_OUT0, WS_OUT1, WS_OUT2, WS_PART_I, WS_PART_D, WS_LIST_I, WS_LIST_D, WS_SKIPA,
        WS_SKIPB, WS_TMP0, WS_TMP1, WS_FLAG, WS_MISC, WS_CHUNK_PS, WS_CHUNK_OFF, WS_GS0, WS_GS1, WS_GS2, WS_GS3, WS_GS4, WS_GS5, WS_XT, WS_XT_TILE, WS_XT_PROGRESS };
+
+// cudaFuncSetAttribute applies to the CURRENT device: one flag per (call site, device), so that a process that opens contexts
+// on several GPUs raises the dynamic shared-memory limit on each of them
+struct cvb_once_per_device {
+  std::atomic<bool> done[64];
+  cvb_once_per_device() { for (auto& d : done) d.store(false); }
+  bool first(int device) {
+    if (device < 0 || device >= 64) return true;
+    return !done[device].exchange(true);
+  }
+};
 
 int cvb_fail(cvb_ctx* ctx, int code, const char* fmt, ...);
 void* cvb_ws(cvb_ctx* ctx, int slot, size_t bytes);          // returns nullptr on failure (ctx->err set)

@@ -578,12 +578,11 @@ Plan make_plan(int nq, int n_seg, int max_len, int sm, int qpt_big, bool allow_s
 
 template <class M, int QPT, int K, int MODE>
 int launch_scan(cvb_ctx* ctx, const ScanParams& sp, const Plan& pl, cudaStream_t st) {
-  static bool attr_set = false;
+  static cvb_once_per_device once;
   const size_t smem = scan_smem_bytes<M>();
-  if (!attr_set) {
+  if (once.first(ctx->device)) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(scan_kernel<M, QPT, K, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    attr_set = true;
   }
   dim3 grid((unsigned)(sp.n_seg * pl.splits), (unsigned)pl.qblocks);
   scan_kernel<M, QPT, K, MODE><<<grid, kThreads, smem, st>>>(sp);

@@ -994,10 +994,9 @@ int launch_xt(cvb_ctx* ctx, TcParams p, long total_tiles, cudaStream_t st) {
     if (!p.progress) return CVB_ERR_CUDA;
     CVB_CUDA(ctx, cudaMemsetAsync(p.progress, 0, sizeof(int) * (size_t)p.nqb * p.parts, st));
   }
-  static bool attr = false;
-  if (!attr) {
+  static cvb_once_per_device once;
+  if (once.first(ctx->device)) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(tc_xt_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    attr = true;
   }
   tc_xt_kernel<K><<<p.nqb * p.parts, XTHREADS, kSmemBytes, st>>>(p);
   CVB_CHECK_LAUNCH(ctx);
@@ -1026,11 +1025,10 @@ int expand_tiles(cvb_ctx* ctx, const uint8_t* d_rows, const int32_t* d_seg_ptr, 
 
 template <class M, int K>
 int launch_tc(cvb_ctx* ctx, const TcParams& p, cudaStream_t st) {
-  static bool attr = false;
+  static cvb_once_per_device once;
   const size_t smem = smem_bytes<M, K>();
-  if (!attr) {
+  if (once.first(ctx->device)) {
     CVB_CUDA(ctx, cudaFuncSetAttribute(tc_scan_kernel<M, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   tc_scan_kernel<M, K><<<p.nqb * p.parts, NUM_THREADS, smem, st>>>(p);
   CVB_CHECK_LAUNCH(ctx);
