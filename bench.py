@@ -653,7 +653,7 @@ def run_ours(args):
         "e2e": {"value": done / dt_e2e, "unit": "iterations/s", "h2d_bytes_per_step": int(h2d_gba // max(done, 1)),
                 "d2h_bytes_per_step": int(d2h_gba // max(done, 1)), "steps": int(done),
                 "runs_s": [round(r[0], 4) for r in e2e_runs],
-                "note": "cvb_ba_create + iterate + result_get on host buffers: flatten/H2D/symbolic setup and the D2H read are inside; median of 3 complete calls"},
+                "note": "cvb_ba_create + iterate + result_get on host buffers: flatten/H2D/symbolic setup and the D2H read are inside; median of 3 complete calls after one warm-up call"},
         "gpu_launches": int(gba_launches),
         "clocks": clk.summary(),
         "phase_ms_per_step": {k: round(v / args.steps, 3) for k, v in tm.items() if k.endswith("_ms")},
