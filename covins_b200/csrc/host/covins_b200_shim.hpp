@@ -30,6 +30,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -864,6 +865,76 @@ inline std::vector<int> SearchBySE3(Context& ctx, const KFPtr& kf1, const std::v
     found[p] = nf[p];
   }
   return found;
+}
+
+// FeatureMatcher::SearchByProjection(pKF, Tcw, vpPoints, vpMatched, th) (feature_matcher_be.cpp:168-291): loop landmarks projected
+// into a keyframe.  The kernel returns, in list order, the decision the reference's sequential loop takes for every landmark
+// (cvb_search_by_projection); this wrapper flattens the containers and replays the decisions on them: a new match goes into
+// vpMatched, a better keypoint for an already observed landmark becomes pKF->RemapLandmark(pMP, existing, best).  Returns nmatches.
+// Members used beyond SearchBySE3's: KF::GetLandmark(i), KF::RemapLandmark; Landmark::GetNormal / GetMinDistanceInvariance /
+// GetMaxDistanceInvariance / GetMaxDistance.  Camera: Adapter<KF>::camera (+ camera_model for the non-pinhole/radtan types).
+template <class KFPtr, class LandmarkVector, class Transform4>
+inline int SearchByProjection(Context& ctx, const KFPtr& pKF, const Transform4& Tcw, const LandmarkVector& vpPoints, LandmarkVector& vpMatched,
+                              double th, int desc_matching_th_low, int num_octaves, double scale_factor) {
+  using KF = typename std::remove_reference<decltype(*pKF)>::type;
+  using LmPtr = typename std::remove_reference<decltype(vpPoints[0])>::type;
+  const size_t n = pKF->keypoints_distorted_.size(), m = vpPoints.size();
+  KfViewStorage S;
+  S.kp.resize(2 * n); S.octave.resize(n); S.desc.resize(32 * n); S.lm_valid.assign(n, 0); S.lm_pos.assign(3 * n, 0.0);
+  S.lm_maxdist.assign(n, 1.0); S.lm_desc.assign(32 * n, 0);
+  std::map<const void*, int> index_of;                     // landmark object → first position in vpPoints
+  for (size_t i = 0; i < m; i++)
+    if (vpPoints[i]) index_of.emplace((const void*)&*vpPoints[i], (int)i);
+  std::vector<int32_t> kf_lm_cand(n ? n : 1, -1);
+  std::vector<uint8_t> matched(n ? n : 1, 0);
+  std::set<const void*> already;                          // spAlreadyFound (:175-177)
+  for (size_t i = 0; i < n; i++) {
+    S.kp[2 * i] = pKF->keypoints_distorted_[i][0]; S.kp[2 * i + 1] = pKF->keypoints_distorted_[i][1];
+    S.octave[i] = pKF->keypoints_aors_[i][1];
+    std::copy(pKF->GetDescriptor(i), pKF->GetDescriptor(i) + 32, S.desc.begin() + 32 * i);
+    const auto lm = pKF->GetLandmark(i);
+    if (lm) {                                             // pKF->GetLandmark(bestIdx) != nullptr (:268); invalid ones count too
+      S.lm_valid[i] = 1;
+      const auto it = index_of.find((const void*)&*lm);
+      if (it != index_of.end()) kf_lm_cand[i] = it->second;
+    }
+    if (i < vpMatched.size() && vpMatched[i]) { matched[i] = 1; already.insert((const void*)&*vpMatched[i]); }
+  }
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) S.v.Tcw[4 * r + c] = Tcw(r, c);
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) S.v.K[3 * r + c] = pKF->calibration_K(r, c);
+  S.v.img[0] = pKF->img_dim_x_min_; S.v.img[1] = pKF->img_dim_x_max_; S.v.img[2] = pKF->img_dim_y_min_; S.v.img[3] = pKF->img_dim_y_max_;
+  S.assign_grid(pKF->image_width(), pKF->image_height());
+  std::vector<uint8_t> valid(m ? m : 1, 0), desc(32 * (m ? m : 1), 0);
+  std::vector<double> pos(3 * (m ? m : 1), 0.0), normal(3 * (m ? m : 1), 0.0), dmin(m ? m : 1, 0.0), dmax(m ? m : 1, 0.0), dist0(m ? m : 1, 1.0);
+  std::vector<int32_t> feat(m ? m : 1, -1);
+  for (size_t i = 0; i < m; i++) {
+    const LmPtr& lm = vpPoints[i];
+    if (!lm || lm->IsInvalid() || already.count((const void*)&*lm)) continue;                        // :184-187
+    valid[i] = 1;
+    const auto p = lm->GetWorldPos(), nn = lm->GetNormal();
+    for (int c = 0; c < 3; c++) { pos[3 * i + c] = p[c]; normal[3 * i + c] = nn[c]; }
+    dmin[i] = lm->GetMinDistanceInvariance(); dmax[i] = lm->GetMaxDistanceInvariance(); dist0[i] = lm->GetMaxDistance();
+    std::copy(lm->GetDescriptorPtr(), lm->GetDescriptorPtr() + 32, desc.begin() + 32 * i);
+    feat[i] = lm->GetFeatureIndex(pKF);
+  }
+  double intr[4], dist[4], xi = 0.0, tcw[16];
+  int cam_model = 0, dist_model = 0;
+  Adapter<KF>::camera(*pKF, intr, dist);
+  Adapter<KF>::camera_model(*pKF, &cam_model, &dist_model, &xi);
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) tcw[4 * r + c] = Tcw(r, c);
+  cvb_proj_landmarks L{(int32_t)m, valid.data(), pos.data(), normal.data(), dmin.data(), dmax.data(), dist0.data(), desc.data(), feat.data()};
+  cvb_search_params prm{th, desc_matching_th_low, num_octaves, scale_factor};
+  std::vector<int32_t> action(m ? m : 1, 0), best(m ? m : 1, -1);
+  int32_t nmatches = 0;
+  ctx.check(cvb_search_by_projection(ctx.get(), S.view(), kf_lm_cand.data(), tcw, intr, dist, cam_model, dist_model, xi, &L, matched.data(), &prm,
+                                     action.data(), best.data(), &nmatches),
+            "cvb_search_by_projection");
+  if (vpMatched.size() < n) vpMatched.resize(n);
+  for (size_t i = 0; i < m; i++) {                                                                    // the decisions, in list order
+    if (action[i] == 1) vpMatched[best[i]] = vpPoints[i];                                              // :285
+    else if (action[i] == 2) pKF->RemapLandmark(vpPoints[i], (size_t)vpPoints[i]->GetFeatureIndex(pKF), (size_t)best[i]);   // :281
+  }
+  return nmatches;
 }
 
 // RANSAC hypothesis scoring (the countWithinDistance / selectWithinDistance inner loops of opengv::sac::Ransac for

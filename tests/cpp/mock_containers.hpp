@@ -35,7 +35,7 @@ struct Keyframe;
 using KeyframePtr = std::shared_ptr<Keyframe>;
 using LandmarkPtr = std::shared_ptr<Landmark>;
 
-struct Keyframe {
+struct Keyframe : std::enable_shared_from_this<Keyframe> {
   idpair id_;
   bool invalid = false, is_loaded_ = false, is_gba_optimized_ = false;
   Transform T_w_s_ = Transform::Identity(), T_w_s_vio_ = Transform::Identity(), T_s_c_ = Transform::Identity();
@@ -55,6 +55,8 @@ struct Keyframe {
   double img_dim_x_min_ = 0, img_dim_x_max_ = 752, img_dim_y_min_ = 0, img_dim_y_max_ = 480;
   const unsigned char* GetDescriptor(size_t i) const { return descriptors_[i].data(); }   // keyframe_base.cpp:254-256
   std::vector<LandmarkPtr> GetLandmarks() const { return landmarks_; }
+  LandmarkPtr GetLandmark(size_t i) const { return landmarks_[i]; }
+  void RemapLandmark(LandmarkPtr lm, size_t feat_id_now, size_t feat_id_new);       // keyframe_be.cpp:484-495, defined below Landmark
   Transform GetPoseTcw() const { return T_c_w_; }
   double calibration_K(int r, int c) const { return K_[3 * r + c]; }                       // calibration_.K(r, c)
   double image_width() const { return 752.0; }                                              // camera_->imageWidth()
@@ -96,10 +98,14 @@ struct Landmark {
   std::map<KeyframePtr, size_t> observations_;   // pointer-ordered like the reference (typedefs_base.hpp:187)
   KeyframePtr ref_kf;
   int n_optimized = 0;
-  double max_distance_ = 1.0;
+  double max_distance_ = 1.0, min_distance_ = 0.0;
+  Vector3 normal_{0, 0, 0};
   std::array<unsigned char, 32> descriptor_{};
   double GetMaxDistanceInvariance() const { return 1.2 * max_distance_; }                    // landmark_base.cpp:68-71
   double GetMaxDistance() const { return max_distance_; }                                   // the added getter (PredictScale's operand)
+  double GetMinDistanceInvariance() const { return 0.8 * min_distance_; }                    // landmark_base.cpp:73-76
+  Vector3 GetNormal() const { return normal_; }
+  void AddObservation(const KeyframePtr& kf, size_t idx) { observations_[kf] = idx; }      // (the plain map insert of LandmarkBase::AddObservation)
   const unsigned char* GetDescriptorPtr() const { return descriptor_.data(); }              // Landmark::GetDescriptor().data
   int GetFeatureIndex(const KeyframePtr& kf) const {
     auto it = observations_.find(kf);
@@ -113,6 +119,15 @@ struct Landmark {
   void EraseObservation(const KeyframePtr& kf) { observations_.erase(kf); }
   KeyframePtr GetReferenceKeyframe() const { return ref_kf; }
 };
+
+inline void Keyframe::RemapLandmark(LandmarkPtr lm, size_t feat_id_now, size_t feat_id_new) {   // statement order of the reference
+  auto lm_new = landmarks_[feat_id_new];
+  landmarks_[feat_id_now] = nullptr;
+  landmarks_[feat_id_new] = lm;
+  lm->EraseObservation(shared_from_this());
+  lm->AddObservation(shared_from_this(), feat_id_new);
+  if (lm_new) lm_new->EraseObservation(shared_from_this());
+}
 
 struct LoopConstraint {   // typedefs_base.hpp:264-277
   KeyframePtr kf1, kf2;
